@@ -1,0 +1,123 @@
+/*
+ * vqb200.h -- C ABI of the B200-native VQ-VAE-2 quantizer hot path.
+ *
+ * This is the drop-in boundary for ONE path of alehdaghi/vq-vae-2-pytorch: the `Quantize`
+ * module (reference vqvae.py:28-78).  The reference has no FFI of its own (it is pure PyTorch),
+ * so every entry point below names the reference expression(s) it replaces; the Python class
+ * `vq_vae_2_pytorch_b200.Quantize` binds them with ctypes and keeps the reference's module
+ * surface (INTEGRATION.md shows the binding a reference maintainer would add).
+ *
+ * Conventions
+ *   - plain C types only: raw pointers, sizes, strides, a `void* stream` (cudaStream_t);
+ *   - every pointer named d_* is DEVICE memory on the current device, h_* is HOST memory;
+ *   - no allocation inside the device entry points: the caller passes workspaces whose sizes
+ *     come from the vqb200_*_bytes() queries; all work is enqueued on `stream`, nothing syncs;
+ *   - return value: 0 on success, a negative VQB200_E* code otherwise (vqb200_error_string()).
+ *   - arithmetic type: fp32 in / fp32 out, int64 indices (the reference's dtypes).
+ *
+ * Row layout ("vq_layout"): the module receives a [..., D] tensor whose leading dims flatten to
+ * N rows (vqvae.py:43).  Two physical layouts are accepted without a copy:
+ *     element (n, d) lives at   (n / rows_per_image) * image_stride
+ *                             + (n % rows_per_image) * row_stride + d * col_stride
+ *   contiguous [N, D]:            rows_per_image = N,   image_stride = 0, row_stride = D, col_stride = 1
+ *   permute(0,2,3,1) of NCHW      rows_per_image = H*W, image_stride = D*H*W, row_stride = 1,
+ *   (what VQVAE.encode passes,                          col_stride = H*W
+ *    vqvae.py:227,235):
+ * `quantize` is written with the same layout as the input (vqvae.py:73 keeps the input's strides).
+ */
+#ifndef VQB200_H_
+#define VQB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VQB200_ABI_VERSION 1
+
+#define VQB200_OK             0
+#define VQB200_EINVAL        -1   /* bad argument (null pointer, non-positive size, ...)            */
+#define VQB200_EUNSUPPORTED  -2   /* shape / layout outside what the kernels cover                  */
+#define VQB200_ECUDA         -3   /* a CUDA call failed; see vqb200_last_cuda_error()               */
+#define VQB200_ENODEVICE     -4   /* no sm_100 device                                               */
+
+/* assignment engines for vqb200_quantize_forward / vqb200_assign */
+#define VQB200_ENGINE_AUTO    0   /* tcgen05 path when the shape is covered, else exact SIMT        */
+#define VQB200_ENGINE_SIMT    1   /* exact fp32 SIMT distance kernel                                */
+#define VQB200_ENGINE_TCGEN05 2   /* TMA + tcgen05 split-bf16 filter with exact fp32 re-score       */
+
+int         vqb200_abi_version(void);
+const char* vqb200_error_string(int code);
+int         vqb200_last_cuda_error(void);      /* cudaError_t of the last failing CUDA call, 0 if none */
+uint64_t    vqb200_launch_count(void);         /* kernels launched by this library so far (process-wide) */
+
+/* ---- workspace sizes (bytes) ------------------------------------------------------------------ */
+/* prepared codebook image: code-major fp32 copy, ||e_k||^2, tensor-core operand images            */
+size_t vqb200_codebook_bytes(int32_t dim, int32_t n_embed);
+/* per-call scratch of the forward (diff accumulator, flagged-row list, counters)                   */
+size_t vqb200_forward_scratch_bytes(int64_t n_rows, int32_t dim, int32_t n_embed);
+/* packed codebook statistics: n_embed*dim per-code sums (code-major), then n_embed counts, then 4
+ * spare floats the EMA kernels use as scalars; only the first n_embed*(dim+1) floats are all-reduced */
+size_t vqb200_stats_bytes(int32_t dim, int32_t n_embed);
+
+/* ---- codebook ---------------------------------------------------------------------------------- */
+/* Re-derive the prepared image from `embed` [dim, n_embed] (the module buffer, vqvae.py:37-38).
+ * Must be called after any external write to `embed` (load_state_dict, .to(), DDP broadcast).     */
+int vqb200_codebook_prepare(const float* d_embed, int32_t dim, int32_t n_embed,
+                            void* d_codebook, void* stream);
+
+/* ---- forward ----------------------------------------------------------------------------------- */
+/* vqvae.py:43-52,72-73 (+ the statistics of :50,55-56 when d_stats != NULL), one pass over x:
+ *   embed_ind[n] = argmin_k ||x_n - e_k||^2 (lowest k on ties)              -> d_embed_ind (int64 [N])
+ *   quantize     = x + (e[embed_ind] - x)                                   -> d_quantize (layout of x)
+ *   diff         = mean((e[embed_ind] - x)^2)                               -> d_diff (1 float)
+ *   stats        = [sum of rows per code | rows per code], zeroed here      -> d_stats (training only)
+ * d_quantize may be NULL (index extraction only, extract_code.py:23), d_diff may be NULL.          */
+int vqb200_quantize_forward(const float* d_x, int64_t n_rows, int32_t dim, int32_t n_embed,
+                            int64_t rows_per_image, int64_t image_stride,
+                            int64_t row_stride, int64_t col_stride,
+                            const void* d_codebook,
+                            float* d_quantize, int64_t* d_embed_ind, float* d_diff,
+                            float* d_stats, void* d_scratch, int32_t engine, void* stream);
+
+/* vqvae.py:61-70 after the (optional) all-reduce of vqvae.py:58-59: EMA of cluster_size / embed_avg,
+ * Laplace-smoothed renormalisation, in-place write of `embed`, and refresh of the prepared codebook
+ * image for the next forward.  `one_minus_decay` is passed separately because the reference evaluates
+ * `1 - decay` in double precision (vqvae.py:62).  d_codebook may be NULL (no image refresh).         */
+int vqb200_ema_update(const float* d_stats, float* d_cluster_size, float* d_embed_avg, float* d_embed,
+                      int32_t dim, int32_t n_embed, float decay, float one_minus_decay, float eps,
+                      void* d_codebook, void* stream);
+
+/* Gradient implied by vqvae.py:72-73:  grad_x = grad_quantize + grad_diff * 2 (x - e[ind]) / (N*D).
+ * d_grad_quantize (same layout as x) and d_grad_diff (1 float) may each be NULL (= zero).           */
+int vqb200_quantize_backward(const float* d_x, const int64_t* d_embed_ind, const void* d_codebook,
+                             const float* d_grad_quantize, const float* d_grad_diff, float* d_grad_x,
+                             int64_t n_rows, int32_t dim, int32_t n_embed,
+                             int64_t rows_per_image, int64_t image_stride,
+                             int64_t row_stride, int64_t col_stride, void* stream);
+
+/* vqvae.py:77-78 `embed_code`: out[n, :] = e[:, embed_id[n]]  (contiguous [N, dim] output).
+ * Returns VQB200_EINVAL semantics on the device side: out-of-range ids are reported through
+ * d_status (1 int32, set non-zero) like F.embedding's index check; d_status may be NULL.           */
+int vqb200_embed_code(const int64_t* d_embed_id, int64_t n_rows, const void* d_codebook,
+                      int32_t dim, int32_t n_embed, float* d_out, int32_t* d_status, void* stream);
+
+/* ---- host-buffer convenience path (what bench.py's `e2e` times) -------------------------------- */
+/* Same contract as vqb200_quantize_forward (+ optional EMA update when `training`), but x / quantize /
+ * embed_ind / diff are HOST buffers (pinned for full speed); H2D and D2H copies are pipelined in row
+ * chunks across internal streams.  The context owns device staging memory sized for max_rows.       */
+typedef struct vqb200_host_ctx vqb200_host_ctx;
+int  vqb200_host_ctx_create(int64_t max_rows, int32_t dim, int32_t n_embed, vqb200_host_ctx** out);
+void vqb200_host_ctx_destroy(vqb200_host_ctx* ctx);
+/* device-resident module buffers (embed / cluster_size / embed_avg) stay on the device */
+int  vqb200_host_quantize(vqb200_host_ctx* ctx, const float* h_x, int64_t n_rows,
+                          float* d_embed, float* d_cluster_size, float* d_embed_avg,
+                          float decay, float one_minus_decay, float eps, int32_t training,
+                          float* h_quantize, int64_t* h_embed_ind, float* h_diff, int32_t engine);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VQB200_H_ */

@@ -1,0 +1,87 @@
+// Shared device/host helpers for the vqb200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vqb200 {
+
+// Physical placement of the N logical rows of a [..., D] tensor (see include/vqb200.h "vq_layout").
+struct RowLayout {
+    int64_t n_rows;
+    int64_t rows_per_image;
+    int64_t image_stride;
+    int64_t row_stride;
+    int64_t col_stride;
+};
+
+__host__ __device__ __forceinline__ int64_t row_offset(const RowLayout& L, int64_t n) {
+    int64_t img = n / L.rows_per_image;
+    int64_t r = n - img * L.rows_per_image;
+    return img * L.image_stride + r * L.row_stride;
+}
+
+// Prepared codebook image (what vqb200_codebook_prepare / vqb200_ema_update maintain).
+//   cbT   [K][D]   fp32, code-major: row k is code e_k (coalesced gather, exact re-score operand)
+//   ee    [K]      fp32 ||e_k||^2, summed in a fixed order
+//   tc    tensor-core operand image + per-code norms for the error bound (see tc_kernel.cuh)
+struct CodebookImage {
+    float* cbT;
+    float* ee;
+    float* enorm_max;   // 1 float: max_k ||e_k|| over "near" codes (tcgen05 bound), [1]=far threshold
+    unsigned char* tc;  // bf16 operand image, 1024-byte aligned
+};
+
+__host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// tensor-core image geometry: shared by host sizing code and the kernels
+__host__ __device__ inline int tc_dim_padded(int dim) { return (dim + 63) / 64 * 64; }          // K-major rows of 64 bf16 = 128 B
+__host__ __device__ inline int tc_codes_padded(int n_embed) { return (n_embed + 255) / 256 * 256; }
+// number of 64-wide bf16 k-blocks: 3 split terms per 64 input dims + 1 bias/offset block
+__host__ __device__ inline int tc_kblocks(int dim) { return 3 * (tc_dim_padded(dim) / 64) + 1; }
+__host__ __device__ inline size_t tc_image_bytes(int dim, int n_embed) {
+    return (size_t)tc_kblocks(dim) * tc_codes_padded(n_embed) * 128;
+}
+
+__host__ __device__ inline size_t codebook_bytes(int dim, int n_embed) {
+    size_t b = align_up((size_t)n_embed * dim * 4, 1024);
+    b += align_up((size_t)n_embed * 4, 1024);
+    b += 1024;                                   // scalars
+    b += align_up(tc_image_bytes(dim, n_embed), 1024);
+    return b;
+}
+
+__host__ __device__ inline CodebookImage codebook_view(void* base, int dim, int n_embed) {
+    unsigned char* p = (unsigned char*)base;
+    CodebookImage v;
+    v.cbT = (float*)p;            p += align_up((size_t)n_embed * dim * 4, 1024);
+    v.ee = (float*)p;             p += align_up((size_t)n_embed * 4, 1024);
+    v.enorm_max = (float*)p;      p += 1024;
+    v.tc = p;
+    return v;
+}
+
+// per-call scratch of the forward
+struct ForwardScratch {
+    double* diff_acc;      // 1 double: sum (q-x)^2
+    int* flagged_count;    // 1 int: rows sent to the exact re-score
+    int* flagged_rows;     // [n_rows] row ids
+};
+__host__ __device__ inline size_t forward_scratch_bytes(int64_t n_rows) {
+    return 256 + align_up((size_t)n_rows * 4, 256);
+}
+__host__ __device__ inline ForwardScratch scratch_view(void* base) {
+    unsigned char* p = (unsigned char*)base;
+    ForwardScratch s;
+    s.diff_acc = (double*)p;
+    s.flagged_count = (int*)(p + 16);
+    s.flagged_rows = (int*)(p + 256);
+    return s;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace vqb200

@@ -1,0 +1,307 @@
+// Exact fp32 SIMT kernels of the quantizer path.
+//
+// These pin the semantics (Appendix A of SURVEY.md, reference vqvae.py:42-78) and stay in the product
+// as (a) the exact re-score / fallback engine of the tcgen05 path and (b) the engine for shapes the
+// tensor-core kernel does not cover.  Streaming kernels are laid out for coalesced 128-byte accesses
+// in both accepted row layouts (contiguous rows, or NCHW-physical rows with unit row stride).
+#pragma once
+#include "common.cuh"
+
+namespace vqb200 {
+
+// ------------------------------------------------------------------------------------------------
+// codebook image: transpose embed [D,K] -> cbT [K,D] and ||e_k||^2
+// ------------------------------------------------------------------------------------------------
+__global__ void k_codebook_transpose(const float* __restrict__ embed, float* __restrict__ cbT, int D, int K) {
+    __shared__ float tile[32][33];
+    int k0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        int d = d0 + j, k = k0 + threadIdx.x;
+        tile[j][threadIdx.x] = (d < D && k < K) ? embed[(size_t)d * K + k] : 0.f;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        int k = k0 + j, d = d0 + threadIdx.x;
+        if (k < K && d < D) cbT[(size_t)k * D + d] = tile[threadIdx.x][j];
+    }
+}
+
+// one warp per code; fixed summation order (lane-strided partials, xor tree)
+__global__ void k_codebook_norms(const float* __restrict__ cbT, float* __restrict__ ee, int D, int K) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= K) return;
+    const float* e = cbT + (size_t)warp * D;
+    float s = 0.f;
+    for (int d = lane; d < D; d += 32) s = fmaf(e[d], e[d], s);
+    s = warp_sum(s);
+    if (lane == 0) ee[warp] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// exact distance + argmin (vqvae.py:44-49): register-tiled fp32 FMA, 64 rows x 64 codes per step
+// ------------------------------------------------------------------------------------------------
+constexpr int AS_BM = 64, AS_BN = 64, AS_DC = 32, AS_THREADS = 256;
+
+// rows come either from [0, n_rows) or, when row_list != nullptr, from row_list[0 .. *row_count)
+__global__ void __launch_bounds__(AS_THREADS)
+k_assign_exact(const float* __restrict__ x, RowLayout L, int D, int K,
+               const float* __restrict__ cbT, const float* __restrict__ ee,
+               int64_t* __restrict__ embed_ind,
+               const int* __restrict__ row_list, const int* __restrict__ row_count) {
+    __shared__ float xs[AS_DC][AS_BM + 4];
+    __shared__ float es[AS_DC][AS_BN + 4];
+    __shared__ int64_t row_off[AS_BM];
+    __shared__ int row_id[AS_BM];
+
+    const int64_t total = row_list ? (int64_t)(*row_count) : L.n_rows;
+    const int64_t n0 = (int64_t)blockIdx.x * AS_BM;
+    if (n0 >= total) return;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+
+    if (tid < AS_BM) {
+        int64_t i = n0 + tid;
+        int64_t n = -1;
+        if (i < total) n = row_list ? (int64_t)row_list[i] : i;
+        row_id[tid] = (int)n;
+        row_off[tid] = n >= 0 ? row_offset(L, n) : 0;
+    }
+    __syncthreads();
+
+    float best[4];
+    int best_k[4];
+    float xx[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { best[i] = INFINITY; best_k[i] = 0; }
+
+    for (int c0 = 0; c0 < K; c0 += AS_BN) {
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+        for (int d0 = 0; d0 < D; d0 += AS_DC) {
+            // x tile: pick the thread->element map that coalesces for this layout
+            for (int i = tid; i < AS_BM * AS_DC; i += AS_THREADS) {
+                int r, dd;
+                if (L.col_stride == 1) { r = i / AS_DC; dd = i % AS_DC; } else { dd = i / AS_BM; r = i % AS_BM; }
+                int d = d0 + dd;
+                float v = 0.f;
+                if (row_id[r] >= 0 && d < D) v = x[row_off[r] + (int64_t)d * L.col_stride];
+                xs[dd][r] = v;
+            }
+            for (int i = tid; i < AS_BN * AS_DC; i += AS_THREADS) {
+                int c = i / AS_DC, dd = i % AS_DC;
+                int k = c0 + c, d = d0 + dd;
+                es[dd][c] = (k < K && d < D) ? cbT[(size_t)k * D + d] : 0.f;
+            }
+            __syncthreads();
+#pragma unroll 8
+            for (int dd = 0; dd < AS_DC; ++dd) {
+                float4 xv = *reinterpret_cast<const float4*>(&xs[dd][ty * 4]);
+                float4 ev = *reinterpret_cast<const float4*>(&es[dd][tx * 4]);
+                float xr[4] = {xv.x, xv.y, xv.z, xv.w};
+                float er[4] = {ev.x, ev.y, ev.z, ev.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (c0 == 0) xx[i] = fmaf(xr[i], xr[i], xx[i]);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xr[i], er[j], acc[i][j]);
+                }
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int k = c0 + tx * 4 + j;
+            if (k < K) {
+                float e2 = ee[k];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float dist = (xx[i] - 2.f * acc[i][j]) + e2;   // vqvae.py:44-48, left to right
+                    if (dist < best[i]) { best[i] = dist; best_k[i] = k; }
+                }
+            }
+        }
+    }
+    // lexicographic (dist, k) min across the 16 code-lanes that share a row group
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float b = best[i];
+        int bk = best_k[i];
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+            float ob = __shfl_xor_sync(0xffffffffu, b, o);
+            int obk = __shfl_xor_sync(0xffffffffu, bk, o);
+            if (ob < b || (ob == b && obk < bk)) { b = ob; bk = obk; }
+        }
+        int r = ty * 4 + i;
+        if (tx == 0 && row_id[r] >= 0) embed_ind[row_id[r]] = (int64_t)bk;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// gather + straight-through output + commitment loss + code statistics, one pass over x
+// (vqvae.py:52, 72-73 and the statistics of :50,55-56 without a one-hot)
+// ------------------------------------------------------------------------------------------------
+constexpr int GS_BM = 32, GS_THREADS = 256;
+
+__global__ void __launch_bounds__(GS_THREADS)
+k_gather_stats(const float* __restrict__ x, RowLayout L, int D, int K,
+               const float* __restrict__ cbT, const int64_t* __restrict__ embed_ind,
+               float* __restrict__ quantize, double* __restrict__ diff_acc,
+               float* __restrict__ stat_sums, float* __restrict__ stat_counts) {
+    extern __shared__ float tile[];              // [GS_BM][D + 1]
+    __shared__ int64_t row_off[GS_BM];
+    __shared__ int code[GS_BM];
+    __shared__ float warp_part[GS_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ld = D + 1;
+    const int64_t n0 = (int64_t)blockIdx.x * GS_BM;
+    const int rows = (int)min((int64_t)GS_BM, L.n_rows - n0);
+
+    if (tid < GS_BM) {
+        bool ok = tid < rows;
+        row_off[tid] = ok ? row_offset(L, n0 + tid) : 0;
+        int64_t k = ok ? embed_ind[n0 + tid] : 0;
+        code[tid] = (int)k;
+    }
+    __syncthreads();
+    for (int i = tid; i < GS_BM * D; i += GS_THREADS) {
+        int r, d;
+        if (L.col_stride == 1) { r = i / D; d = i % D; } else { d = i / GS_BM; r = i % GS_BM; }
+        if (r < rows) tile[r * ld + d] = x[row_off[r] + (int64_t)d * L.col_stride];
+    }
+    __syncthreads();
+    float acc = 0.f;
+    for (int r = warp; r < rows; r += GS_THREADS / 32) {
+        const int k = code[r];
+        const float* e = cbT + (size_t)k * D;
+        for (int d = lane; d < D; d += 32) {
+            float xv = tile[r * ld + d];
+            float dl = e[d] - xv;                 // (quantize - input), vqvae.py:72-73
+            acc = fmaf(dl, dl, acc);
+            tile[r * ld + d] = xv + dl;           // input + (quantize - input).detach()
+            if (stat_sums) atomicAdd(&stat_sums[(size_t)k * D + d], xv);
+        }
+        if (stat_counts && lane == 0) atomicAdd(&stat_counts[k], 1.0f);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) warp_part[warp] = acc;
+    __syncthreads();
+    if (quantize) {
+        for (int i = tid; i < GS_BM * D; i += GS_THREADS) {
+            int r, d;
+            if (L.col_stride == 1) { r = i / D; d = i % D; } else { d = i / GS_BM; r = i % GS_BM; }
+            if (r < rows) quantize[row_off[r] + (int64_t)d * L.col_stride] = tile[r * ld + d];
+        }
+    }
+    if (tid == 0 && diff_acc) {
+        float s = 0.f;
+        for (int w = 0; w < GS_THREADS / 32; ++w) s += warp_part[w];
+        atomicAdd(diff_acc, (double)s);
+    }
+}
+
+__global__ void k_finalize_diff(const double* __restrict__ diff_acc, float* __restrict__ diff, double inv_count) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) diff[0] = (float)(diff_acc[0] * inv_count);
+}
+
+// ------------------------------------------------------------------------------------------------
+// EMA update + Laplace-smoothed renormalisation (vqvae.py:61-70), also refreshes cbT / ee
+// ------------------------------------------------------------------------------------------------
+// single block: cluster_size <- cluster_size*decay + counts*(1-decay);  n = sum(cluster_size)
+__global__ void k_ema_cluster(const float* __restrict__ counts, float* __restrict__ cluster_size, int K,
+                              float decay, float one_minus_decay, float* __restrict__ n_out) {
+    __shared__ float part[32];
+    float s = 0.f;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        float c = cluster_size[k] * decay;
+        c = c + counts[k] * one_minus_decay;
+        cluster_size[k] = c;
+        s += c;
+    }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.f;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) n_out[0] = v;
+    }
+}
+
+// one warp per code: embed_avg / embed columns, code-major copy and norm
+__global__ void k_ema_embed(const float* __restrict__ sums, const float* __restrict__ cluster_size,
+                            const float* __restrict__ n_in, float* __restrict__ embed_avg,
+                            float* __restrict__ embed, float* __restrict__ cbT, float* __restrict__ ee,
+                            int D, int K, float decay, float one_minus_decay, float eps) {
+    int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (k >= K) return;
+    const float n = n_in[0];
+    const float denom = n + (float)((double)K * (double)eps);
+    const float cs = (cluster_size[k] + eps) / denom * n;      // vqvae.py:66-68
+    float s2 = 0.f;
+    for (int d = lane; d < D; d += 32) {
+        size_t o = (size_t)d * K + k;
+        float a = embed_avg[o] * decay;
+        a = a + sums[(size_t)k * D + d] * one_minus_decay;     // vqvae.py:64
+        embed_avg[o] = a;
+        float e = a / cs;                                      // vqvae.py:69-70
+        embed[o] = e;
+        if (cbT) cbT[(size_t)k * D + d] = e;
+        s2 = fmaf(e, e, s2);
+    }
+    s2 = warp_sum(s2);
+    if (lane == 0 && ee) ee[k] = s2;
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward implied by vqvae.py:72-73
+// ------------------------------------------------------------------------------------------------
+__global__ void k_backward(const float* __restrict__ x, RowLayout L, int D,
+                           const int64_t* __restrict__ embed_ind, const float* __restrict__ cbT,
+                           const float* __restrict__ grad_q, const float* __restrict__ grad_diff,
+                           float* __restrict__ grad_x, double two_over_count) {
+    const int64_t total = L.n_rows * (int64_t)D;
+    const float c = grad_diff ? (float)(two_over_count * (double)grad_diff[0]) : 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t n;
+        int d;
+        if (L.col_stride == 1) { n = i / D; d = (int)(i - n * D); }
+        else {  // walk the physical NCHW order: (image, d, row-in-image)
+            int64_t per_img = L.rows_per_image * D;
+            int64_t img = i / per_img, rem = i - img * per_img;
+            d = (int)(rem / L.rows_per_image);
+            n = img * L.rows_per_image + (rem - (int64_t)d * L.rows_per_image);
+        }
+        int64_t off = row_offset(L, n) + (int64_t)d * L.col_stride;
+        float g = grad_q ? grad_q[off] : 0.f;
+        if (c != 0.f) {
+            float q = cbT[(size_t)embed_ind[n] * D + d];
+            g = fmaf(c, x[off] - q, g);
+        }
+        grad_x[off] = g;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// embed_code (vqvae.py:77-78): contiguous [N, D] gather
+// ------------------------------------------------------------------------------------------------
+__global__ void k_embed_code(const int64_t* __restrict__ ids, int64_t n_rows, const float* __restrict__ cbT,
+                             int D, int K, float* __restrict__ out, int* __restrict__ status) {
+    int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (row >= n_rows) return;
+    int64_t k = ids[row];
+    if (k < 0 || k >= K) {
+        if (lane == 0 && status) atomicExch(status, 1);
+        return;
+    }
+    const float* e = cbT + (size_t)k * D;
+    float* o = out + row * D;
+    for (int d = lane; d < D; d += 32) o[d] = e[d];
+}
+
+}  // namespace vqb200

@@ -1,0 +1,334 @@
+// C ABI of the B200-native VQ-VAE-2 quantizer path (see include/vqb200.h for the contract).
+// One translation unit: nvcc -gencode arch=compute_100a,code=sm_100a -shared -> libvqb200.so
+#include "../../include/vqb200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <new>
+
+#include "common.cuh"
+#include "simt_kernels.cuh"
+#include "tc_kernel.cuh"
+
+using namespace vqb200;
+
+namespace {
+
+thread_local int g_last_cuda_error = 0;
+std::atomic<unsigned long long> g_launches{0};   // kernels this library launched (bench.py's gpu_launches)
+
+inline int cuda_fail(cudaError_t e) {
+    g_last_cuda_error = (int)e;
+    return VQB200_ECUDA;
+}
+#define VQ_CUDA(call)                                     \
+    do {                                                  \
+        cudaError_t e__ = (call);                         \
+        if (e__ != cudaSuccess) return cuda_fail(e__);    \
+    } while (0)
+#define VQ_LAUNCH_CHECK()              \
+    do {                               \
+        g_launches.fetch_add(1);       \
+        VQ_CUDA(cudaGetLastError());   \
+    } while (0)
+
+bool layout_ok(int64_t n_rows, int32_t dim, int64_t rpi, int64_t img_stride, int64_t row_stride,
+               int64_t col_stride) {
+    if (n_rows < 0 || dim <= 0 || rpi <= 0 || row_stride <= 0 || col_stride <= 0) return false;
+    if (n_rows > rpi && img_stride <= 0) return false;
+    // the two layouts the streaming kernels coalesce for
+    return col_stride == 1 || row_stride == 1;
+}
+
+int prepare_codebook(const float* d_embed, int dim, int n_embed, void* d_codebook, cudaStream_t st) {
+    CodebookImage cb = codebook_view(d_codebook, dim, n_embed);
+    dim3 grid((n_embed + 31) / 32, (dim + 31) / 32), block(32, 8);
+    k_codebook_transpose<<<grid, block, 0, st>>>(d_embed, cb.cbT, dim, n_embed);
+    VQ_LAUNCH_CHECK();
+    int warps_per_block = 8;
+    k_codebook_norms<<<(n_embed + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(
+        cb.cbT, cb.ee, dim, n_embed);
+    VQ_LAUNCH_CHECK();
+    return tc_prepare_codebook(cb, dim, n_embed, st) ? cuda_fail(cudaGetLastError()) : VQB200_OK;
+}
+
+// The forward, split so the host-buffer path can stream row chunks through it:
+//   zero_first : clear statistics / diff accumulator before accumulating
+//   finalize   : write diff = acc / (total_rows * dim)
+int forward_impl(const float* d_x, const RowLayout& L, int dim, int n_embed, const void* d_codebook,
+                 float* d_quantize, int64_t* d_ind, float* d_diff, float* d_stats, void* d_scratch,
+                 int engine, bool zero_first, bool finalize, int64_t total_rows, cudaStream_t st) {
+    CodebookImage cb = codebook_view(const_cast<void*>(d_codebook), dim, n_embed);
+    ForwardScratch sc = scratch_view(d_scratch);
+    float* sums = d_stats;
+    float* counts = d_stats ? d_stats + (size_t)n_embed * dim : nullptr;
+    if (zero_first) {
+        VQ_CUDA(cudaMemsetAsync(sc.diff_acc, 0, 256, st));
+        if (d_stats) VQ_CUDA(cudaMemsetAsync(d_stats, 0, vqb200_stats_bytes(dim, n_embed), st));
+    }
+    if (L.n_rows > 0) {
+        bool use_tc = false;
+        if (engine == VQB200_ENGINE_TCGEN05 || engine == VQB200_ENGINE_AUTO)
+            use_tc = tc_supported(L, dim, n_embed);
+        if (engine == VQB200_ENGINE_TCGEN05 && !use_tc) return VQB200_EUNSUPPORTED;
+        if (use_tc) {
+            int rc = tc_forward(d_x, L, dim, n_embed, cb, d_quantize, d_ind, sc, sums, counts, st);
+            if (rc) return cuda_fail(cudaGetLastError());
+        } else {
+            int64_t blocks = (L.n_rows + AS_BM - 1) / AS_BM;
+            k_assign_exact<<<(unsigned)blocks, AS_THREADS, 0, st>>>(d_x, L, dim, n_embed, cb.cbT, cb.ee, d_ind,
+                                                                      nullptr, nullptr);
+            VQ_LAUNCH_CHECK();
+            if (d_quantize || d_diff || d_stats) {
+                size_t smem = (size_t)GS_BM * (dim + 1) * sizeof(float);
+                if (smem > 200 * 1024) return VQB200_EUNSUPPORTED;
+                if (smem > 48 * 1024)
+                    VQ_CUDA(cudaFuncSetAttribute(k_gather_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                int64_t gblocks = (L.n_rows + GS_BM - 1) / GS_BM;
+                k_gather_stats<<<(unsigned)gblocks, GS_THREADS, smem, st>>>(
+                    d_x, L, dim, n_embed, cb.cbT, d_ind, d_quantize, d_diff ? sc.diff_acc : nullptr, sums, counts);
+                VQ_LAUNCH_CHECK();
+            }
+        }
+    }
+    if (finalize && d_diff) {
+        double inv = total_rows > 0 ? 1.0 / ((double)total_rows * (double)dim) : 0.0;
+        // mean over zero elements is NaN in the reference (0/0); keep that
+        if (total_rows == 0) inv = std::numeric_limits<double>::quiet_NaN();
+        k_finalize_diff<<<1, 32, 0, st>>>(sc.diff_acc, d_diff, inv);
+        VQ_LAUNCH_CHECK();
+    }
+    return VQB200_OK;
+}
+
+int ema_impl(const float* d_stats, float* d_cluster_size, float* d_embed_avg, float* d_embed, int dim,
+             int n_embed, float decay, float one_minus_decay, float eps, void* d_codebook, cudaStream_t st) {
+    // d_stats = [sums K*D | counts K | 1 spare float used for n = sum(cluster_size)] -- see vqb200_stats_bytes
+    const float* sums = d_stats;
+    const float* counts = d_stats + (size_t)n_embed * dim;
+    float* n_scratch = const_cast<float*>(d_stats) + (size_t)n_embed * (dim + 1);
+    k_ema_cluster<<<1, 1024, 0, st>>>(counts, d_cluster_size, n_embed, decay, one_minus_decay, n_scratch);
+    VQ_LAUNCH_CHECK();
+    CodebookImage cb{nullptr, nullptr, nullptr, nullptr};
+    if (d_codebook) cb = codebook_view(d_codebook, dim, n_embed);
+    int wpb = 8;
+    k_ema_embed<<<(n_embed + wpb - 1) / wpb, wpb * 32, 0, st>>>(sums, d_cluster_size, n_scratch, d_embed_avg,
+                                                                 d_embed, cb.cbT, cb.ee, dim, n_embed, decay,
+                                                                 one_minus_decay, eps);
+    VQ_LAUNCH_CHECK();
+    if (!d_codebook) return VQB200_OK;
+    return tc_prepare_codebook(cb, dim, n_embed, st) ? cuda_fail(cudaGetLastError()) : VQB200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vqb200_abi_version(void) { return VQB200_ABI_VERSION; }
+
+const char* vqb200_error_string(int code) {
+    switch (code) {
+        case VQB200_OK: return "ok";
+        case VQB200_EINVAL: return "invalid argument";
+        case VQB200_EUNSUPPORTED: return "unsupported shape or layout";
+        case VQB200_ECUDA: return "CUDA error (see vqb200_last_cuda_error)";
+        case VQB200_ENODEVICE: return "no sm_100 CUDA device";
+        default: return "unknown error";
+    }
+}
+
+int vqb200_last_cuda_error(void) { return g_last_cuda_error; }
+uint64_t vqb200_launch_count(void) { return (uint64_t)g_launches.load(); }
+
+size_t vqb200_codebook_bytes(int32_t dim, int32_t n_embed) {
+    if (dim <= 0 || n_embed <= 0) return 0;
+    return codebook_bytes(dim, n_embed);
+}
+size_t vqb200_forward_scratch_bytes(int64_t n_rows, int32_t dim, int32_t n_embed) {
+    (void)dim; (void)n_embed;
+    if (n_rows < 0) return 0;
+    return forward_scratch_bytes(n_rows);
+}
+size_t vqb200_stats_bytes(int32_t dim, int32_t n_embed) {
+    if (dim <= 0 || n_embed <= 0) return 0;
+    return ((size_t)n_embed * (dim + 1) + 4) * sizeof(float);   // + spare scalars (n = sum cluster_size)
+}
+
+int vqb200_codebook_prepare(const float* d_embed, int32_t dim, int32_t n_embed, void* d_codebook, void* stream) {
+    if (!d_embed || !d_codebook || dim <= 0 || n_embed <= 0) return VQB200_EINVAL;
+    return prepare_codebook(d_embed, dim, n_embed, d_codebook, (cudaStream_t)stream);
+}
+
+int vqb200_quantize_forward(const float* d_x, int64_t n_rows, int32_t dim, int32_t n_embed,
+                            int64_t rows_per_image, int64_t image_stride, int64_t row_stride,
+                            int64_t col_stride, const void* d_codebook, float* d_quantize,
+                            int64_t* d_embed_ind, float* d_diff, float* d_stats, void* d_scratch,
+                            int32_t engine, void* stream) {
+    if (!d_codebook || !d_scratch || dim <= 0 || n_embed <= 0 || n_rows < 0) return VQB200_EINVAL;
+    if (n_rows > 0 && (!d_x || !d_embed_ind)) return VQB200_EINVAL;
+    if (n_rows > (int64_t)INT32_MAX) return VQB200_EUNSUPPORTED;
+    if (engine < VQB200_ENGINE_AUTO || engine > VQB200_ENGINE_TCGEN05) return VQB200_EINVAL;
+    if (n_rows > 0 && !layout_ok(n_rows, dim, rows_per_image, image_stride, row_stride, col_stride))
+        return VQB200_EUNSUPPORTED;
+    RowLayout L{n_rows, rows_per_image > 0 ? rows_per_image : 1, image_stride, row_stride, col_stride};
+    return forward_impl(d_x, L, dim, n_embed, d_codebook, d_quantize, d_embed_ind, d_diff, d_stats, d_scratch,
+                        engine, true, true, n_rows, (cudaStream_t)stream);
+}
+
+int vqb200_ema_update(const float* d_stats, float* d_cluster_size, float* d_embed_avg, float* d_embed,
+                      int32_t dim, int32_t n_embed, float decay, float one_minus_decay, float eps,
+                      void* d_codebook, void* stream) {
+    if (!d_stats || !d_cluster_size || !d_embed_avg || !d_embed || dim <= 0 || n_embed <= 0)
+        return VQB200_EINVAL;
+    return ema_impl(d_stats, d_cluster_size, d_embed_avg, d_embed, dim, n_embed, decay, one_minus_decay, eps,
+                    d_codebook, (cudaStream_t)stream);
+}
+
+int vqb200_quantize_backward(const float* d_x, const int64_t* d_embed_ind, const void* d_codebook,
+                             const float* d_grad_quantize, const float* d_grad_diff, float* d_grad_x,
+                             int64_t n_rows, int32_t dim, int32_t n_embed, int64_t rows_per_image,
+                             int64_t image_stride, int64_t row_stride, int64_t col_stride, void* stream) {
+    if (!d_codebook || dim <= 0 || n_embed <= 0 || n_rows < 0) return VQB200_EINVAL;
+    if (n_rows == 0) return VQB200_OK;
+    if (!d_x || !d_embed_ind || !d_grad_x) return VQB200_EINVAL;
+    if (!layout_ok(n_rows, dim, rows_per_image, image_stride, row_stride, col_stride)) return VQB200_EUNSUPPORTED;
+    RowLayout L{n_rows, rows_per_image, image_stride, row_stride, col_stride};
+    CodebookImage cb = codebook_view(const_cast<void*>(d_codebook), dim, n_embed);
+    int64_t total = n_rows * (int64_t)dim;
+    int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
+    k_backward<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_x, L, dim, d_embed_ind, cb.cbT, d_grad_quantize,
+                                                          d_grad_diff, d_grad_x, 2.0 / (double)total);
+    VQ_LAUNCH_CHECK();
+    return VQB200_OK;
+}
+
+int vqb200_embed_code(const int64_t* d_embed_id, int64_t n_rows, const void* d_codebook, int32_t dim,
+                      int32_t n_embed, float* d_out, int32_t* d_status, void* stream) {
+    if (!d_codebook || dim <= 0 || n_embed <= 0 || n_rows < 0) return VQB200_EINVAL;
+    if (n_rows == 0) return VQB200_OK;
+    if (!d_embed_id || !d_out) return VQB200_EINVAL;
+    CodebookImage cb = codebook_view(const_cast<void*>(d_codebook), dim, n_embed);
+    if (d_status) VQ_CUDA(cudaMemsetAsync(d_status, 0, sizeof(int32_t), (cudaStream_t)stream));
+    int64_t blocks = (n_rows + 7) / 8;
+    k_embed_code<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_embed_id, n_rows, cb.cbT, dim, n_embed, d_out,
+                                                                      d_status);
+    VQ_LAUNCH_CHECK();
+    return VQB200_OK;
+}
+
+// ---- host-buffer path ----------------------------------------------------------------------------
+struct vqb200_host_ctx {
+    int64_t max_rows;
+    int dim, n_embed;
+    int64_t chunk_rows;
+    float* d_x;
+    float* d_q;
+    int64_t* d_ind;
+    float* d_diff;
+    float* d_stats;
+    void* d_scratch;
+    void* d_codebook;
+    cudaStream_t s_in, s_run, s_out;
+    cudaEvent_t ev_in[64], ev_run[64], ev_start;
+};
+
+int vqb200_host_ctx_create(int64_t max_rows, int32_t dim, int32_t n_embed, vqb200_host_ctx** out) {
+    if (!out || max_rows <= 0 || dim <= 0 || n_embed <= 0) return VQB200_EINVAL;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return VQB200_ENODEVICE;
+    vqb200_host_ctx* c = new (std::nothrow) vqb200_host_ctx();
+    if (!c) return VQB200_EINVAL;
+    std::memset(c, 0, sizeof(*c));
+    c->max_rows = max_rows; c->dim = dim; c->n_embed = n_embed;
+    // ~8 MiB of fp32 rows per chunk keeps PCIe busy in both directions while the kernels run
+    int64_t cr = std::max<int64_t>(4096, (8ll << 20) / ((int64_t)dim * 4));
+    cr = (cr + 127) / 128 * 128;
+    while ((max_rows + cr - 1) / cr > 64) cr *= 2;
+    c->chunk_rows = cr;
+#define VQ_CTX(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { vqb200_host_ctx_destroy(c); return cuda_fail(e__); } } while (0)
+    VQ_CTX(cudaMalloc(&c->d_x, (size_t)max_rows * dim * 4));
+    VQ_CTX(cudaMalloc(&c->d_q, (size_t)max_rows * dim * 4));
+    VQ_CTX(cudaMalloc(&c->d_ind, (size_t)max_rows * 8));
+    VQ_CTX(cudaMalloc(&c->d_diff, 256));
+    VQ_CTX(cudaMalloc(&c->d_stats, vqb200_stats_bytes(dim, n_embed)));
+    VQ_CTX(cudaMalloc(&c->d_scratch, forward_scratch_bytes(max_rows)));
+    VQ_CTX(cudaMalloc(&c->d_codebook, codebook_bytes(dim, n_embed)));
+    VQ_CTX(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+    VQ_CTX(cudaStreamCreateWithFlags(&c->s_run, cudaStreamNonBlocking));
+    VQ_CTX(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 64; ++i) {
+        VQ_CTX(cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
+        VQ_CTX(cudaEventCreateWithFlags(&c->ev_run[i], cudaEventDisableTiming));
+    }
+    VQ_CTX(cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming));
+#undef VQ_CTX
+    *out = c;
+    return VQB200_OK;
+}
+
+void vqb200_host_ctx_destroy(vqb200_host_ctx* c) {
+    if (!c) return;
+    cudaFree(c->d_x); cudaFree(c->d_q); cudaFree(c->d_ind); cudaFree(c->d_diff);
+    cudaFree(c->d_stats); cudaFree(c->d_scratch); cudaFree(c->d_codebook);
+    if (c->s_in) cudaStreamDestroy(c->s_in);
+    if (c->s_run) cudaStreamDestroy(c->s_run);
+    if (c->s_out) cudaStreamDestroy(c->s_out);
+    for (int i = 0; i < 64; ++i) {
+        if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
+        if (c->ev_run[i]) cudaEventDestroy(c->ev_run[i]);
+    }
+    if (c->ev_start) cudaEventDestroy(c->ev_start);
+    delete c;
+}
+
+int vqb200_host_quantize(vqb200_host_ctx* c, const float* h_x, int64_t n_rows, float* d_embed,
+                         float* d_cluster_size, float* d_embed_avg, float decay, float one_minus_decay,
+                         float eps, int32_t training, float* h_quantize, int64_t* h_embed_ind, float* h_diff,
+                         int32_t engine) {
+    if (!c || !d_embed || n_rows < 0 || n_rows > c->max_rows) return VQB200_EINVAL;
+    if (n_rows > 0 && (!h_x || !h_embed_ind)) return VQB200_EINVAL;
+    if (training && (!d_cluster_size || !d_embed_avg)) return VQB200_EINVAL;
+    const int D = c->dim, K = c->n_embed;
+    int rc = prepare_codebook(d_embed, D, K, c->d_codebook, c->s_run);
+    if (rc) return rc;
+    float* stats = training ? c->d_stats : nullptr;
+    const int64_t nchunks = n_rows > 0 ? (n_rows + c->chunk_rows - 1) / c->chunk_rows : 1;
+    for (int64_t i = 0; i < nchunks; ++i) {
+        int64_t r0 = i * c->chunk_rows, rows = std::max<int64_t>(0, std::min(c->chunk_rows, n_rows - r0));
+        if (rows > 0) {
+            VQ_CUDA(cudaMemcpyAsync(c->d_x + r0 * D, h_x + r0 * D, (size_t)rows * D * 4, cudaMemcpyHostToDevice, c->s_in));
+            VQ_CUDA(cudaEventRecord(c->ev_in[i], c->s_in));
+            VQ_CUDA(cudaStreamWaitEvent(c->s_run, c->ev_in[i], 0));
+        }
+        RowLayout L{rows, rows > 0 ? rows : 1, 0, D, 1};
+        rc = forward_impl(c->d_x + r0 * D, L, D, K, c->d_codebook, h_quantize ? c->d_q + r0 * D : nullptr,
+                          c->d_ind + r0, c->d_diff, stats, c->d_scratch, engine, i == 0, i == nchunks - 1, n_rows,
+                          c->s_run);
+        if (rc) return rc;
+        if (rows > 0) {
+            VQ_CUDA(cudaEventRecord(c->ev_run[i], c->s_run));
+            VQ_CUDA(cudaStreamWaitEvent(c->s_out, c->ev_run[i], 0));
+            if (h_quantize)
+                VQ_CUDA(cudaMemcpyAsync(h_quantize + r0 * D, c->d_q + r0 * D, (size_t)rows * D * 4,
+                                        cudaMemcpyDeviceToHost, c->s_out));
+            VQ_CUDA(cudaMemcpyAsync(h_embed_ind + r0, c->d_ind + r0, (size_t)rows * 8, cudaMemcpyDeviceToHost, c->s_out));
+        }
+    }
+    if (h_diff) VQ_CUDA(cudaMemcpyAsync(h_diff, c->d_diff, 4, cudaMemcpyDeviceToHost, c->s_run));
+    if (training) {
+        rc = ema_impl(c->d_stats, d_cluster_size, d_embed_avg, d_embed, D, K, decay, one_minus_decay, eps,
+                      c->d_codebook, c->s_run);
+        if (rc) return rc;
+    }
+    VQ_CUDA(cudaStreamSynchronize(c->s_out));
+    VQ_CUDA(cudaStreamSynchronize(c->s_run));
+    return VQB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,235 @@
+"""`Quantize` -- drop-in for the reference VQ layer (/root/reference/vqvae.py:28-78).
+
+Same constructor, attributes, registered buffers (names, order, shapes, dtype), return tuple and
+autograd behaviour as the reference class, so `VQVAE.quantize_t / quantize_b` (vqvae.py:185,190),
+`VQVAE_Deep` (vqvae_deep.py:252,257), train_vqvae.py and extract_code.py can use it unchanged and
+reference checkpoints load strictly.  All arithmetic runs in hand-written sm_100a CUDA behind the C
+ABI of include/vqb200.h; PyTorch supplies device memory, streams and torch.distributed only.
+There is no CPU or PyTorch fallback: non-CUDA tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+from torch import nn
+
+from . import _native
+from . import distributed as dist_fn
+
+
+def _collapse(sizes, strides):
+    """Collapse dims into one (size, stride) if they are nested-contiguous; None otherwise."""
+    dims = [(s, st) for s, st in zip(sizes, strides) if s != 1]
+    if not dims:
+        return 1, 0
+    for (s0, st0), (s1, st1) in zip(dims[:-1], dims[1:]):
+        if st0 != st1 * s1:
+            return None
+    n = 1
+    for s, _ in dims:
+        n *= s
+    return n, dims[-1][1]
+
+
+def row_layout(x: torch.Tensor):
+    """Map a [..., D] tensor to the C ABI's row layout (n_rows, rows_per_image, image_stride,
+    row_stride, col_stride) without copying, or None when the strides fit neither accepted form."""
+    D = x.shape[-1]
+    lead_sizes, lead_strides = list(x.shape[:-1]), list(x.stride()[:-1])
+    col = x.stride(-1) if D > 1 else 1
+    n = 1
+    for s in lead_sizes:
+        n *= s
+    if n == 0:
+        return 0, 1, 0, D, 1
+    if col <= 0:
+        return None
+    for split in range(len(lead_sizes) + 1):
+        outer = _collapse(lead_sizes[:split], lead_strides[:split])
+        inner = _collapse(lead_sizes[split:], lead_strides[split:])
+        if outer is None or inner is None:
+            continue
+        (n_img, img_stride), (rpi, row_stride) = outer, inner
+        if rpi == 1:
+            rpi, row_stride, n_img, img_stride = n_img, img_stride, 1, 0
+        if row_stride <= 0 or (n_img > 1 and img_stride <= 0):
+            continue
+        if col != 1 and row_stride != 1:
+            continue
+        return n, rpi, (img_stride if n_img > 1 else 0), row_stride, col
+    return None
+
+
+class _QuantizeFunction(torch.autograd.Function):
+    """forward = CUDA kernels; backward = straight-through + commitment gradient (vqvae.py:72-73)."""
+
+    @staticmethod
+    def forward(ctx, x, module):
+        quantize, diff, ind, image, lay = module._run_forward(x, keep_image=x.requires_grad)
+        ctx.save_for_backward(x, ind)
+        ctx.image, ctx.lay, ctx.dims = image, lay, (module.dim, module.n_embed)
+        ctx.mark_non_differentiable(ind)
+        return quantize, diff, ind
+
+    @staticmethod
+    def backward(ctx, grad_quantize, grad_diff, _grad_ind):
+        x, ind = ctx.saved_tensors
+        lib = _native.load()
+        n, rpi, img, row, col = ctx.lay
+        dim, n_embed = ctx.dims
+        gq = None
+        if grad_quantize is not None:
+            gq = grad_quantize
+            if gq.stride() != x.stride() or gq.dtype != torch.float32:
+                gq = torch.empty_strided(x.shape, x.stride(), dtype=torch.float32, device=x.device)
+                gq.copy_(grad_quantize)
+        gd = None
+        if grad_diff is not None:
+            gd = grad_diff.to(torch.float32).reshape(1).contiguous()
+        gx = torch.empty_strided(x.shape, x.stride(), dtype=torch.float32, device=x.device)
+        stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+        with torch.cuda.device(x.device):
+            _native.check(lib.vqb200_quantize_backward(
+                _native.ptr(x), _native.ptr(ind), _native.ptr(ctx.image), _native.ptr(gq), _native.ptr(gd),
+                _native.ptr(gx), n, dim, n_embed, rpi, img, row, col, stream), "vqb200_quantize_backward")
+        return gx, None
+
+
+class Quantize(nn.Module):
+    """Vector-quantisation layer with EMA codebook (reference vqvae.py:28-78).
+
+    Extra keyword (not in the reference, defaults keep reference behaviour):
+      engine: "auto" | "simt" | "tcgen05" -- which assignment kernel the C ABI uses.
+    """
+
+    def __init__(self, dim, n_embed, decay=0.99, eps=1e-5, engine="auto"):
+        super().__init__()
+        self.dim = dim
+        self.n_embed = n_embed
+        self.decay = decay
+        self.eps = eps
+        if engine not in _native.ENGINES:
+            raise ValueError(f"engine must be one of {sorted(_native.ENGINES)}")
+        self.engine = engine
+        self.check_ids = False
+
+        embed = torch.randn(dim, n_embed)                                 # vqvae.py:37
+        self.register_buffer("embed", embed)                              # vqvae.py:38
+        self.register_buffer("cluster_size", torch.zeros(n_embed))        # vqvae.py:39
+        self.register_buffer("embed_avg", embed.clone())                  # vqvae.py:40
+        # private device workspaces (never in the state_dict)
+        self._ws = {}
+
+    # ------------------------------------------------------------------ workspaces
+    def _workspace(self, device, n_rows):
+        lib = _native.load()
+        ws = self._ws.get(device)
+        if ws is None:
+            ws = {"image": torch.empty(lib.vqb200_codebook_bytes(self.dim, self.n_embed), dtype=torch.uint8, device=device),
+                  "stats": torch.empty(lib.vqb200_stats_bytes(self.dim, self.n_embed) // 4, dtype=torch.float32, device=device),
+                  "scratch": None, "rows": -1}
+            self._ws = {device: ws}           # one device at a time (module.to() moves it)
+        if ws["rows"] < n_rows:
+            ws["scratch"] = torch.empty(lib.vqb200_forward_scratch_bytes(n_rows, self.dim, self.n_embed),
+                                        dtype=torch.uint8, device=device)
+            ws["rows"] = n_rows
+        return ws
+
+    def _check_input(self, x):
+        if not isinstance(x, torch.Tensor):
+            raise TypeError("Quantize expects a torch.Tensor")
+        if x.dim() < 1 or x.shape[-1] != self.dim:
+            raise RuntimeError(f"Quantize: last dimension of input {tuple(x.shape)} must equal dim={self.dim}")
+        if x.dtype != torch.float32:
+            raise RuntimeError(f"Quantize: expected float32 input (the codebook is float32), got {x.dtype}")
+        if not x.is_cuda:
+            raise RuntimeError("Quantize (B200-native): input must be a CUDA tensor; there is no CPU fallback")
+        if self.embed.device != x.device or self.embed.dtype != torch.float32:
+            raise RuntimeError("Quantize: module buffers must be float32 on the input's device")
+
+    # ------------------------------------------------------------------ forward
+    def _run_forward(self, x, keep_image=False, want_quantize=True):
+        lib = _native.load()
+        lay = row_layout(x)
+        if lay is None:
+            raise RuntimeError("Quantize: unsupported input strides (internal: forward() copies such inputs)")
+        n, rpi, img, row, col = lay
+        dev = x.device
+        ws = self._workspace(dev, n)
+        image = ws["image"]
+        if keep_image:                        # backward gathers from the codebook this forward used
+            image = torch.empty_like(ws["image"])
+        quantize = torch.empty_strided(x.shape, x.stride(), dtype=torch.float32, device=dev) if want_quantize else None
+        ind = torch.empty(x.shape[:-1], dtype=torch.int64, device=dev)
+        diff = torch.empty((), dtype=torch.float32, device=dev)
+        stats = ws["stats"] if self.training else None
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        eng = _native.ENGINES[self.engine]
+        with torch.cuda.device(dev):
+            # the codebook image is re-derived from `embed` on every call: external writes to the buffer
+            # (load_state_dict, .data.copy_, DDP buffer broadcast) can never leave it stale
+            _native.check(lib.vqb200_codebook_prepare(_native.ptr(self.embed), self.dim, self.n_embed,
+                                                      _native.ptr(image), stream), "vqb200_codebook_prepare")
+            _native.check(lib.vqb200_quantize_forward(
+                _native.ptr(x), n, self.dim, self.n_embed, rpi, img, row, col, _native.ptr(image),
+                _native.ptr(quantize), _native.ptr(ind), _native.ptr(diff), _native.ptr(stats),
+                _native.ptr(ws["scratch"]), eng, stream), "vqb200_quantize_forward")
+            if self.training:
+                dist_fn.all_reduce(stats[: self.n_embed * (self.dim + 1)])  # vqvae.py:58-59 (one packed call)
+                _native.check(lib.vqb200_ema_update(
+                    _native.ptr(stats), _native.ptr(self.cluster_size), _native.ptr(self.embed_avg),
+                    _native.ptr(self.embed), self.dim, self.n_embed, float(self.decay), float(1 - self.decay),
+                    float(self.eps), None, stream), "vqb200_ema_update")                      # vqvae.py:61-70
+        return quantize, diff, ind, image, lay
+
+    def forward(self, input):
+        self._check_input(input)
+        if row_layout(input) is None:         # exotic strides: one explicit copy, like reshape() in vqvae.py:43
+            input = input.contiguous()
+        if input.requires_grad and torch.is_grad_enabled():
+            quantize, diff, embed_ind = _QuantizeFunction.apply(input, self)
+        else:
+            quantize, diff, embed_ind, _, _ = self._run_forward(input)
+        return quantize, diff, embed_ind
+
+    @torch.no_grad()
+    def assign(self, input):
+        """Index extraction only (extract_code.py:23 uses nothing but the ids): no quantize / diff output,
+        never touches the EMA buffers."""
+        self._check_input(input)
+        if row_layout(input) is None:
+            input = input.contiguous()
+        was = self.training
+        self.training = False
+        try:
+            _, _, ind, _, _ = self._run_forward(input, want_quantize=False)
+        finally:
+            self.training = was
+        return ind
+
+    def embed_code(self, embed_id):
+        """vqvae.py:77-78: F.embedding(embed_id, embed.T) -> [..., dim]."""
+        if not embed_id.is_cuda:
+            raise RuntimeError("Quantize.embed_code (B200-native): embed_id must be a CUDA tensor")
+        if embed_id.dtype != torch.int64:
+            if embed_id.dtype not in (torch.int32,):
+                raise RuntimeError("Quantize.embed_code: expected an integer index tensor (int64/int32)")
+            embed_id = embed_id.to(torch.int64)
+        lib = _native.load()
+        dev = embed_id.device
+        ids = embed_id.contiguous()
+        n = ids.numel()
+        ws = self._workspace(dev, 0)
+        out = torch.empty(tuple(embed_id.shape) + (self.dim,), dtype=torch.float32, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        with torch.cuda.device(dev):
+            _native.check(lib.vqb200_codebook_prepare(_native.ptr(self.embed), self.dim, self.n_embed,
+                                                      _native.ptr(ws["image"]), stream), "vqb200_codebook_prepare")
+            _native.check(lib.vqb200_embed_code(_native.ptr(ids), n, _native.ptr(ws["image"]), self.dim,
+                                                self.n_embed, _native.ptr(out), _native.ptr(status), stream),
+                          "vqb200_embed_code")
+        if self.check_ids and int(status.item()) != 0:   # opt-in (costs a host sync): F.embedding-style range check
+            raise IndexError("Quantize.embed_code: index out of range")
+        return out
