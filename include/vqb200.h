@@ -104,6 +104,16 @@ int vqb200_quantize_backward(const float* d_x, const int64_t* d_embed_ind, const
 int vqb200_embed_code(const int64_t* d_embed_id, int64_t n_rows, const void* d_codebook,
                       int32_t dim, int32_t n_embed, float* d_out, int32_t* d_status, void* stream);
 
+/* ---- diagnostics ---------------------------------------------------------------------------------- */
+/* Runs the tcgen05 engine on contiguous rows and additionally dumps the tensor-core scores
+ * (certified lower bounds of ||x_n - e_k||^2 + row offset) to d_scores [n_rows, n_embed]; the tests use
+ * it to check the error-bound certificate against float64.  d_flagged_count (1 int32, may be NULL)
+ * receives the number of rows that were sent to the exact re-score.                                  */
+int vqb200_debug_tc_scores(const float* d_x, int64_t n_rows, int32_t dim, int32_t n_embed,
+                           const void* d_codebook, int64_t* d_embed_ind, float* d_scores,
+                           int32_t* d_flagged_count, void* d_scratch, void* stream);
+int vqb200_tc_split(void);   /* 3 = split-bf16 filter (default), 1 = plain bf16 (env VQB200_TC_SPLIT) */
+
 /* ---- host-buffer convenience path (what bench.py's `e2e` times) -------------------------------- */
 /* Same contract as vqb200_quantize_forward (+ optional EMA update when `training`), but x / quantize /
  * embed_ind / diff are HOST buffers (pinned for full speed); H2D and D2H copies are pipelined in row

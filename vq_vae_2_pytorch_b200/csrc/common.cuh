@@ -33,13 +33,10 @@ struct CodebookImage {
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-// tensor-core image geometry: shared by host sizing code and the kernels
-__host__ __device__ inline int tc_dim_padded(int dim) { return (dim + 63) / 64 * 64; }          // K-major rows of 64 bf16 = 128 B
-__host__ __device__ inline int tc_codes_padded(int n_embed) { return (n_embed + 255) / 256 * 256; }
-// number of 64-wide bf16 k-blocks: 3 split terms per 64 input dims + 1 bias/offset block
-__host__ __device__ inline int tc_kblocks(int dim) { return 3 * (tc_dim_padded(dim) / 64) + 1; }
+// tensor-core operand image (tc_kernel.cuh): per code 2 x dim bf16 (hi, lo) + 32 B misc row + fp32 norm
 __host__ __device__ inline size_t tc_image_bytes(int dim, int n_embed) {
-    return (size_t)tc_kblocks(dim) * tc_codes_padded(n_embed) * 128;
+    size_t dpad = (size_t)(dim + 63) / 64 * 64;
+    return (size_t)n_embed * (dpad * 4 + 32 + 4) + 1024;
 }
 
 __host__ __device__ inline size_t codebook_bytes(int dim, int n_embed) {

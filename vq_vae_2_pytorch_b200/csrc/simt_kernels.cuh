@@ -54,10 +54,9 @@ k_assign_exact(const float* __restrict__ x, RowLayout L, int D, int K,
     __shared__ int row_id[AS_BM];
 
     const int64_t total = row_list ? (int64_t)(*row_count) : L.n_rows;
-    const int64_t n0 = (int64_t)blockIdx.x * AS_BM;
-    if (n0 >= total) return;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-
+  for (int64_t n0 = (int64_t)blockIdx.x * AS_BM; n0 < total; n0 += (int64_t)gridDim.x * AS_BM) {
+    __syncthreads();                              // previous tile's row_id / row_off readers are done
     if (tid < AS_BM) {
         int64_t i = n0 + tid;
         int64_t n = -1;
@@ -138,6 +137,7 @@ k_assign_exact(const float* __restrict__ x, RowLayout L, int D, int K,
         int r = ty * 4 + i;
         if (tx == 0 && row_id[r] >= 0) embed_ind[row_id[r]] = (int64_t)bk;
     }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -150,20 +150,24 @@ __global__ void __launch_bounds__(GS_THREADS)
 k_gather_stats(const float* __restrict__ x, RowLayout L, int D, int K,
                const float* __restrict__ cbT, const int64_t* __restrict__ embed_ind,
                float* __restrict__ quantize, double* __restrict__ diff_acc,
-               float* __restrict__ stat_sums, float* __restrict__ stat_counts) {
+               float* __restrict__ stat_sums, float* __restrict__ stat_counts,
+               const int* __restrict__ row_list, const int* __restrict__ row_count) {
     extern __shared__ float tile[];              // [GS_BM][D + 1]
     __shared__ int64_t row_off[GS_BM];
     __shared__ int code[GS_BM];
     __shared__ float warp_part[GS_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ld = D + 1;
-    const int64_t n0 = (int64_t)blockIdx.x * GS_BM;
-    const int rows = (int)min((int64_t)GS_BM, L.n_rows - n0);
-
+    const int64_t total = row_list ? (int64_t)(*row_count) : L.n_rows;
+    float acc = 0.f;
+  for (int64_t n0 = (int64_t)blockIdx.x * GS_BM; n0 < total; n0 += (int64_t)gridDim.x * GS_BM) {
+    const int rows = (int)min((int64_t)GS_BM, total - n0);
+    __syncthreads();                              // previous tile fully written out
     if (tid < GS_BM) {
         bool ok = tid < rows;
-        row_off[tid] = ok ? row_offset(L, n0 + tid) : 0;
-        int64_t k = ok ? embed_ind[n0 + tid] : 0;
+        int64_t n = ok ? (row_list ? (int64_t)row_list[n0 + tid] : n0 + tid) : 0;
+        row_off[tid] = ok ? row_offset(L, n) : 0;
+        int64_t k = ok ? embed_ind[n] : 0;
         code[tid] = (int)k;
     }
     __syncthreads();
@@ -173,7 +177,6 @@ k_gather_stats(const float* __restrict__ x, RowLayout L, int D, int K,
         if (r < rows) tile[r * ld + d] = x[row_off[r] + (int64_t)d * L.col_stride];
     }
     __syncthreads();
-    float acc = 0.f;
     for (int r = warp; r < rows; r += GS_THREADS / 32) {
         const int k = code[r];
         const float* e = cbT + (size_t)k * D;
@@ -186,8 +189,6 @@ k_gather_stats(const float* __restrict__ x, RowLayout L, int D, int K,
         }
         if (stat_counts && lane == 0) atomicAdd(&stat_counts[k], 1.0f);
     }
-    acc = warp_sum(acc);
-    if (lane == 0) warp_part[warp] = acc;
     __syncthreads();
     if (quantize) {
         for (int i = tid; i < GS_BM * D; i += GS_THREADS) {
@@ -196,6 +197,10 @@ k_gather_stats(const float* __restrict__ x, RowLayout L, int D, int K,
             if (r < rows) quantize[row_off[r] + (int64_t)d * L.col_stride] = tile[r * ld + d];
         }
     }
+  }
+    acc = warp_sum(acc);
+    if (lane == 0) warp_part[warp] = acc;
+    __syncthreads();
     if (tid == 0 && diff_acc) {
         float s = 0.f;
         for (int w = 0; w < GS_THREADS / 32; ++w) s += warp_part[w];

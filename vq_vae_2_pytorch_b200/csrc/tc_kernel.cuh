@@ -1,12 +1,584 @@
-// tcgen05 / TMA engine (placeholder until the tensor-core kernel lands in this file).
+// tcgen05 / TMEM / bulk-copy (TMA engine) assignment kernel for sm_100a.
+//
+// One persistent, warp-specialised CTA per SM computes, for tiles of 128 input rows, a LOWER BOUND of
+// the squared distance to every code on the 5th-gen tensor cores, certifies the arg-min with a rigorous
+// error bound, and fuses gather / straight-through output / commitment loss / code statistics behind it
+// (reference vqvae.py:43-56,72-73 in one pass over x).  Rows the bound cannot certify (near-ties) are
+// appended to a list and re-scored by the exact fp32 kernels of simt_kernels.cuh, so the result is the
+// exact-arithmetic arg-min regardless of tensor-core precision.
+//
+// GEMM formulation (all operands bf16, fp32 accumulation in TMEM; K-major, M=128, N=256, K=16 per MMA):
+//   A row i  = [ xh | xl | xh | 1 1 1  o1 o2 o3  nx 1  0.. ]      xh+xl ~ x_i (split bf16, 16 bits)
+//   B row k  = [ eh | eh | el | b1 b2 b3 1 1 1  -cA*ne  -cB*ne^2  0.. ]   eh+el ~ -2 e_k
+//   acc_ik   = -2 x_i.e_k + ||e_k||^2 + off_i - E'_ik  =  lower bound of  ||x_i-e_k||^2 + (off_i-||x_i||^2)
+// with b1+b2+b3 = ||e_k||^2 and o1+o2+o3 = off_i = ||x_i||^2 (1+2^-9) exactly (3-term bf16 splits), and
+// E'_ik = cA ||x_i|| ||e_k|| + cB ||e_k||^2 an upper bound of the filter's own error, folded into the
+// contraction.  NSPLIT=1 drops the xl/el blocks (plain bf16 filter, wider bound).
+//
+// Warp roles (448 threads):  w0 bulk-copy producer | w1 MMA issuer + TMEM owner | w2-5 fp32->bf16
+// converters | w6-9 TMEM epilogue (thread = row, top-2 scan) | w10-13 output (gather, STE, loss, stats).
 #pragma once
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace vqb200 {
+namespace tc {
 
-inline bool tc_supported(const RowLayout&, int, int) { return false; }
-inline int tc_prepare_codebook(const CodebookImage&, int, int, cudaStream_t) { return 0; }
-inline int tc_forward(const float*, const RowLayout&, int, int, const CodebookImage&, float*, int64_t*,
-                      const ForwardScratch&, float*, float*, cudaStream_t) { return 1; }
+constexpr int TILE_M = 128;        // rows per tile = UMMA M
+constexpr int UNIT_N = 256;        // codes per MMA = UMMA N
+constexpr int TC_D = 64;           // supported dim: one 128-byte swizzle row of bf16
+constexpr int THREADS = 448;
+constexpr int NORM_RING = 8;
+constexpr int RES_RING = 2;
+
+// error-bound constants (see DESIGN.md "certificate"): dot-product error <= c1 ||x|| ||e||
+//   split-bf16 (3 products): 3.1 * 2^-18 rounding + fp32 accumulation  -> c1 = 2^-16, cA = 2 c1
+//   plain bf16             : (1+2^-9)^2 - 1                            -> c1 = 2^-8 * 1.01
+__host__ __device__ constexpr float bound_cA(int nsplit) { return nsplit == 3 ? 3.0517578125e-5f : 7.9e-3f; }
+constexpr float BOUND_CB = 4.0e-6f;        // fp32 accumulation of <= 14 MMAs, relative to ||x||^2 + ||e||^2
+constexpr float BOUND_UP = 1.03125f;       // covers the upward bf16 roundings of ||x||, ||e||, ||e||^2
+
+// ---------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+// the loaded registers are in/out operands so no use of them can be scheduled above the wait
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                   "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                   "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+                   "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+                 :: "memory");
+}
+
+__device__ __forceinline__ void red_add_v4(float* p, float4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void red_add_f32(float* p, float v) {
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+// shared-memory matrix descriptors (cute::UMMA::SmemDescriptor bit layout), K-major operands
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr) {   // rows of 128 B, 8-row atoms of 1024 B
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ uint64_t desc_sw32(uint32_t saddr) {    // rows of 32 B, 8-row atoms of 256 B
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46) | (6ull << 61);
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, K-major both, N=256, M=128
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(UNIT_N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+
+// byte offset of bf16 element (row, col) inside a 128B-swizzled K-major block (Swizzle<3,4,3>)
+__host__ __device__ __forceinline__ uint32_t sw128_off(uint32_t row, uint32_t col) {
+    uint32_t chunk = col >> 3;
+    return row * 128u + (((chunk ^ (row & 7u)) << 4) | ((col & 7u) << 1));
+}
+// byte offset of the 16-byte chunk c (0/1) of `row` inside a 32B-swizzled K-major block (Swizzle<1,4,3>)
+__host__ __device__ __forceinline__ uint32_t sw32_chunk_off(uint32_t row, uint32_t c) {
+    return (row >> 3) * 256u + (row & 7u) * 32u + ((c ^ ((row >> 2) & 1u)) << 4);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {   // element 0 in the low half
+    __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&p);
+}
+__device__ __forceinline__ float bf16_round(float f) { return __bfloat162float(__float2bfloat16_rn(f)); }
+// exact 3-term bf16 split of an fp32 value
+__device__ __forceinline__ void split3(float f, float& a, float& b, float& c) {
+    a = bf16_round(f);
+    float r = f - a;
+    b = bf16_round(r);
+    c = bf16_round(r - b);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// tensor-core operand image of the codebook (global memory, byte-identical to its smem layout)
+//   [ eh : K*128 | el : K*128 | misc : K*32 ]   + enorm[K] (fp32 ||e_k||) kept next to it
+// ---------------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t image_off_lo(int K) { return (size_t)K * 128; }
+__host__ __device__ inline size_t image_off_misc(int K) { return (size_t)K * 256; }
+__host__ __device__ inline size_t image_off_enorm(int K) { return (size_t)K * 288; }
+__host__ __device__ inline size_t image_bytes(int K) { return (size_t)K * 288 + (size_t)K * 4; }
+
+// one thread per (code, 8-dim chunk); requires D == 64
+__global__ void k_tc_image(const float* __restrict__ cbT, const float* __restrict__ ee, unsigned char* __restrict__ img,
+                           int K, float cA, float cB) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int k = t >> 3, c = t & 7;
+    if (k >= K) return;
+    const float* e = cbT + (size_t)k * TC_D + c * 8;
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float a = -2.f * e[2 * j], b = -2.f * e[2 * j + 1];
+        float ah = bf16_round(a), bh = bf16_round(b);
+        hi[j] = pack_bf16(ah, bh);
+        lo[j] = pack_bf16(a - ah, b - bh);
+    }
+    uint32_t off = sw128_off((uint32_t)k, (uint32_t)c * 8);
+    *reinterpret_cast<uint4*>(img + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(img + image_off_lo(K) + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    if (c == 0) {
+        float b1, b2, b3;
+        float e2 = ee[k];
+        split3(e2, b1, b2, b3);
+        float ne = sqrtf(e2);
+        float t6 = -bf16_round(cA * ne * 1.0078125f);           // rounded up in magnitude
+        float t7 = -bf16_round(cB * e2 * 1.0078125f);
+        unsigned char* m = img + image_off_misc(K);
+        *reinterpret_cast<uint4*>(m + sw32_chunk_off((uint32_t)k, 0)) =
+            make_uint4(pack_bf16(b1, b2), pack_bf16(b3, 1.f), pack_bf16(1.f, 1.f), pack_bf16(t6, t7));
+        *reinterpret_cast<uint4*>(m + sw32_chunk_off((uint32_t)k, 1)) = make_uint4(0, 0, 0, 0);
+        reinterpret_cast<float*>(img + image_off_enorm(K))[k] = ne;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// shared-memory plan
+// ---------------------------------------------------------------------------------------------------
+template <int NSPLIT, int AS, int XS>
+struct Plan {
+    static constexpr uint32_t A_STAGE = (NSPLIT == 3 ? 2u : 1u) * 16384u + 4096u;
+    static constexpr uint32_t X_STAGE = TILE_M * TC_D * 4;
+    __host__ __device__ static uint32_t b_bytes(int K) { return (uint32_t)K * (NSPLIT == 3 ? 256u : 128u) + (uint32_t)K * 32u; }
+    __host__ __device__ static uint32_t off_b_lo(int K) { return (uint32_t)K * 128u; }
+    __host__ __device__ static uint32_t off_b_misc(int K) { return (uint32_t)K * (NSPLIT == 3 ? 256u : 128u); }
+    __host__ __device__ static uint32_t off_a(int K) { return b_bytes(K); }
+    __host__ __device__ static uint32_t off_x(int K) { return off_a(K) + AS * A_STAGE; }
+    __host__ __device__ static uint32_t off_small(int K) { return off_x(K) + XS * X_STAGE; }
+    // small region: enorm[K] | rownorm[NORM_RING][128] | codes[RES_RING][128] | barriers | tmem ptr
+    __host__ __device__ static uint32_t off_rownorm(int K) { return off_small(K) + (uint32_t)K * 4u; }
+    __host__ __device__ static uint32_t off_codes(int K) { return off_rownorm(K) + NORM_RING * TILE_M * 4u; }
+    __host__ __device__ static uint32_t off_bars(int K) { return off_codes(K) + RES_RING * TILE_M * 4u; }
+    __host__ __device__ static uint32_t total(int K) { return off_bars(K) + 512u + 1024u /* base alignment slack */; }
+};
+
+struct Params {
+    const float* x;
+    int64_t n_rows;
+    int K;
+    const unsigned char* image;      // tensor-core operand image
+    const float* cbT;                // [K][64] fp32
+    float* quantize;                 // may be null
+    int64_t* embed_ind;
+    double* diff_acc;                // may be null
+    float* stat_sums;                // may be null
+    float* stat_counts;
+    int* flagged_count;
+    int* flagged_rows;
+    float* dbg_scores;               // optional [n_rows][K] dump of the tensor-core scores
+    float cA, cB;
+};
+
+enum BarId { BAR_B = 0, BAR_XF = 1, BAR_XE = 5, BAR_AF = 9, BAR_AE = 13, BAR_TF = 17, BAR_TE = 19, BAR_RF = 21, BAR_RE = 23, BAR_COUNT = 25 };
+
+template <int NSPLIT, int AS, int XS>
+__global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
+    using P = Plan<NSPLIT, AS, XS>;
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    unsigned char* sm = smem_raw + (base - raw);
+    const int K = p.K;
+    const int U = K / UNIT_N;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    const uint32_t sB = base, sA = base + P::off_a(K), sX = base + P::off_x(K);
+    float* enorm_s = reinterpret_cast<float*>(sm + P::off_small(K));
+    float* rownorm_s = reinterpret_cast<float*>(sm + P::off_rownorm(K));
+    int* codes_s = reinterpret_cast<int*>(sm + P::off_codes(K));
+    const uint32_t bars = base + P::off_bars(K);
+    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(sm + P::off_bars(K) + BAR_COUNT * 8);
+    auto bar = [&](int id) { return bars + 8u * (uint32_t)id; };
+
+    const int64_t n_tiles = (p.n_rows + TILE_M - 1) / TILE_M;
+
+    // ---- one-time setup -----------------------------------------------------------------------------
+    if (threadIdx.x == 0) {
+        mbar_init(bar(BAR_B), 1);
+        for (int s = 0; s < XS; ++s) { mbar_init(bar(BAR_XF + s), 1); mbar_init(bar(BAR_XE + s), 128); }
+        for (int s = 0; s < AS; ++s) { mbar_init(bar(BAR_AF + s), 128); mbar_init(bar(BAR_AE + s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(bar(BAR_TF + s), 1); mbar_init(bar(BAR_TE + s), 128); }
+        for (int s = 0; s < RES_RING; ++s) { mbar_init(bar(BAR_RF + s), 128); mbar_init(bar(BAR_RE + s), 128); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_ptr_s), 512);
+    // constant part of the A "misc" blocks: [1 1 1 | o1 o2 o3 | nx 1 | 0 x8]; zero chunk 1 once
+    for (int i = threadIdx.x; i < AS * TILE_M; i += THREADS) {
+        int s = i / TILE_M, r = i % TILE_M;
+        unsigned char* m = sm + P::off_a(K) + s * P::A_STAGE + (P::A_STAGE - 4096u);
+        *reinterpret_cast<uint4*>(m + sw32_chunk_off((uint32_t)r, 1)) = make_uint4(0, 0, 0, 0);
+    }
+    fence_async_smem();
+    for (int i = threadIdx.x; i < K; i += THREADS)
+        enorm_s[i] = reinterpret_cast<const float*>(p.image + image_off_enorm(K))[i];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_s;
+
+    if (warp == 0) {
+        // ================= bulk-copy producer =========================================================
+        if (lane == 0) {
+            const uint32_t bbytes = P::b_bytes(K);
+            mbar_expect_tx(bar(BAR_B), bbytes);
+            // eh [, el], misc : three contiguous pieces of the image
+            bulk_g2s(sB, p.image, (uint32_t)K * 128u, bar(BAR_B));
+            if (NSPLIT == 3) bulk_g2s(sB + P::off_b_lo(K), p.image + image_off_lo(K), (uint32_t)K * 128u, bar(BAR_B));
+            bulk_g2s(sB + P::off_b_misc(K), p.image + image_off_misc(K), (uint32_t)K * 32u, bar(BAR_B));
+            uint32_t it = 0;
+            for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+                const uint32_t s = it % XS, ph = (it / XS) & 1u;
+                mbar_wait(bar(BAR_XE + s), ph ^ 1u);
+                const int64_t r0 = t * TILE_M;
+                const uint32_t rows = (uint32_t)min((int64_t)TILE_M, p.n_rows - r0);
+                const uint32_t bytes = rows * TC_D * 4u;
+                mbar_expect_tx(bar(BAR_XF + s), bytes);
+                bulk_g2s(sX + s * P::X_STAGE, p.x + r0 * TC_D, bytes, bar(BAR_XF + s));
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer ==================================================================
+        mbar_wait(bar(BAR_B), 0);
+        uint32_t it = 0, uc = 0;
+        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+            const uint32_t sa = it % AS, pha = (it / AS) & 1u;
+            mbar_wait(bar(BAR_AF + sa), pha);
+            tc_fence_after();
+            const uint32_t a0 = sA + sa * P::A_STAGE;
+            for (int u = 0; u < U; ++u, ++uc) {
+                const uint32_t buf = uc & 1u, pht = (uc >> 1) & 1u;
+                mbar_wait(bar(BAR_TE + buf), pht ^ 1u);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t d_tmem = tmem_base + buf * UNIT_N;
+                    const uint32_t b_hi = sB + (uint32_t)u * UNIT_N * 128u;
+                    const uint32_t b_lo = sB + P::off_b_lo(K) + (uint32_t)u * UNIT_N * 128u;
+                    const uint32_t b_mi = sB + P::off_b_misc(K) + (uint32_t)u * UNIT_N * 32u;
+                    uint32_t acc = 0;
+                    // misc block first (bias, offset, error bound), then the split products
+                    umma_bf16(d_tmem, desc_sw32(a0 + (P::A_STAGE - 4096u)), desc_sw32(b_mi), IDESC, acc);
+                    acc = 1;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)      // xh . eh
+                        umma_bf16(d_tmem, desc_sw128(a0) + 2u * ks, desc_sw128(b_hi) + 2u * ks, IDESC, acc);
+                    if (NSPLIT == 3) {
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)  // xl . eh
+                            umma_bf16(d_tmem, desc_sw128(a0 + 16384u) + 2u * ks, desc_sw128(b_hi) + 2u * ks, IDESC, acc);
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)  // xh . el
+                            umma_bf16(d_tmem, desc_sw128(a0) + 2u * ks, desc_sw128(b_lo) + 2u * ks, IDESC, acc);
+                    }
+                    umma_commit(bar(BAR_TF + buf));
+                }
+                __syncwarp();
+            }
+            if (lane == 0) umma_commit(bar(BAR_AE + sa));
+            __syncwarp();
+        }
+    } else if (warp < 6) {
+        // ================= converters: fp32 rows -> split-bf16 K-major operand ==========================
+        const int cw = warp - 2;                 // rows cw*32 .. cw*32+31
+        const int half = lane >> 4, q4 = lane & 15;
+        uint32_t it = 0;
+        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+            const uint32_t sx = it % XS, phx = (it / XS) & 1u, sa = it % AS, pha = (it / AS) & 1u;
+            mbar_wait(bar(BAR_XF + sx), phx);
+            mbar_wait(bar(BAR_AE + sa), pha ^ 1u);
+            const unsigned char* xs = sm + P::off_x(K) + sx * P::X_STAGE;
+            unsigned char* ah = sm + P::off_a(K) + sa * P::A_STAGE;
+            unsigned char* al = ah + 16384u;
+            unsigned char* am = ah + (P::A_STAGE - 4096u);
+            float my_sq = 0.f;
+#pragma unroll 4
+            for (int i = 0; i < 16; ++i) {
+                const int r = cw * 32 + 2 * i + half;
+                const float4 v = *reinterpret_cast<const float4*>(xs + r * 256 + q4 * 16);
+                const float h0 = bf16_round(v.x), h1 = bf16_round(v.y), h2 = bf16_round(v.z), h3 = bf16_round(v.w);
+                const uint32_t off = sw128_off((uint32_t)r, (uint32_t)q4 * 4);
+                *reinterpret_cast<uint2*>(ah + off) = make_uint2(pack_bf16(h0, h1), pack_bf16(h2, h3));
+                if (NSPLIT == 3)
+                    *reinterpret_cast<uint2*>(al + off) = make_uint2(pack_bf16(v.x - h0, v.y - h1), pack_bf16(v.z - h2, v.w - h3));
+                float sq = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)));
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+                if (q4 == i) my_sq = sq;          // lane (half, q4=i) keeps row cw*32 + 2i + half
+            }
+            {
+                const int r = cw * 32 + 2 * q4 + half;
+                const float nx = sqrtf(my_sq);
+                float o1, o2, o3;
+                split3(my_sq * 1.001953125f, o1, o2, o3);            // off_i = ||x||^2 (1 + 2^-9)
+                const float nxu = bf16_round(nx * 1.0078125f);        // ||x|| rounded up
+                *reinterpret_cast<uint4*>(am + sw32_chunk_off((uint32_t)r, 0)) =
+                    make_uint4(pack_bf16(1.f, 1.f), pack_bf16(1.f, o1), pack_bf16(o2, o3), pack_bf16(nxu, 1.f));
+                rownorm_s[(it % NORM_RING) * TILE_M + r] = nx;
+            }
+            fence_async_smem();
+            mbar_arrive(bar(BAR_AF + sa));
+            mbar_arrive(bar(BAR_XE + sx));
+        }
+    } else if (warp < 10) {
+        // ================= epilogue: TMEM -> top-2 scan -> certified arg-min ============================
+        const int wq = warp & 3;                 // TMEM lane quarter this warp may access
+        const int row_in_tile = wq * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(wq * 32) << 16);
+        uint32_t it = 0, uc = 0;
+        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+            float m1 = INFINITY, m2 = INFINITY, pm1 = INFINITY;
+            int cbest = 0;
+            const int64_t grow = t * TILE_M + row_in_tile;
+            for (int u = 0; u < U; ++u, ++uc) {
+                const uint32_t buf = uc & 1u, pht = (uc >> 1) & 1u;
+                mbar_wait(bar(BAR_TF + buf), pht);
+                tc_fence_after();
+                uint32_t va[32], vb[32];
+                tmem_ld32(lane_addr + buf * UNIT_N, va);
+#pragma unroll
+                for (int c = 0; c < 8; c += 2) {
+                    tmem_ld_wait(va);
+                    tmem_ld32(lane_addr + buf * UNIT_N + (c + 1) * 32, vb);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float kf = __uint_as_float((va[j] & 0xFFFFFFE0u) | (uint32_t)j);
+                        const float tmx = fmaxf(m1, kf);
+                        m1 = fminf(m1, kf);
+                        m2 = fminf(m2, tmx);
+                    }
+                    if (m1 != pm1) { cbest = u * 8 + c; pm1 = m1; }
+                    if (p.dbg_scores && grow < p.n_rows) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) p.dbg_scores[grow * K + u * UNIT_N + c * 32 + j] = __uint_as_float(va[j]);
+                    }
+                    tmem_ld_wait(vb);
+                    if (c + 2 < 8) tmem_ld32(lane_addr + buf * UNIT_N + (c + 2) * 32, va);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float kf = __uint_as_float((vb[j] & 0xFFFFFFE0u) | (uint32_t)j);
+                        const float tmx = fmaxf(m1, kf);
+                        m1 = fminf(m1, kf);
+                        m2 = fminf(m2, tmx);
+                    }
+                    if (m1 != pm1) { cbest = u * 8 + c + 1; pm1 = m1; }
+                    if (p.dbg_scores && grow < p.n_rows) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) p.dbg_scores[grow * K + u * UNIT_N + (c + 1) * 32 + j] = __uint_as_float(vb[j]);
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(bar(BAR_TE + buf));
+            }
+            // certificate: every other code's lower bound must clear the winner's upper bound
+            const uint32_t m1b = __float_as_uint(m1);
+            const int k1 = cbest * 32 + (int)(m1b & 31u);
+            const float v1 = __uint_as_float(m1b & 0xFFFFFFE0u);
+            const float xn = rownorm_s[(it % NORM_RING) * TILE_M + row_in_tile];
+            const float en = enorm_s[k1 < K ? k1 : 0];
+            const float need = 2.f * (p.cA * BOUND_UP * xn * en + p.cB * (BOUND_UP * en * en + xn * xn)) +
+                               (fabsf(m1) + fabsf(m2)) * 3.814697265625e-6f;      // packing truncation, 2^-18 each
+            const bool certified = (m2 - v1) > need;                                // NaN -> false
+            const bool in_range = grow < p.n_rows;
+            const uint32_t rs = it % RES_RING, phr = (it / RES_RING) & 1u;
+            mbar_wait(bar(BAR_RE + rs), phr ^ 1u);
+            int code = -2;
+            if (in_range) {
+                code = certified ? k1 : -1;
+                if (certified) p.embed_ind[grow] = (int64_t)k1;
+            }
+            codes_s[rs * TILE_M + row_in_tile] = code;
+            const unsigned fl = __ballot_sync(0xffffffffu, code == -1);
+            if (fl) {
+                int basei = 0;
+                const int leader = __ffs(fl) - 1;
+                if (lane == leader) basei = atomicAdd(p.flagged_count, __popc(fl));
+                basei = __shfl_sync(0xffffffffu, basei, leader);
+                if (code == -1) p.flagged_rows[basei + __popc(fl & ((1u << lane) - 1u))] = (int)grow;
+            }
+            mbar_arrive(bar(BAR_RF + rs));
+        }
+    } else {
+        // ================= output: gather, straight-through value, loss, statistics ====================
+        const int ow = warp - 10;                // rows ow*32 .. ow*32+31 of the tile
+        const int half = lane >> 4, q4 = lane & 15;
+        float dacc = 0.f;
+        uint32_t it = 0;
+        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+            const uint32_t rs = it % RES_RING, phr = (it / RES_RING) & 1u;
+            mbar_wait(bar(BAR_RF + rs), phr);
+            const int64_t r0 = t * TILE_M;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                int kk[4];
+                float4 xv[4], qv[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int r = ow * 32 + b * 8 + i * 2 + half;
+                    kk[i] = codes_s[rs * TILE_M + r];
+                    if (kk[i] >= 0) {
+                        xv[i] = *reinterpret_cast<const float4*>(p.x + (r0 + r) * TC_D + q4 * 4);
+                        qv[i] = __ldg(reinterpret_cast<const float4*>(p.cbT + (size_t)kk[i] * TC_D + q4 * 4));
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (kk[i] < 0) continue;
+                    const int r = ow * 32 + b * 8 + i * 2 + half;
+                    float4 d, o;
+                    d.x = qv[i].x - xv[i].x; d.y = qv[i].y - xv[i].y; d.z = qv[i].z - xv[i].z; d.w = qv[i].w - xv[i].w;
+                    o.x = xv[i].x + d.x; o.y = xv[i].y + d.y; o.z = xv[i].z + d.z; o.w = xv[i].w + d.w;
+                    dacc = fmaf(d.x, d.x, fmaf(d.y, d.y, fmaf(d.z, d.z, fmaf(d.w, d.w, dacc))));
+                    if (p.quantize) __stcs(reinterpret_cast<float4*>(p.quantize + (r0 + r) * TC_D + q4 * 4), o);
+                    if (p.stat_sums) {
+                        red_add_v4(p.stat_sums + (size_t)kk[i] * TC_D + q4 * 4, xv[i]);
+                        if (q4 == 0) red_add_f32(p.stat_counts + kk[i], 1.0f);
+                    }
+                }
+            }
+            mbar_arrive(bar(BAR_RE + rs));
+        }
+        if (p.diff_acc) {
+            dacc = warp_sum(dacc);
+            if (lane == 0) atomicAdd(p.diff_acc, (double)dacc);
+        }
+    }
+
+    // ---- teardown -------------------------------------------------------------------------------------
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace tc
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+inline int tc_nsplit() {
+    static int v = [] {
+        const char* e = getenv("VQB200_TC_SPLIT");
+        int n = e ? atoi(e) : 3;
+        return n == 1 ? 1 : 3;
+    }();
+    return v;
+}
+inline int tc_num_sms() {
+    static int v = [] {
+        int dev = 0, n = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        return n > 0 ? n : 148;
+    }();
+    return v;
+}
+
+inline bool tc_shape_ok(int dim, int n_embed) { return dim == tc::TC_D && (n_embed == 256 || n_embed == 512); }
+
+inline bool tc_supported(const RowLayout& L, const float* x, int dim, int n_embed) {
+    if (!tc_shape_ok(dim, n_embed) || L.n_rows < 1) return false;
+    if (getenv("VQB200_DISABLE_TC")) return false;
+    if (L.col_stride != 1 || L.row_stride != dim) return false;                 // contiguous rows only (for now)
+    if (L.n_rows > L.rows_per_image && L.image_stride != L.rows_per_image * dim) return false;
+    return (reinterpret_cast<uintptr_t>(x) & 15u) == 0;                          // bulk copies need 16-byte alignment
+}
+
+// builds the tensor-core operand image next to cbT / ee (no-op for shapes the kernel does not cover)
+inline int tc_prepare_codebook(const CodebookImage& cb, int dim, int n_embed, cudaStream_t st) {
+    if (!tc_shape_ok(dim, n_embed)) return 0;
+    int threads = n_embed * 8;
+    tc::k_tc_image<<<(threads + 255) / 256, 256, 0, st>>>(cb.cbT, cb.ee, cb.tc, n_embed, tc::bound_cA(tc_nsplit()), tc::BOUND_CB);
+    return cudaGetLastError() != cudaSuccess;
+}
+
+template <int NSPLIT, int AS, int XS>
+inline int tc_launch(const tc::Params& prm, cudaStream_t st) {
+    using P = tc::Plan<NSPLIT, AS, XS>;
+    auto kern = tc::k_vq_tc<NSPLIT, AS, XS>;
+    const int smem = (int)P::total(prm.K);
+    static int configured = 0;
+    if (configured < smem) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 1;
+        configured = smem;
+    }
+    int64_t n_tiles = (prm.n_rows + tc::TILE_M - 1) / tc::TILE_M;
+    int grid = (int)std::min<int64_t>(n_tiles, tc_num_sms());
+    kern<<<grid, tc::THREADS, smem, st>>>(prm);
+    return cudaGetLastError() != cudaSuccess;
+}
+
+// main kernel only; the caller runs the exact fix-up over the flagged rows afterwards
+inline int tc_forward(const float* x, const RowLayout& L, int dim, int n_embed, const CodebookImage& cb,
+                      float* quantize, int64_t* embed_ind, const ForwardScratch& sc, double* diff_acc,
+                      float* sums, float* counts, float* dbg_scores, cudaStream_t st) {
+    (void)dim;
+    tc::Params prm;
+    prm.x = x; prm.n_rows = L.n_rows; prm.K = n_embed; prm.image = cb.tc; prm.cbT = cb.cbT;
+    prm.quantize = quantize; prm.embed_ind = embed_ind; prm.diff_acc = diff_acc;
+    prm.stat_sums = sums; prm.stat_counts = counts;
+    prm.flagged_count = sc.flagged_count; prm.flagged_rows = sc.flagged_rows; prm.dbg_scores = dbg_scores;
+    prm.cA = tc::bound_cA(tc_nsplit()); prm.cB = tc::BOUND_CB;
+    if (tc_nsplit() == 3) return tc_launch<3, 1, 1>(prm, st);
+    return tc_launch<1, 2, 2>(prm, st);
+}
 
 }  // namespace vqb200

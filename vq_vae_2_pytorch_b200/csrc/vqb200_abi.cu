@@ -63,7 +63,8 @@ int prepare_codebook(const float* d_embed, int dim, int n_embed, void* d_codeboo
 //   finalize   : write diff = acc / (total_rows * dim)
 int forward_impl(const float* d_x, const RowLayout& L, int dim, int n_embed, const void* d_codebook,
                  float* d_quantize, int64_t* d_ind, float* d_diff, float* d_stats, void* d_scratch,
-                 int engine, bool zero_first, bool finalize, int64_t total_rows, cudaStream_t st) {
+                 int engine, bool zero_first, bool finalize, int64_t total_rows, cudaStream_t st,
+                 float* dbg_scores = nullptr) {
     CodebookImage cb = codebook_view(const_cast<void*>(d_codebook), dim, n_embed);
     ForwardScratch sc = scratch_view(d_scratch);
     float* sums = d_stats;
@@ -75,24 +76,40 @@ int forward_impl(const float* d_x, const RowLayout& L, int dim, int n_embed, con
     if (L.n_rows > 0) {
         bool use_tc = false;
         if (engine == VQB200_ENGINE_TCGEN05 || engine == VQB200_ENGINE_AUTO)
-            use_tc = tc_supported(L, dim, n_embed);
+            use_tc = tc_supported(L, d_x, dim, n_embed);
         if (engine == VQB200_ENGINE_TCGEN05 && !use_tc) return VQB200_EUNSUPPORTED;
+        const bool want_gather = d_quantize || d_diff || d_stats;
+        const size_t gsmem = (size_t)GS_BM * (dim + 1) * sizeof(float);
+        if (gsmem > 200 * 1024) return VQB200_EUNSUPPORTED;
+        if (gsmem > 48 * 1024)
+            VQ_CUDA(cudaFuncSetAttribute(k_gather_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+        const int sms = tc_num_sms();
         if (use_tc) {
-            int rc = tc_forward(d_x, L, dim, n_embed, cb, d_quantize, d_ind, sc, sums, counts, st);
+            // tensor-core filter + fused output for certified rows; flagged rows -> exact SIMT fix-up
+            VQ_CUDA(cudaMemsetAsync(sc.flagged_count, 0, sizeof(int), st));
+            int rc = tc_forward(d_x, L, dim, n_embed, cb, d_quantize, d_ind, sc, d_diff ? sc.diff_acc : nullptr, sums,
+                                counts, dbg_scores, st);
+            g_launches.fetch_add(1);
             if (rc) return cuda_fail(cudaGetLastError());
+            k_assign_exact<<<sms * 2, AS_THREADS, 0, st>>>(d_x, L, dim, n_embed, cb.cbT, cb.ee, d_ind,
+                                                           sc.flagged_rows, sc.flagged_count);
+            VQ_LAUNCH_CHECK();
+            if (want_gather) {
+                k_gather_stats<<<sms * 2, GS_THREADS, gsmem, st>>>(d_x, L, dim, n_embed, cb.cbT, d_ind, d_quantize,
+                                                                    d_diff ? sc.diff_acc : nullptr, sums, counts,
+                                                                    sc.flagged_rows, sc.flagged_count);
+                VQ_LAUNCH_CHECK();
+            }
         } else {
-            int64_t blocks = (L.n_rows + AS_BM - 1) / AS_BM;
+            int64_t blocks = std::min<int64_t>((L.n_rows + AS_BM - 1) / AS_BM, (int64_t)sms * 64);
             k_assign_exact<<<(unsigned)blocks, AS_THREADS, 0, st>>>(d_x, L, dim, n_embed, cb.cbT, cb.ee, d_ind,
                                                                       nullptr, nullptr);
             VQ_LAUNCH_CHECK();
-            if (d_quantize || d_diff || d_stats) {
-                size_t smem = (size_t)GS_BM * (dim + 1) * sizeof(float);
-                if (smem > 200 * 1024) return VQB200_EUNSUPPORTED;
-                if (smem > 48 * 1024)
-                    VQ_CUDA(cudaFuncSetAttribute(k_gather_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                int64_t gblocks = (L.n_rows + GS_BM - 1) / GS_BM;
-                k_gather_stats<<<(unsigned)gblocks, GS_THREADS, smem, st>>>(
-                    d_x, L, dim, n_embed, cb.cbT, d_ind, d_quantize, d_diff ? sc.diff_acc : nullptr, sums, counts);
+            if (want_gather) {
+                int64_t gblocks = std::min<int64_t>((L.n_rows + GS_BM - 1) / GS_BM, (int64_t)sms * 64);
+                k_gather_stats<<<(unsigned)gblocks, GS_THREADS, gsmem, st>>>(
+                    d_x, L, dim, n_embed, cb.cbT, d_ind, d_quantize, d_diff ? sc.diff_acc : nullptr, sums, counts,
+                    nullptr, nullptr);
                 VQ_LAUNCH_CHECK();
             }
         }
@@ -221,6 +238,24 @@ int vqb200_embed_code(const int64_t* d_embed_id, int64_t n_rows, const void* d_c
     VQ_LAUNCH_CHECK();
     return VQB200_OK;
 }
+
+int vqb200_debug_tc_scores(const float* d_x, int64_t n_rows, int32_t dim, int32_t n_embed, const void* d_codebook,
+                           int64_t* d_embed_ind, float* d_scores, int32_t* d_flagged_count, void* d_scratch,
+                           void* stream) {
+    if (!d_x || !d_codebook || !d_embed_ind || !d_scores || !d_scratch || n_rows <= 0) return VQB200_EINVAL;
+    RowLayout L{n_rows, n_rows, 0, dim, 1};
+    if (!tc_supported(L, d_x, dim, n_embed)) return VQB200_EUNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = forward_impl(d_x, L, dim, n_embed, d_codebook, nullptr, d_embed_ind, nullptr, nullptr, d_scratch,
+                          VQB200_ENGINE_TCGEN05, true, false, n_rows, st, d_scores);
+    if (rc) return rc;
+    if (d_flagged_count)
+        VQ_CUDA(cudaMemcpyAsync(d_flagged_count, scratch_view(d_scratch).flagged_count, sizeof(int),
+                                cudaMemcpyDeviceToDevice, st));
+    return VQB200_OK;
+}
+
+int vqb200_tc_split(void) { return tc_nsplit(); }
 
 // ---- host-buffer path ----------------------------------------------------------------------------
 struct vqb200_host_ctx {

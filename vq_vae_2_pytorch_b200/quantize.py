@@ -45,6 +45,8 @@ def row_layout(x: torch.Tensor):
         return 0, 1, 0, D, 1
     if col <= 0:
         return None
+    if n == 1:                                # a single row: any row stride describes it
+        return 1, 1, 0, (D if col == 1 else 1), col
     for split in range(len(lead_sizes) + 1):
         outer = _collapse(lead_sizes[:split], lead_strides[:split])
         inner = _collapse(lead_sizes[split:], lead_strides[split:])
