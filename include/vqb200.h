@@ -112,6 +112,12 @@ int vqb200_embed_code(const int64_t* d_embed_id, int64_t n_rows, const void* d_c
 int vqb200_debug_tc_scores(const float* d_x, int64_t n_rows, int32_t dim, int32_t n_embed,
                            const void* d_codebook, int64_t* d_embed_ind, float* d_scores,
                            int32_t* d_flagged_count, void* d_scratch, void* stream);
+/* Same run with per-role cycle counters: d_prof [n_CTAs(<=160)][vqb200_tc_profile_slots()] uint64, zeroed by
+ * the caller; slot meaning = enum ProfSlot in csrc/tc_kernel.cuh (pipeline bubble analysis for profiles/). */
+int vqb200_debug_tc_profile(const float* d_x, int64_t n_rows, int32_t dim, int32_t n_embed,
+                            const void* d_codebook, float* d_quantize, int64_t* d_embed_ind,
+                            void* d_scratch, uint64_t* d_prof, void* stream);
+int vqb200_tc_profile_slots(void);
 int vqb200_tc_split(void);   /* 3 = split-bf16 filter (default), 1 = plain bf16 (env VQB200_TC_SPLIT) */
 
 /* ---- host-buffer convenience path (what bench.py's `e2e` times) -------------------------------- */

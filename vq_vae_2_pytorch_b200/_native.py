@@ -33,6 +33,8 @@ SIGNATURES = {
     "vqb200_embed_code": (C.c_int, [_p, _i64, _p, _i32, _i32, _p, _p, _p]),
     "vqb200_debug_tc_scores": (C.c_int, [_p, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p]),
     "vqb200_tc_split": (C.c_int, []),
+    "vqb200_debug_tc_profile": (C.c_int, [_p, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p]),
+    "vqb200_tc_profile_slots": (C.c_int, []),
     "vqb200_host_ctx_create": (C.c_int, [_i64, _i32, _i32, C.POINTER(_p)]),
     "vqb200_host_ctx_destroy": (None, [_p]),
     "vqb200_host_quantize": (C.c_int, [_p, _p, _i64, _p, _p, _p, _f32, _f32, _f32, _i32, _p, _p, _p, _i32]),

@@ -62,16 +62,19 @@ struct ForwardScratch {
     double* diff_acc;      // 1 double: sum (q-x)^2
     int* flagged_count;    // 1 int: rows sent to the exact re-score
     int* flagged_rows;     // [n_rows] row ids
+    float* stat_partials;  // [STAT_PARTS][K*(D+1)] per-CTA statistics tables
 };
-__host__ __device__ inline size_t forward_scratch_bytes(int64_t n_rows) {
-    return 256 + align_up((size_t)n_rows * 4, 256);
+constexpr int STAT_PARTS = 160;
+__host__ __device__ inline size_t forward_scratch_bytes(int64_t n_rows, int dim, int n_embed) {
+    return 256 + align_up((size_t)n_rows * 4, 256) + (size_t)STAT_PARTS * n_embed * (dim + 1) * 4;
 }
-__host__ __device__ inline ForwardScratch scratch_view(void* base) {
+__host__ __device__ inline ForwardScratch scratch_view(void* base, int64_t n_rows) {
     unsigned char* p = (unsigned char*)base;
     ForwardScratch s;
     s.diff_acc = (double*)p;
     s.flagged_count = (int*)(p + 16);
     s.flagged_rows = (int*)(p + 256);
+    s.stat_partials = (float*)(p + 256 + align_up((size_t)n_rows * 4, 256));
     return s;
 }
 

@@ -15,8 +15,10 @@
 // E'_ik = cA ||x_i|| ||e_k|| + cB ||e_k||^2 an upper bound of the filter's own error, folded into the
 // contraction.  NSPLIT=1 drops the xl/el blocks (plain bf16 filter, wider bound).
 //
-// Warp roles (448 threads):  w0 bulk-copy producer | w1 MMA issuer + TMEM owner | w2-5 fp32->bf16
-// converters | w6-9 TMEM epilogue (thread = row, top-2 scan) | w10-13 output (gather, STE, loss, stats).
+// Warp roles (640 threads = 5 warpgroups, registers re-balanced with setmaxnreg: 128/128/104/80/40):
+//   WG0, WG1: two epilogue warpgroups, one per TMEM buffer (thread = row; arg-min and the runner-up from a
+//   two-class min scan, ONE ALU op per score) | WG2: output (gather, straight-through value, loss) |
+//   WG3: fp32->bf16 converters | WG4: w16 bulk-copy producer, w17 MMA issuer + TMEM owner (w18-19 idle).
 #pragma once
 #include <cuda_bf16.h>
 
@@ -28,7 +30,12 @@ namespace tc {
 constexpr int TILE_M = 128;        // rows per tile = UMMA M
 constexpr int UNIT_N = 256;        // codes per MMA = UMMA N
 constexpr int TC_D = 64;           // supported dim: one 128-byte swizzle row of bf16
-constexpr int THREADS = 448;
+constexpr int THREADS = 640;        // 5 warpgroups; register budgets re-balanced with setmaxnreg
+// Warp -> role map.  The SM's issue arbiter favours HIGHER warp ids (measured: the warpgroup with the higher
+// ids ran its identical scan 30% faster), so the latency-critical roles sit at the top: the MMA issuer and the
+// producer, then the converters (their latency serialises with the MMAs while A is single-buffered), then
+// the output warps; the two epilogue groups have slack and take what is left.
+constexpr int W_EPI0 = 0, W_EPI1 = 4, W_OUT = 8, W_CONV = 12, W_PROD = 16, W_MMA = 17;
 constexpr int NORM_RING = 8;
 constexpr int RES_RING = 2;
 
@@ -57,9 +64,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        : "=r"(ok) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
     return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
@@ -194,6 +201,109 @@ __global__ void k_tc_image(const float* __restrict__ cbT, const float* __restric
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// epilogue scan of one 256-column accumulator unit (thread = row).
+// Every score feeds two families of running minima: class A = j mod 8 (8 registers) and class B = j div 8
+// (32 registers), each updated with one 3-input minimum per two scores -> ONE ALU op per score, no index
+// bookkeeping in the hot loop.  A and B together identify a column (j = 8 b + a), so afterwards
+//   m1  = the global minimum, found in exactly one A-class a* and one B-class b*  (arg-min = 8 b* + a*),
+//   m2  = min( min over A-classes != a*, min over B-classes != b* ) = the exact runner-up value,
+// because any other column differs from the winner in its A-class or its B-class.  If the minimum value
+// occurs in several classes (exact tie) the row is reported with m2 = m1 and goes to the exact re-score.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float fmin3(float a, float b, float c) { return fminf(a, fminf(b, c)); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t (&v)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                   "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+                 :: "memory");
+}
+
+template <int REGS> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
+template <int REGS> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
+
+__device__ __forceinline__ float min8(const float* e) {
+    return fmin3(fmin3(e[0], e[1], e[2]), fmin3(e[3], e[4], e[5]), fminf(e[6], e[7]));
+}
+
+// 16 scores of columns 16H .. 16H+15: class A = j mod 8 (rA[8]), class B = j div 8 (rB[32])
+template <int H, bool DBG>
+__device__ __forceinline__ void scan_half(const uint32_t (&v)[16], float (&rA)[8], float (&rB)[32], float* dbg) {
+    float key[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) key[i] = __uint_as_float(v[i]);
+    if (DBG && dbg) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) dbg[H * 16 + j] = key[j];
+    }
+#pragma unroll
+    for (int a = 0; a < 8; ++a) rA[a] = fmin3(rA[a], key[a], key[a + 8]);
+    rB[2 * H] = min8(key);
+    rB[2 * H + 1] = min8(key + 8);
+}
+
+// software-pipelined walk over the 16 column groups of a unit: the TMEM load of group H+1 is in flight while
+// group H is reduced (fully unrolled so the 32 class-B minima stay in registers)
+template <int H, bool DBG>
+__device__ __forceinline__ void scan_pairs(uint32_t lane_addr, uint32_t (&va)[16], uint32_t (&vb)[16],
+                                           float (&rA)[8], float (&rB)[32], float* dbg) {
+    tmem_ld_wait16(va);
+    tmem_ld16(lane_addr + (H + 1) * 16, vb);
+    scan_half<H, DBG>(va, rA, rB, dbg);
+    tmem_ld_wait16(vb);
+    if constexpr (H + 2 < 16) tmem_ld16(lane_addr + (H + 2) * 16, va);
+    scan_half<H + 1, DBG>(vb, rA, rB, dbg);
+    if constexpr (H + 2 < 16) scan_pairs<H + 2, DBG>(lane_addr, va, vb, rA, rB, dbg);
+}
+
+// min over the entries != m1, the index of the entry == m1, and how many entries equal m1
+template <int N>
+__device__ __forceinline__ float min_excluding(const float (&r)[N], float m1, int& where, int& hits) {
+    float e[N];
+    where = 0;
+    hits = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const bool eq = (r[i] == m1);
+        e[i] = eq ? INFINITY : r[i];
+        where = eq ? i : where;
+        hits += eq ? 1 : 0;
+    }
+    float m = min8(e);
+#pragma unroll
+    for (int g = 8; g < N; g += 8) m = fminf(m, min8(e + g));
+    return m;
+}
+
+// returns the winning column (0..255) of the unit, its score m1 and the runner-up score m2 (m2 == m1 on exact
+// ties and NaN scores -> never certified)
+template <bool DBG>
+__device__ __forceinline__ int scan_unit(uint32_t lane_addr, float& m1, float& m2, float* dbg) {
+    float rA[8], rB[32];
+#pragma unroll
+    for (int a = 0; a < 8; ++a) rA[a] = INFINITY;
+    uint32_t va[16], vb[16];
+    tmem_ld16(lane_addr, va);
+    scan_pairs<0, DBG>(lane_addr, va, vb, rA, rB, dbg);
+    m1 = min8(rA);
+    int a_star, b_star, hits_a, hits_b;
+    const float ea = min_excluding<8>(rA, m1, a_star, hits_a);
+    const float eb = min_excluding<32>(rB, m1, b_star, hits_b);
+    m2 = fminf(ea, eb);
+    if (hits_a != 1 || hits_b != 1) m2 = m1;
+    return 8 * b_star + a_star;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // shared-memory plan
 // ---------------------------------------------------------------------------------------------------
@@ -207,10 +317,11 @@ struct Plan {
     __host__ __device__ static uint32_t off_a(int K) { return b_bytes(K); }
     __host__ __device__ static uint32_t off_x(int K) { return off_a(K) + AS * A_STAGE; }
     __host__ __device__ static uint32_t off_small(int K) { return off_x(K) + XS * X_STAGE; }
-    // small region: enorm[K] | rownorm[NORM_RING][128] | codes[RES_RING][128] | barriers | tmem ptr
+    // small region: enorm[K] | rownorm[NORM_RING][128] | codes[RES_RING][128] | partials[2][128] | barriers | tmem ptr
     __host__ __device__ static uint32_t off_rownorm(int K) { return off_small(K) + (uint32_t)K * 4u; }
     __host__ __device__ static uint32_t off_codes(int K) { return off_rownorm(K) + NORM_RING * TILE_M * 4u; }
-    __host__ __device__ static uint32_t off_bars(int K) { return off_codes(K) + RES_RING * TILE_M * 4u; }
+    __host__ __device__ static uint32_t off_parts(int K) { return off_codes(K) + RES_RING * TILE_M * 4u; }
+    __host__ __device__ static uint32_t off_bars(int K) { return off_parts(K) + 2u * TILE_M * 16u; }
     __host__ __device__ static uint32_t total(int K) { return off_bars(K) + 512u + 1024u /* base alignment slack */; }
 };
 
@@ -228,12 +339,20 @@ struct Params {
     int* flagged_count;
     int* flagged_rows;
     float* dbg_scores;               // optional [n_rows][K] dump of the tensor-core scores
+    unsigned long long* prof;        // optional [grid][PROF_SLOTS] cycle counters (pipeline bubble analysis)
+    int dbg_skip;                    // DBG builds only: bit0 skip output work, bit1 skip conversion, bit2 skip scan, bit3 skip MMAs
     float cA, cB;
 };
+// profile slots (cycles, summed over the CTA's tiles; one recording lane per role)
+enum ProfSlot { PF_PROD_WAIT_XE = 0, PF_MMA_WAIT_AF, PF_MMA_WAIT_TE, PF_MMA_TOTAL, PF_CONV_WAIT_XF, PF_CONV_WAIT_AE,
+                PF_CONV_TOTAL, PF_EPI0_WAIT_TF, PF_EPI0_SCAN, PF_EPI0_TOTAL, PF_EPI1_WAIT_TF, PF_EPI1_SCAN, PF_EPI1_WAIT_PF,
+                PF_EPI1_WAIT_RE, PF_EPI1_TOTAL, PF_OUT_WAIT_RF, PF_OUT_TOTAL, PF_KERNEL, PF_CONV_LOOP, PF_CONV_TAIL, PF_CONV_FENCE,
+                PROF_SLOTS = 24 };
 
-enum BarId { BAR_B = 0, BAR_XF = 1, BAR_XE = 5, BAR_AF = 9, BAR_AE = 13, BAR_TF = 17, BAR_TE = 19, BAR_RF = 21, BAR_RE = 23, BAR_COUNT = 25 };
+enum BarId { BAR_B = 0, BAR_XF = 1, BAR_XE = 5, BAR_AF = 9, BAR_AE = 13, BAR_TF = 17, BAR_TE = 19, BAR_RF = 21, BAR_RE = 23,
+             BAR_PF = 25, BAR_PE = 27, BAR_COUNT = 29 };
 
-template <int NSPLIT, int AS, int XS>
+template <int NSPLIT, int AS, int XS, bool DBG>
 __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
     using P = Plan<NSPLIT, AS, XS>;
     extern __shared__ unsigned char smem_raw[];
@@ -248,11 +367,27 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
     float* enorm_s = reinterpret_cast<float*>(sm + P::off_small(K));
     float* rownorm_s = reinterpret_cast<float*>(sm + P::off_rownorm(K));
     int* codes_s = reinterpret_cast<int*>(sm + P::off_codes(K));
+    float4* part_s = reinterpret_cast<float4*>(sm + P::off_parts(K));
     const uint32_t bars = base + P::off_bars(K);
     uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(sm + P::off_bars(K) + BAR_COUNT * 8);
     auto bar = [&](int id) { return bars + 8u * (uint32_t)id; };
 
     const int64_t n_tiles = (p.n_rows + TILE_M - 1) / TILE_M;
+    unsigned long long* prof = (DBG && p.prof) ? p.prof + (size_t)blockIdx.x * PROF_SLOTS : nullptr;
+    const long long t_kernel0 = clock64();
+    // timed barrier wait: accumulates the stall into a REGISTER counter when profiling is on (flushed to
+    // global memory once per role, so the instrumentation does not add memory round trips to the pipeline)
+    long long pacc[6] = {0, 0, 0, 0, 0, 0};
+    auto wait_t = [&](int id, uint32_t parity, int acc, bool rec) {
+        if (DBG && prof && rec) {
+            const long long t0 = clock64();
+            mbar_wait(bar(id), parity);
+            pacc[acc] += clock64() - t0;
+        } else {
+            mbar_wait(bar(id), parity);
+        }
+    };
+    auto flush = [&](int slot, int acc) { prof[slot] = (unsigned long long)pacc[acc]; };
 
     // ---- one-time setup -----------------------------------------------------------------------------
     if (threadIdx.x == 0) {
@@ -261,9 +396,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
         for (int s = 0; s < AS; ++s) { mbar_init(bar(BAR_AF + s), 128); mbar_init(bar(BAR_AE + s), 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(bar(BAR_TF + s), 1); mbar_init(bar(BAR_TE + s), 128); }
         for (int s = 0; s < RES_RING; ++s) { mbar_init(bar(BAR_RF + s), 128); mbar_init(bar(BAR_RE + s), 128); }
+        for (int s = 0; s < 2; ++s) { mbar_init(bar(BAR_PF + s), 128); mbar_init(bar(BAR_PE + s), 128); }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(smem_u32(tmem_ptr_s), 512);
+    if (warp == W_MMA) tmem_alloc(smem_u32(tmem_ptr_s), 512);
     // constant part of the A "misc" blocks: [1 1 1 | o1 o2 o3 | nx 1 | 0 x8]; zero chunk 1 once
     for (int i = threadIdx.x; i < AS * TILE_M; i += THREADS) {
         int s = i / TILE_M, r = i % TILE_M;
@@ -271,15 +407,20 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
         *reinterpret_cast<uint4*>(m + sw32_chunk_off((uint32_t)r, 1)) = make_uint4(0, 0, 0, 0);
     }
     fence_async_smem();
-    for (int i = threadIdx.x; i < K; i += THREADS)
-        enorm_s[i] = reinterpret_cast<const float*>(p.image + image_off_enorm(K))[i];
+    int bad = 0;
+    for (int i = threadIdx.x; i < K; i += THREADS) {
+        const float ne = reinterpret_cast<const float*>(p.image + image_off_enorm(K))[i];
+        enorm_s[i] = ne;
+        bad |= !(ne < 1.0e18f);                   // NaN / inf / absurd norms: certify nothing, exact path decides
+    }
     tc_fence_before();
-    __syncthreads();
+    const bool cb_bad = __syncthreads_or(bad) != 0;
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_s;
 
-    if (warp == 0) {
+    if (warp == W_PROD) {
         // ================= bulk-copy producer =========================================================
+        reg_dec<40>();
         if (lane == 0) {
             const uint32_t bbytes = P::b_bytes(K);
             mbar_expect_tx(bar(BAR_B), bbytes);
@@ -290,28 +431,31 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
             uint32_t it = 0;
             for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
                 const uint32_t s = it % XS, ph = (it / XS) & 1u;
-                mbar_wait(bar(BAR_XE + s), ph ^ 1u);
+                wait_t(BAR_XE + s, ph ^ 1u, 0, true);
                 const int64_t r0 = t * TILE_M;
                 const uint32_t rows = (uint32_t)min((int64_t)TILE_M, p.n_rows - r0);
                 const uint32_t bytes = rows * TC_D * 4u;
                 mbar_expect_tx(bar(BAR_XF + s), bytes);
                 bulk_g2s(sX + s * P::X_STAGE, p.x + r0 * TC_D, bytes, bar(BAR_XF + s));
             }
+            if (DBG && prof) flush(PF_PROD_WAIT_XE, 0);
         }
-    } else if (warp == 1) {
+    } else if (warp == W_MMA) {
         // ================= MMA issuer ==================================================================
+        reg_dec<40>();
         mbar_wait(bar(BAR_B), 0);
+        const long long t_role0 = clock64();
         uint32_t it = 0, uc = 0;
         for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
             const uint32_t sa = it % AS, pha = (it / AS) & 1u;
-            mbar_wait(bar(BAR_AF + sa), pha);
+            wait_t(BAR_AF + sa, pha, 0, lane == 0);
             tc_fence_after();
             const uint32_t a0 = sA + sa * P::A_STAGE;
             for (int u = 0; u < U; ++u, ++uc) {
                 const uint32_t buf = uc & 1u, pht = (uc >> 1) & 1u;
-                mbar_wait(bar(BAR_TE + buf), pht ^ 1u);
+                wait_t(BAR_TE + buf, pht ^ 1u, 1, lane == 0);
                 tc_fence_after();
-                if (lane == 0) {
+                if (lane == 0 && !(DBG && (p.dbg_skip & 8))) {
                     const uint32_t d_tmem = tmem_base + buf * UNIT_N;
                     const uint32_t b_hi = sB + (uint32_t)u * UNIT_N * 128u;
                     const uint32_t b_lo = sB + P::off_b_lo(K) + (uint32_t)u * UNIT_N * 128u;
@@ -332,40 +476,74 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
                             umma_bf16(d_tmem, desc_sw128(a0) + 2u * ks, desc_sw128(b_lo) + 2u * ks, IDESC, acc);
                     }
                     umma_commit(bar(BAR_TF + buf));
+                } else if (lane == 0) {
+                    umma_commit(bar(BAR_TF + buf));
                 }
                 __syncwarp();
             }
             if (lane == 0) umma_commit(bar(BAR_AE + sa));
             __syncwarp();
         }
-    } else if (warp < 6) {
+        if (DBG && prof && lane == 0) { flush(PF_MMA_WAIT_AF, 0); flush(PF_MMA_WAIT_TE, 1); prof[PF_MMA_TOTAL] = (unsigned long long)(clock64() - t_role0); }
+    } else if (warp > W_MMA) {
+        reg_dec<40>();                           // spare warps of the producer/MMA warpgroup
+    } else if (warp >= W_CONV) {
         // ================= converters: fp32 rows -> split-bf16 K-major operand ==========================
-        const int cw = warp - 2;                 // rows cw*32 .. cw*32+31
+        reg_dec<80>();
+        const int cw = warp - W_CONV;            // rows cw*32 .. cw*32+31
         const int half = lane >> 4, q4 = lane & 15;
+        const bool rec = (warp == W_CONV && lane == 0);
+        const long long t_role0 = clock64();
         uint32_t it = 0;
         for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
             const uint32_t sx = it % XS, phx = (it / XS) & 1u, sa = it % AS, pha = (it / AS) & 1u;
-            mbar_wait(bar(BAR_XF + sx), phx);
-            mbar_wait(bar(BAR_AE + sa), pha ^ 1u);
+            wait_t(BAR_XF + sx, phx, 0, rec);
+            wait_t(BAR_AE + sa, pha ^ 1u, 1, rec);
             const unsigned char* xs = sm + P::off_x(K) + sx * P::X_STAGE;
             unsigned char* ah = sm + P::off_a(K) + sa * P::A_STAGE;
             unsigned char* al = ah + 16384u;
             unsigned char* am = ah + (P::A_STAGE - 4096u);
-            float my_sq = 0.f;
-#pragma unroll 4
-            for (int i = 0; i < 16; ++i) {
-                const int r = cw * 32 + 2 * i + half;
-                const float4 v = *reinterpret_cast<const float4*>(xs + r * 256 + q4 * 16);
-                const float h0 = bf16_round(v.x), h1 = bf16_round(v.y), h2 = bf16_round(v.z), h3 = bf16_round(v.w);
-                const uint32_t off = sw128_off((uint32_t)r, (uint32_t)q4 * 4);
-                *reinterpret_cast<uint2*>(ah + off) = make_uint2(pack_bf16(h0, h1), pack_bf16(h2, h3));
-                if (NSPLIT == 3)
-                    *reinterpret_cast<uint2*>(al + off) = make_uint2(pack_bf16(v.x - h0, v.y - h1), pack_bf16(v.z - h2, v.w - h3));
-                float sq = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)));
+            const long long tc0 = (DBG && prof && rec) ? clock64() : 0;
+            float my_sq = 1.f;
+            if (!(DBG && (p.dbg_skip & 2))) {
+#pragma unroll 1
+                for (int g8 = 0; g8 < 2; ++g8) {          // 8 row pairs per trip (8 independent 16-byte smem loads in flight)
+                    float4 v[8];
+                    float sq[8];
 #pragma unroll
-                for (int o = 8; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-                if (q4 == i) my_sq = sq;          // lane (half, q4=i) keeps row cw*32 + 2i + half
+                    for (int u = 0; u < 8; ++u)
+                        v[u] = *reinterpret_cast<const float4*>(xs + (cw * 32 + 2 * (8 * g8 + u) + half) * 256 + q4 * 16);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int r = cw * 32 + 2 * (8 * g8 + u) + half;
+                        const uint32_t p01 = pack_bf16(v[u].x, v[u].y), p23 = pack_bf16(v[u].z, v[u].w);
+                        const uint32_t off = sw128_off((uint32_t)r, (uint32_t)q4 * 4);
+                        *reinterpret_cast<uint2*>(ah + off) = make_uint2(p01, p23);
+                        if (NSPLIT == 3) {
+                            const float h0 = __uint_as_float(p01 << 16), h1 = __uint_as_float(p01 & 0xFFFF0000u);
+                            const float h2 = __uint_as_float(p23 << 16), h3 = __uint_as_float(p23 & 0xFFFF0000u);
+                            *reinterpret_cast<uint2*>(al + off) =
+                                make_uint2(pack_bf16(v[u].x - h0, v[u].y - h1), pack_bf16(v[u].z - h2, v[u].w - h3));
+                        }
+                        sq[u] = fmaf(v[u].x, v[u].x, fmaf(v[u].y, v[u].y, fmaf(v[u].z, v[u].z, v[u].w * v[u].w)));
+                    }
+                    // transposing butterfly over lane bits 2,1,0 (8 values -> 1), then a plain sum over bit 3:
+                    // every lane ends with the full row sum of row pair 8*g8 + (q4 & 7)
+#pragma unroll
+                    for (int w = 4; w >= 1; w >>= 1) {
+                        const bool up = (q4 & w) != 0;
+#pragma unroll
+                        for (int i = 0; i < w; ++i) {
+                            const float send = up ? sq[i] : sq[i + w];
+                            const float keep = up ? sq[i + w] : sq[i];
+                            sq[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+                        }
+                    }
+                    const float tot = sq[0] + __shfl_xor_sync(0xffffffffu, sq[0], 8);
+                    if ((q4 >> 3) == g8) my_sq = tot;
+                }
             }
+            const long long tc1 = (DBG && prof && rec) ? clock64() : 0;
             {
                 const int r = cw * 32 + 2 * q4 + half;
                 const float nx = sqrtf(my_sq);
@@ -376,72 +554,66 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
                     make_uint4(pack_bf16(1.f, 1.f), pack_bf16(1.f, o1), pack_bf16(o2, o3), pack_bf16(nxu, 1.f));
                 rownorm_s[(it % NORM_RING) * TILE_M + r] = nx;
             }
+            const long long tc2 = (DBG && prof && rec) ? clock64() : 0;
             fence_async_smem();
             mbar_arrive(bar(BAR_AF + sa));
             mbar_arrive(bar(BAR_XE + sx));
+            if (DBG && prof && rec) {
+                const long long tc3 = clock64();
+                pacc[2] += tc1 - tc0; pacc[3] += tc2 - tc1; pacc[4] += tc3 - tc2;
+            }
         }
-    } else if (warp < 10) {
-        // ================= epilogue: TMEM -> top-2 scan -> certified arg-min ============================
+        if (DBG && prof && rec) { flush(PF_CONV_WAIT_XF, 0); flush(PF_CONV_WAIT_AE, 1); flush(PF_CONV_LOOP, 2); flush(PF_CONV_TAIL, 3); flush(PF_CONV_FENCE, 4); prof[PF_CONV_TOTAL] = (unsigned long long)(clock64() - t_role0); }
+    } else if (warp < W_OUT) {
+        // ================= epilogue: TMEM -> two-class min scan -> certified arg-min =====================
+        // warpgroup g owns TMEM buffer g.  n_embed = 512: unit 0 of every tile lands in buffer 0, unit 1 in
+        // buffer 1, so both groups work on the same tile and group 1 merges.  n_embed = 256: tiles alternate.
+        reg_inc<128>();
+        const int g = warp >> 2;
         const int wq = warp & 3;                 // TMEM lane quarter this warp may access
         const int row_in_tile = wq * 32 + lane;
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(wq * 32) << 16);
-        uint32_t it = 0, uc = 0;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)g * UNIT_N;
+        const bool rec = ((warp & 3) == 0 && lane == 0);      // first warp of each group
+        const int pbase = g ? PF_EPI1_WAIT_TF : PF_EPI0_WAIT_TF;
+        const long long t_role0 = clock64();
+        uint32_t it = 0;
         for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-            float m1 = INFINITY, m2 = INFINITY, pm1 = INFINITY;
-            int cbest = 0;
+            if (U == 1 && (int)(it & 1u) != g) continue;
+            const uint32_t pht = (U == 2) ? (it & 1u) : ((it >> 1) & 1u);
             const int64_t grow = t * TILE_M + row_in_tile;
-            for (int u = 0; u < U; ++u, ++uc) {
-                const uint32_t buf = uc & 1u, pht = (uc >> 1) & 1u;
-                mbar_wait(bar(BAR_TF + buf), pht);
-                tc_fence_after();
-                uint32_t va[32], vb[32];
-                tmem_ld32(lane_addr + buf * UNIT_N, va);
-#pragma unroll
-                for (int c = 0; c < 8; c += 2) {
-                    tmem_ld_wait(va);
-                    tmem_ld32(lane_addr + buf * UNIT_N + (c + 1) * 32, vb);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float kf = __uint_as_float((va[j] & 0xFFFFFFE0u) | (uint32_t)j);
-                        const float tmx = fmaxf(m1, kf);
-                        m1 = fminf(m1, kf);
-                        m2 = fminf(m2, tmx);
-                    }
-                    if (m1 != pm1) { cbest = u * 8 + c; pm1 = m1; }
-                    if (p.dbg_scores && grow < p.n_rows) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) p.dbg_scores[grow * K + u * UNIT_N + c * 32 + j] = __uint_as_float(va[j]);
-                    }
-                    tmem_ld_wait(vb);
-                    if (c + 2 < 8) tmem_ld32(lane_addr + buf * UNIT_N + (c + 2) * 32, va);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float kf = __uint_as_float((vb[j] & 0xFFFFFFE0u) | (uint32_t)j);
-                        const float tmx = fmaxf(m1, kf);
-                        m1 = fminf(m1, kf);
-                        m2 = fminf(m2, tmx);
-                    }
-                    if (m1 != pm1) { cbest = u * 8 + c + 1; pm1 = m1; }
-                    if (p.dbg_scores && grow < p.n_rows) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) p.dbg_scores[grow * K + u * UNIT_N + (c + 1) * 32 + j] = __uint_as_float(vb[j]);
-                    }
+            wait_t(BAR_TF + g, pht, 0, rec);
+            tc_fence_after();
+            float m1, m2;
+            const long long t_scan0 = clock64();
+            int jbest = 0;
+            if (DBG && (p.dbg_skip & 4)) { m1 = 1.f; m2 = 1e9f; } else
+            jbest = scan_unit<DBG>(lane_addr, m1, m2, (DBG && p.dbg_scores && grow < p.n_rows) ? p.dbg_scores + grow * K + g * (U == 2 ? UNIT_N : 0) : nullptr);
+            if (DBG && prof && rec) pacc[1] += clock64() - t_scan0;
+            tc_fence_before();
+            mbar_arrive(bar(BAR_TE + g));
+            int k1 = jbest;
+            if (U == 2) {
+                const uint32_t ps = it & 1u, php = (it >> 1) & 1u;
+                if (g == 0) {                    // hand the unit-0 result to group 1
+                    mbar_wait(bar(BAR_PE + ps), php ^ 1u);
+                    part_s[ps * TILE_M + row_in_tile] = make_float4(m1, m2, __int_as_float(jbest), 0.f);
+                    mbar_arrive(bar(BAR_PF + ps));
+                    continue;
                 }
-                tc_fence_before();
-                mbar_arrive(bar(BAR_TE + buf));
+                wait_t(BAR_PF + ps, php, 2, rec);
+                const float4 o = part_s[ps * TILE_M + row_in_tile];
+                mbar_arrive(bar(BAR_PE + ps));
+                m2 = fminf(fminf(o.y, m2), fmaxf(o.x, m1));
+                if (m1 < o.x) { k1 = UNIT_N + jbest; } else { m1 = o.x; k1 = __float_as_int(o.z); }   // tie: lower unit, gap 0 -> flagged
             }
             // certificate: every other code's lower bound must clear the winner's upper bound
-            const uint32_t m1b = __float_as_uint(m1);
-            const int k1 = cbest * 32 + (int)(m1b & 31u);
-            const float v1 = __uint_as_float(m1b & 0xFFFFFFE0u);
             const float xn = rownorm_s[(it % NORM_RING) * TILE_M + row_in_tile];
             const float en = enorm_s[k1 < K ? k1 : 0];
-            const float need = 2.f * (p.cA * BOUND_UP * xn * en + p.cB * (BOUND_UP * en * en + xn * xn)) +
-                               (fabsf(m1) + fabsf(m2)) * 3.814697265625e-6f;      // packing truncation, 2^-18 each
-            const bool certified = (m2 - v1) > need;                                // NaN -> false
+            const float need = 2.f * (p.cA * BOUND_UP * xn * en + p.cB * (BOUND_UP * en * en + xn * xn));
+            const bool certified = ((m2 - m1) > need) && (xn < 1.0e18f) && !cb_bad;   // NaN -> false
             const bool in_range = grow < p.n_rows;
             const uint32_t rs = it % RES_RING, phr = (it / RES_RING) & 1u;
-            mbar_wait(bar(BAR_RE + rs), phr ^ 1u);
+            wait_t(BAR_RE + rs, phr ^ 1u, 3, rec);
             int code = -2;
             if (in_range) {
                 code = certified ? k1 : -1;
@@ -458,39 +630,44 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
             }
             mbar_arrive(bar(BAR_RF + rs));
         }
+        if (DBG && prof && rec) { flush(pbase, 0); flush(pbase + 1, 1); if (g) { flush(PF_EPI1_WAIT_PF, 2); flush(PF_EPI1_WAIT_RE, 3); } prof[g ? PF_EPI1_TOTAL : PF_EPI0_TOTAL] = (unsigned long long)(clock64() - t_role0); }
     } else {
-        // ================= output: gather, straight-through value, loss, statistics ====================
-        const int ow = warp - 10;                // rows ow*32 .. ow*32+31 of the tile
+        // ================= output: gather, straight-through value, loss =================================
+        reg_inc<104>();
+        const int ow = warp - W_OUT;             // rows ow*32 .. ow*32+31 of the tile
         const int half = lane >> 4, q4 = lane & 15;
         float dacc = 0.f;
+        const bool rec = (warp == W_OUT && lane == 0);
+        const long long t_role0 = clock64();
         uint32_t it = 0;
         for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
             const uint32_t rs = it % RES_RING, phr = (it / RES_RING) & 1u;
-            mbar_wait(bar(BAR_RF + rs), phr);
+            wait_t(BAR_RF + rs, phr, 0, rec);
             const int64_t r0 = t * TILE_M;
+            if (!(DBG && (p.dbg_skip & 1)))
+#pragma unroll 1
+            for (int b = 0; b < 2; ++b) {        // 16 rows per batch: 16 independent 16-byte loads in flight per lane
+                int kk[8];
+                float4 xv[8], qv[8];
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                int kk[4];
-                float4 xv[4], qv[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int r = ow * 32 + b * 8 + i * 2 + half;
+                for (int i = 0; i < 8; ++i) {
+                    const int r = ow * 32 + b * 16 + i * 2 + half;
                     kk[i] = codes_s[rs * TILE_M + r];
-                    if (kk[i] >= 0) {
-                        xv[i] = *reinterpret_cast<const float4*>(p.x + (r0 + r) * TC_D + q4 * 4);
-                        qv[i] = __ldg(reinterpret_cast<const float4*>(p.cbT + (size_t)kk[i] * TC_D + q4 * 4));
-                    }
+                    if (kk[i] >= 0) xv[i] = __ldcg(reinterpret_cast<const float4*>(p.x + (r0 + r) * TC_D + q4 * 4));
                 }
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
+                for (int i = 0; i < 8; ++i)
+                    if (kk[i] >= 0) qv[i] = __ldcg(reinterpret_cast<const float4*>(p.cbT + (size_t)kk[i] * TC_D + q4 * 4));
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
                     if (kk[i] < 0) continue;
-                    const int r = ow * 32 + b * 8 + i * 2 + half;
+                    const int r = ow * 32 + b * 16 + i * 2 + half;
                     float4 d, o;
                     d.x = qv[i].x - xv[i].x; d.y = qv[i].y - xv[i].y; d.z = qv[i].z - xv[i].z; d.w = qv[i].w - xv[i].w;
                     o.x = xv[i].x + d.x; o.y = xv[i].y + d.y; o.z = xv[i].z + d.z; o.w = xv[i].w + d.w;
                     dacc = fmaf(d.x, d.x, fmaf(d.y, d.y, fmaf(d.z, d.z, fmaf(d.w, d.w, dacc))));
                     if (p.quantize) __stcs(reinterpret_cast<float4*>(p.quantize + (r0 + r) * TC_D + q4 * 4), o);
-                    if (p.stat_sums) {
+                    if (p.stat_sums) {           // only when the caller has no room for the segmented-reduction kernel
                         red_add_v4(p.stat_sums + (size_t)kk[i] * TC_D + q4 * 4, xv[i]);
                         if (q4 == 0) red_add_f32(p.stat_counts + kk[i], 1.0f);
                     }
@@ -498,6 +675,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
             }
             mbar_arrive(bar(BAR_RE + rs));
         }
+        if (DBG && prof && rec) { flush(PF_OUT_WAIT_RF, 0); prof[PF_OUT_TOTAL] = (unsigned long long)(clock64() - t_role0); }
         if (p.diff_acc) {
             dacc = warp_sum(dacc);
             if (lane == 0) atomicAdd(p.diff_acc, (double)dacc);
@@ -507,7 +685,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
     // ---- teardown -------------------------------------------------------------------------------------
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 512);
+    if (warp == W_MMA) tmem_dealloc(tmem_base, 512);
+    if (DBG && prof && threadIdx.x == 0) prof[PF_KERNEL] = (unsigned long long)(clock64() - t_kernel0);
 }
 
 }  // namespace tc
@@ -550,10 +729,10 @@ inline int tc_prepare_codebook(const CodebookImage& cb, int dim, int n_embed, cu
     return cudaGetLastError() != cudaSuccess;
 }
 
-template <int NSPLIT, int AS, int XS>
+template <int NSPLIT, int AS, int XS, bool DBG>
 inline int tc_launch(const tc::Params& prm, cudaStream_t st) {
     using P = tc::Plan<NSPLIT, AS, XS>;
-    auto kern = tc::k_vq_tc<NSPLIT, AS, XS>;
+    auto kern = tc::k_vq_tc<NSPLIT, AS, XS, DBG>;
     const int smem = (int)P::total(prm.K);
     static int configured = 0;
     if (configured < smem) {
@@ -569,16 +748,20 @@ inline int tc_launch(const tc::Params& prm, cudaStream_t st) {
 // main kernel only; the caller runs the exact fix-up over the flagged rows afterwards
 inline int tc_forward(const float* x, const RowLayout& L, int dim, int n_embed, const CodebookImage& cb,
                       float* quantize, int64_t* embed_ind, const ForwardScratch& sc, double* diff_acc,
-                      float* sums, float* counts, float* dbg_scores, cudaStream_t st) {
+                      float* sums, float* counts, float* dbg_scores, cudaStream_t st,
+                      unsigned long long* prof = nullptr) {
     (void)dim;
     tc::Params prm;
     prm.x = x; prm.n_rows = L.n_rows; prm.K = n_embed; prm.image = cb.tc; prm.cbT = cb.cbT;
     prm.quantize = quantize; prm.embed_ind = embed_ind; prm.diff_acc = diff_acc;
     prm.stat_sums = sums; prm.stat_counts = counts;
     prm.flagged_count = sc.flagged_count; prm.flagged_rows = sc.flagged_rows; prm.dbg_scores = dbg_scores;
+    prm.prof = prof;
+    { const char* e = getenv("VQB200_DBG_SKIP"); prm.dbg_skip = e ? atoi(e) : 0; }
     prm.cA = tc::bound_cA(tc_nsplit()); prm.cB = tc::BOUND_CB;
-    if (tc_nsplit() == 3) return tc_launch<3, 1, 1>(prm, st);
-    return tc_launch<1, 2, 2>(prm, st);
+    const bool dbg = dbg_scores || prof;           // diagnostics live in a separate instantiation
+    if (tc_nsplit() == 3) return dbg ? tc_launch<3, 1, 1, true>(prm, st) : tc_launch<3, 1, 1, false>(prm, st);
+    return dbg ? tc_launch<1, 2, 2, true>(prm, st) : tc_launch<1, 2, 2, false>(prm, st);
 }
 
 }  // namespace vqb200

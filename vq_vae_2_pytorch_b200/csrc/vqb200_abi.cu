@@ -64,9 +64,10 @@ int prepare_codebook(const float* d_embed, int dim, int n_embed, void* d_codeboo
 int forward_impl(const float* d_x, const RowLayout& L, int dim, int n_embed, const void* d_codebook,
                  float* d_quantize, int64_t* d_ind, float* d_diff, float* d_stats, void* d_scratch,
                  int engine, bool zero_first, bool finalize, int64_t total_rows, cudaStream_t st,
-                 float* dbg_scores = nullptr) {
+                 float* dbg_scores = nullptr, int64_t scratch_rows = -1, unsigned long long* prof = nullptr) {
+    if (scratch_rows < 0) scratch_rows = total_rows;
     CodebookImage cb = codebook_view(const_cast<void*>(d_codebook), dim, n_embed);
-    ForwardScratch sc = scratch_view(d_scratch);
+    ForwardScratch sc = scratch_view(d_scratch, scratch_rows);
     float* sums = d_stats;
     float* counts = d_stats ? d_stats + (size_t)n_embed * dim : nullptr;
     if (zero_first) {
@@ -78,7 +79,12 @@ int forward_impl(const float* d_x, const RowLayout& L, int dim, int n_embed, con
         if (engine == VQB200_ENGINE_TCGEN05 || engine == VQB200_ENGINE_AUTO)
             use_tc = tc_supported(L, d_x, dim, n_embed);
         if (engine == VQB200_ENGINE_TCGEN05 && !use_tc) return VQB200_EUNSUPPORTED;
-        const bool want_gather = d_quantize || d_diff || d_stats;
+        // statistics: private-table segmented reduction when [K][D] fp32 fits in shared memory, else the
+        // gather kernels fall back to global atomics
+        const size_t cs_smem = code_stats_smem_bytes(dim, n_embed);
+        const bool stats_kernel = d_stats && cs_smem <= 200 * 1024 && n_embed <= 65535;
+        if (stats_kernel) { sums = nullptr; counts = nullptr; }
+        const bool want_gather = d_quantize || d_diff || sums;
         const size_t gsmem = (size_t)GS_BM * (dim + 1) * sizeof(float);
         if (gsmem > 200 * 1024) return VQB200_EUNSUPPORTED;
         if (gsmem > 48 * 1024)
@@ -88,7 +94,7 @@ int forward_impl(const float* d_x, const RowLayout& L, int dim, int n_embed, con
             // tensor-core filter + fused output for certified rows; flagged rows -> exact SIMT fix-up
             VQ_CUDA(cudaMemsetAsync(sc.flagged_count, 0, sizeof(int), st));
             int rc = tc_forward(d_x, L, dim, n_embed, cb, d_quantize, d_ind, sc, d_diff ? sc.diff_acc : nullptr, sums,
-                                counts, dbg_scores, st);
+                                counts, dbg_scores, st, prof);
             g_launches.fetch_add(1);
             if (rc) return cuda_fail(cudaGetLastError());
             k_assign_exact<<<sms * 2, AS_THREADS, 0, st>>>(d_x, L, dim, n_embed, cb.cbT, cb.ee, d_ind,
@@ -112,6 +118,24 @@ int forward_impl(const float* d_x, const RowLayout& L, int dim, int n_embed, con
                     nullptr, nullptr);
                 VQ_LAUNCH_CHECK();
             }
+        }
+    }
+    if (L.n_rows > 0 && d_stats) {
+        const size_t cs_smem = code_stats_smem_bytes(dim, n_embed);
+        if (cs_smem <= 200 * 1024 && n_embed <= 65535) {
+            // accumulate into d_stats across calls when zero_first == false (host-buffer chunking)
+            VQ_CUDA(cudaFuncSetAttribute(k_code_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs_smem));
+            int64_t n_chunks = (L.n_rows + CS_CHUNK - 1) / CS_CHUNK;
+            int parts = (int)std::min<int64_t>(std::min<int64_t>(n_chunks, tc_num_sms()), STAT_PARTS - 1);
+            k_code_stats<<<parts, CS_THREADS, cs_smem, st>>>(d_x, L, dim, n_embed, d_ind, sc.stat_partials);
+            VQ_LAUNCH_CHECK();
+            int n = n_embed * (dim + 1);
+            // the running total lives in partial slot [parts] so chunked calls keep accumulating
+            float* prev = sc.stat_partials + (size_t)parts * n;
+            if (zero_first) VQ_CUDA(cudaMemsetAsync(prev, 0, (size_t)n * 4, st));
+            else VQ_CUDA(cudaMemcpyAsync(prev, d_stats, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+            k_stats_reduce<<<(n + 255) / 256, 256, 0, st>>>(sc.stat_partials, parts + 1, n, d_stats);
+            VQ_LAUNCH_CHECK();
         }
     }
     if (finalize && d_diff) {
@@ -168,9 +192,9 @@ size_t vqb200_codebook_bytes(int32_t dim, int32_t n_embed) {
     return codebook_bytes(dim, n_embed);
 }
 size_t vqb200_forward_scratch_bytes(int64_t n_rows, int32_t dim, int32_t n_embed) {
-    (void)dim; (void)n_embed;
     if (n_rows < 0) return 0;
-    return forward_scratch_bytes(n_rows);
+    if (dim <= 0 || n_embed <= 0) return 0;
+    return forward_scratch_bytes(n_rows, dim, n_embed);
 }
 size_t vqb200_stats_bytes(int32_t dim, int32_t n_embed) {
     if (dim <= 0 || n_embed <= 0) return 0;
@@ -250,12 +274,23 @@ int vqb200_debug_tc_scores(const float* d_x, int64_t n_rows, int32_t dim, int32_
                           VQB200_ENGINE_TCGEN05, true, false, n_rows, st, d_scores);
     if (rc) return rc;
     if (d_flagged_count)
-        VQ_CUDA(cudaMemcpyAsync(d_flagged_count, scratch_view(d_scratch).flagged_count, sizeof(int),
+        VQ_CUDA(cudaMemcpyAsync(d_flagged_count, scratch_view(d_scratch, n_rows).flagged_count, sizeof(int),
                                 cudaMemcpyDeviceToDevice, st));
     return VQB200_OK;
 }
 
 int vqb200_tc_split(void) { return tc_nsplit(); }
+
+int vqb200_debug_tc_profile(const float* d_x, int64_t n_rows, int32_t dim, int32_t n_embed, const void* d_codebook,
+                            float* d_quantize, int64_t* d_embed_ind, void* d_scratch, uint64_t* d_prof, void* stream) {
+    if (!d_x || !d_codebook || !d_embed_ind || !d_scratch || !d_prof || n_rows <= 0) return VQB200_EINVAL;
+    RowLayout L{n_rows, n_rows, 0, dim, 1};
+    if (!tc_supported(L, d_x, dim, n_embed)) return VQB200_EUNSUPPORTED;
+    return forward_impl(d_x, L, dim, n_embed, d_codebook, d_quantize, d_embed_ind, nullptr, nullptr, d_scratch,
+                        VQB200_ENGINE_TCGEN05, true, false, n_rows, (cudaStream_t)stream, nullptr, -1,
+                        reinterpret_cast<unsigned long long*>(d_prof));
+}
+int vqb200_tc_profile_slots(void) { return (int)tc::PROF_SLOTS; }
 
 // ---- host-buffer path ----------------------------------------------------------------------------
 struct vqb200_host_ctx {
@@ -292,7 +327,7 @@ int vqb200_host_ctx_create(int64_t max_rows, int32_t dim, int32_t n_embed, vqb20
     VQ_CTX(cudaMalloc(&c->d_ind, (size_t)max_rows * 8));
     VQ_CTX(cudaMalloc(&c->d_diff, 256));
     VQ_CTX(cudaMalloc(&c->d_stats, vqb200_stats_bytes(dim, n_embed)));
-    VQ_CTX(cudaMalloc(&c->d_scratch, forward_scratch_bytes(max_rows)));
+    VQ_CTX(cudaMalloc(&c->d_scratch, forward_scratch_bytes(max_rows, dim, n_embed)));
     VQ_CTX(cudaMalloc(&c->d_codebook, codebook_bytes(dim, n_embed)));
     VQ_CTX(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
     VQ_CTX(cudaStreamCreateWithFlags(&c->s_run, cudaStreamNonBlocking));
@@ -344,7 +379,7 @@ int vqb200_host_quantize(vqb200_host_ctx* c, const float* h_x, int64_t n_rows, f
         RowLayout L{rows, rows > 0 ? rows : 1, 0, D, 1};
         rc = forward_impl(c->d_x + r0 * D, L, D, K, c->d_codebook, h_quantize ? c->d_q + r0 * D : nullptr,
                           c->d_ind + r0, c->d_diff, stats, c->d_scratch, engine, i == 0, i == nchunks - 1, n_rows,
-                          c->s_run);
+                          c->s_run, nullptr, c->max_rows);
         if (rc) return rc;
         if (rows > 0) {
             VQ_CUDA(cudaEventRecord(c->ev_run[i], c->s_run));
