@@ -231,27 +231,44 @@ def main():
     reset()
     _native.check(lib.vqb200_codebook_prepare(_native.ptr(q.embed), D, K, _native.ptr(ws["image"]), stream), "prepare")
 
-    def fwd_only(i):
+    def fwd_only(i, with_stats):
         _native.check(lib.vqb200_quantize_forward(_native.ptr(xs[i % 3]), N_ROWS, D, K, N_ROWS, 0, D, 1,
                                                   _native.ptr(ws["image"]), _native.ptr(quant), _native.ptr(ind),
-                                                  _native.ptr(diff), _native.ptr(ws["stats"]), _native.ptr(ws["scratch"]),
-                                                  eng, stream), "forward")
-    for i in range(3):
-        fwd_only(i)
-    torch.cuda.synchronize()
-    ka, kb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ka.record()
-    for i in range(steps):
-        fwd_only(i)
-    kb.record()
-    torch.cuda.synchronize()
-    fwd_ms = ka.elapsed_time(kb) / steps
+                                                  _native.ptr(diff), _native.ptr(ws["stats"]) if with_stats else None,
+                                                  _native.ptr(ws["scratch"]), eng, stream), "forward")
+
+    def time_fwd(with_stats):
+        for i in range(3):
+            fwd_only(i, with_stats)
+        torch.cuda.synchronize()
+        ka, kb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ka.record()
+        for i in range(steps):
+            fwd_only(i, with_stats)
+        kb.record()
+        torch.cuda.synchronize()
+        return ka.elapsed_time(kb) / steps
+
+    # dominant kernel = the fused assignment+gather+loss kernel (tc::k_vq_tc; the call also issues two fix-up launches
+    # that exit immediately when no row was flagged, and the 1-thread loss finalisation)
+    fwd_ms = time_fwd(False)
+    fwd_stats_ms = time_fwd(True)
     algo_bytes = N_ROWS * (8 * D + 8)
     achieved = algo_bytes / (fwd_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r01_dram_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("k_vq_tc_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "vqb200_quantize_forward (assignment+gather+diff+stats)",
+                "traffic": traffic, "kernel": "tc::k_vq_tc via vqb200_quantize_forward (assignment+gather+loss; statistics off)",
                 "launch_ms": fwd_ms, "algorithmic_bytes": algo_bytes, "peak_source": peak_src,
-                "tensor_flops": 2.0 * N_ROWS * D * K, "tensor_tflops_achieved": 2.0 * N_ROWS * D * K / (fwd_ms * 1e-3) / 1e12}
+                "tensor_flops": 2.0 * N_ROWS * D * K, "tensor_tflops_achieved": 2.0 * N_ROWS * D * K / (fwd_ms * 1e-3) / 1e12,
+                "tensor_frac_of_measured_bf16_peak": 2.0 * N_ROWS * D * K / (fwd_ms * 1e-3) / 1e12 / 1659.1,
+                "statistics_kernels_ms": max(fwd_stats_ms - fwd_ms, 0.0),
+                "statistics_algorithmic_bytes": N_ROWS * (4 * D + 8)}
 
     # ---- e2e through the host-buffer C ABI (pinned host in / out, copies inside the timed region)
     e2e = None

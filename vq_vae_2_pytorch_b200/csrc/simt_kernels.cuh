@@ -216,11 +216,11 @@ k_gather_stats(const float* __restrict__ x, RowLayout L, int D, int K,
 // tables are written out and folded by k_stats_reduce in a fixed order.
 // (Global fp32 atomics top out near 170 G adds/s on B200: N*D = 33.5 M adds cost ~200 us at cfg-2.)
 // ------------------------------------------------------------------------------------------------
-constexpr int CS_THREADS = 1024, CS_CHUNK = 2048, CS_MAX_CTAS = 160;
+constexpr int CS_THREADS = 1024, CS_CHUNK = 4096, CS_MAX_CTAS = 160;
 
 __global__ void __launch_bounds__(CS_THREADS, 1)
 k_code_stats(const float* __restrict__ x, RowLayout L, int D, int K, const int64_t* __restrict__ embed_ind,
-             float* __restrict__ partials /* [gridDim.x][K*(D+1)] */) {
+             float* __restrict__ partials /* [gridDim.x][K*(D+1)] */, int chunk /* rows per trip, <= CS_CHUNK */) {
     extern __shared__ float cs_smem[];
     float* table = cs_smem;                                   // [K][D]
     int* cnt_total = reinterpret_cast<int*>(table + (size_t)K * D);   // [K]
@@ -234,12 +234,12 @@ k_code_stats(const float* __restrict__ x, RowLayout L, int D, int K, const int64
 
     for (int i = tid; i < K * D; i += CS_THREADS) table[i] = 0.f;
     for (int i = tid; i < K; i += CS_THREADS) cnt_total[i] = 0;
-    const int64_t n_chunks = (L.n_rows + CS_CHUNK - 1) / CS_CHUNK;
+    const int64_t n_chunks = (L.n_rows + chunk - 1) / chunk;
     // walk the chunks from the END of x: those rows were touched last by the assignment kernel and are
     // the most likely to still sit in L2
     for (int64_t j = n_chunks - 1 - blockIdx.x; j >= 0; j -= gridDim.x) {
-        const int64_t r0 = j * CS_CHUNK;
-        const int rows = (int)min((int64_t)CS_CHUNK, L.n_rows - r0);
+        const int64_t r0 = j * chunk;
+        const int rows = (int)min((int64_t)chunk, L.n_rows - r0);
         __syncthreads();
         for (int i = tid; i < K; i += CS_THREADS) hist[i] = 0;
         __syncthreads();
@@ -269,31 +269,56 @@ k_code_stats(const float* __restrict__ x, RowLayout L, int D, int K, const int64
         for (int i = tid; i < rows; i += CS_THREADS) order[atomicAdd(&cursor[code[i]], 1)] = row_offset(L, r0 + i);
         __syncthreads();
         // one warp per code bucket: coalesced row reads, register accumulation, exclusive table update
+        const bool fast = (D == 64 && L.col_stride == 1 && (reinterpret_cast<uintptr_t>(x) & 7u) == 0);
         for (int k = warp; k < K; k += nwarps) {
             const int b0 = start[k], b1 = start[k + 1];
             if (b0 == b1) continue;
-            for (int d0 = 0; d0 < D; d0 += 64) {
+            if (fast) {                               // lane owns dims (2*lane, 2*lane+1): one 256-byte request per row
                 float a0 = 0.f, a1 = 0.f;
-                const int da = d0 + lane, db = d0 + 32 + lane;
                 int b = b0;
-                for (; b + 4 <= b1; b += 4) {
-                    float v0[4], v1[4];
+                for (; b + 8 <= b1; b += 8) {
+                    float2 v[8];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int64_t off = order[b + u];
-                        v0[u] = da < D ? x[off + (int64_t)da * L.col_stride] : 0.f;
-                        v1[u] = db < D ? x[off + (int64_t)db * L.col_stride] : 0.f;
+                    for (int u = 0; u < 8; ++u) v[u] = __ldcs(reinterpret_cast<const float2*>(x + order[b + u]) + lane);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) { a0 += v[u].x; a1 += v[u].y; }
+                }
+                if (b < b1) {
+                    float2 v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        v[u] = (b + u < b1) ? __ldcs(reinterpret_cast<const float2*>(x + order[b + u]) + lane) : make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) { a0 += v[u].x; a1 += v[u].y; }
+                }
+                float2* trow = reinterpret_cast<float2*>(table + (size_t)k * 64) + lane;
+                float2 tv = *trow;
+                tv.x += a0; tv.y += a1;
+                *trow = tv;
+            } else {
+                for (int d0 = 0; d0 < D; d0 += 64) {
+                    float a0 = 0.f, a1 = 0.f;
+                    const int da = d0 + lane, db = d0 + 32 + lane;
+                    int b = b0;
+                    for (; b + 4 <= b1; b += 4) {
+                        float v0[4], v1[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int64_t off = order[b + u];
+                            v0[u] = da < D ? x[off + (int64_t)da * L.col_stride] : 0.f;
+                            v1[u] = db < D ? x[off + (int64_t)db * L.col_stride] : 0.f;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) { a0 += v0[u]; a1 += v1[u]; }
                     }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) { a0 += v0[u]; a1 += v1[u]; }
+                    for (; b < b1; ++b) {
+                        const int64_t off = order[b];
+                        if (da < D) a0 += x[off + (int64_t)da * L.col_stride];
+                        if (db < D) a1 += x[off + (int64_t)db * L.col_stride];
+                    }
+                    if (da < D) table[(size_t)k * D + da] += a0;
+                    if (db < D) table[(size_t)k * D + db] += a1;
                 }
-                for (; b < b1; ++b) {
-                    const int64_t off = order[b];
-                    if (da < D) a0 += x[off + (int64_t)da * L.col_stride];
-                    if (db < D) a1 += x[off + (int64_t)db * L.col_stride];
-                }
-                if (da < D) table[(size_t)k * D + da] += a0;
-                if (db < D) table[(size_t)k * D + db] += a1;
             }
             if (lane == 0) cnt_total[k] += b1 - b0;
         }
@@ -309,7 +334,15 @@ __global__ void k_stats_reduce(const float* __restrict__ partials, int n_parts, 
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float s = 0.f;
-    for (int c = 0; c < n_parts; ++c) s += partials[(size_t)c * n + i];
+    int c = 0;
+    for (; c + 8 <= n_parts; c += 8) {                 // 8 independent loads in flight, fixed summation order
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldcs(partials + (size_t)(c + u) * n + i);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += v[u];
+    }
+    for (; c < n_parts; ++c) s += partials[(size_t)c * n + i];
     stats[i] = s;
 }
 

@@ -125,16 +125,21 @@ int forward_impl(const float* d_x, const RowLayout& L, int dim, int n_embed, con
         if (cs_smem <= 200 * 1024 && n_embed <= 65535) {
             // accumulate into d_stats across calls when zero_first == false (host-buffer chunking)
             VQ_CUDA(cudaFuncSetAttribute(k_code_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs_smem));
-            int64_t n_chunks = (L.n_rows + CS_CHUNK - 1) / CS_CHUNK;
-            int parts = (int)std::min<int64_t>(std::min<int64_t>(n_chunks, tc_num_sms()), STAT_PARTS - 1);
-            k_code_stats<<<parts, CS_THREADS, cs_smem, st>>>(d_x, L, dim, n_embed, d_ind, sc.stat_partials);
+            // rows per trip chosen so the trips divide evenly over the SMs (one CTA per SM, private table each)
+            const int sms_cs = std::min(tc_num_sms(), STAT_PARTS - 1);
+            int64_t waves = (L.n_rows + (int64_t)sms_cs * CS_CHUNK - 1) / ((int64_t)sms_cs * CS_CHUNK);
+            int64_t chunk = (L.n_rows + sms_cs * waves - 1) / (sms_cs * waves);
+            chunk = std::min<int64_t>(CS_CHUNK, std::max<int64_t>(256, (chunk + 31) / 32 * 32));
+            int64_t n_chunks = (L.n_rows + chunk - 1) / chunk;
+            int parts = (int)std::min<int64_t>(n_chunks, sms_cs);
+            k_code_stats<<<parts, CS_THREADS, cs_smem, st>>>(d_x, L, dim, n_embed, d_ind, sc.stat_partials, (int)chunk);
             VQ_LAUNCH_CHECK();
             int n = n_embed * (dim + 1);
             // the running total lives in partial slot [parts] so chunked calls keep accumulating
             float* prev = sc.stat_partials + (size_t)parts * n;
             if (zero_first) VQ_CUDA(cudaMemsetAsync(prev, 0, (size_t)n * 4, st));
             else VQ_CUDA(cudaMemcpyAsync(prev, d_stats, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
-            k_stats_reduce<<<(n + 255) / 256, 256, 0, st>>>(sc.stat_partials, parts + 1, n, d_stats);
+            k_stats_reduce<<<(n + 63) / 64, 64, 0, st>>>(sc.stat_partials, parts + 1, n, d_stats);
             VQ_LAUNCH_CHECK();
         }
     }
