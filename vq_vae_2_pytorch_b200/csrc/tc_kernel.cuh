@@ -15,7 +15,7 @@
 // E'_ik = cA ||x_i|| ||e_k|| + cB ||e_k||^2 an upper bound of the filter's own error, folded into the
 // contraction.  NSPLIT=1 drops the xl/el blocks (plain bf16 filter, wider bound).
 //
-// Warp roles (640 threads = 5 warpgroups, registers re-balanced with setmaxnreg: 128/128/104/80/40):
+// Warp roles (640 threads = 5 warpgroups, registers re-balanced with setmaxnreg: 128/128/72/72/56/24):
 //   WG0, WG1: two epilogue warpgroups, one per TMEM buffer (thread = row; arg-min and the runner-up from a
 //   two-class min scan, ONE ALU op per score) | WG2: output (gather, straight-through value, loss) |
 //   WG3: fp32->bf16 converters | WG4: w16 bulk-copy producer, w17 MMA issuer + TMEM owner (w18-19 idle).
@@ -30,12 +30,12 @@ namespace tc {
 constexpr int TILE_M = 128;        // rows per tile = UMMA M
 constexpr int UNIT_N = 256;        // codes per MMA = UMMA N
 constexpr int TC_D = 64;           // supported dim: one 128-byte swizzle row of bf16
-constexpr int THREADS = 640;        // 5 warpgroups; register budgets re-balanced with setmaxnreg
+constexpr int THREADS = 768;        // 6 warpgroups; register budgets re-balanced with setmaxnreg
 // Warp -> role map.  The SM's issue arbiter favours HIGHER warp ids (measured: the warpgroup with the higher
 // ids ran its identical scan 30% faster), so the latency-critical roles sit at the top: the MMA issuer and the
 // producer, then the converters (their latency serialises with the MMAs while A is single-buffered), then
 // the output warps; the two epilogue groups have slack and take what is left.
-constexpr int W_EPI0 = 0, W_EPI1 = 4, W_OUT = 8, W_CONV = 12, W_PROD = 16, W_MMA = 17;
+constexpr int W_EPI0 = 0, W_EPI1 = 4, W_OUT = 8, W_CONV = 16, W_PROD = 20, W_MMA = 21;
 constexpr int NORM_RING = 8;
 constexpr int RES_RING = 2;
 
@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
         for (int s = 0; s < XS; ++s) { mbar_init(bar(BAR_XF + s), 1); mbar_init(bar(BAR_XE + s), 128); }
         for (int s = 0; s < AS; ++s) { mbar_init(bar(BAR_AF + s), 128); mbar_init(bar(BAR_AE + s), 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(bar(BAR_TF + s), 1); mbar_init(bar(BAR_TE + s), 128); }
-        for (int s = 0; s < RES_RING; ++s) { mbar_init(bar(BAR_RF + s), 128); mbar_init(bar(BAR_RE + s), 128); }
+        for (int s = 0; s < RES_RING; ++s) { mbar_init(bar(BAR_RF + s), 128); mbar_init(bar(BAR_RE + s), 256); }
         for (int s = 0; s < 2; ++s) { mbar_init(bar(BAR_PF + s), 128); mbar_init(bar(BAR_PE + s), 128); }
         fence_barrier_init();
     }
@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
 
     if (warp == W_PROD) {
         // ================= bulk-copy producer =========================================================
-        reg_dec<40>();
+        reg_dec<24>();
         if (lane == 0) {
             const uint32_t bbytes = P::b_bytes(K);
             mbar_expect_tx(bar(BAR_B), bbytes);
@@ -442,7 +442,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
         }
     } else if (warp == W_MMA) {
         // ================= MMA issuer ==================================================================
-        reg_dec<40>();
+        reg_dec<24>();
         mbar_wait(bar(BAR_B), 0);
         const long long t_role0 = clock64();
         uint32_t it = 0, uc = 0;
@@ -486,10 +486,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
         }
         if (DBG && prof && lane == 0) { flush(PF_MMA_WAIT_AF, 0); flush(PF_MMA_WAIT_TE, 1); prof[PF_MMA_TOTAL] = (unsigned long long)(clock64() - t_role0); }
     } else if (warp > W_MMA) {
-        reg_dec<40>();                           // spare warps of the producer/MMA warpgroup
+        reg_dec<24>();                           // spare warps of the producer/MMA warpgroup
     } else if (warp >= W_CONV) {
         // ================= converters: fp32 rows -> split-bf16 K-major operand ==========================
-        reg_dec<80>();
+        reg_dec<56>();
         const int cw = warp - W_CONV;            // rows cw*32 .. cw*32+31
         const int half = lane >> 4, q4 = lane & 15;
         const bool rec = (warp == W_CONV && lane == 0);
@@ -507,15 +507,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
             float my_sq = 1.f;
             if (!(DBG && (p.dbg_skip & 2))) {
 #pragma unroll 1
-                for (int g8 = 0; g8 < 2; ++g8) {          // 8 row pairs per trip (8 independent 16-byte smem loads in flight)
-                    float4 v[8];
-                    float sq[8];
+                for (int g4 = 0; g4 < 4; ++g4) {          // 4 row pairs per trip
+                    float4 v[4];
+                    float sq[4];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u)
-                        v[u] = *reinterpret_cast<const float4*>(xs + (cw * 32 + 2 * (8 * g8 + u) + half) * 256 + q4 * 16);
+                    for (int u = 0; u < 4; ++u)
+                        v[u] = *reinterpret_cast<const float4*>(xs + (cw * 32 + 2 * (4 * g4 + u) + half) * 256 + q4 * 16);
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int r = cw * 32 + 2 * (8 * g8 + u) + half;
+                    for (int u = 0; u < 4; ++u) {
+                        const int r = cw * 32 + 2 * (4 * g4 + u) + half;
                         const uint32_t p01 = pack_bf16(v[u].x, v[u].y), p23 = pack_bf16(v[u].z, v[u].w);
                         const uint32_t off = sw128_off((uint32_t)r, (uint32_t)q4 * 4);
                         *reinterpret_cast<uint2*>(ah + off) = make_uint2(p01, p23);
@@ -527,20 +527,19 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
                         }
                         sq[u] = fmaf(v[u].x, v[u].x, fmaf(v[u].y, v[u].y, fmaf(v[u].z, v[u].z, v[u].w * v[u].w)));
                     }
-                    // transposing butterfly over lane bits 2,1,0 (8 values -> 1), then a plain sum over bit 3:
-                    // every lane ends with the full row sum of row pair 8*g8 + (q4 & 7)
-#pragma unroll
-                    for (int w = 4; w >= 1; w >>= 1) {
-                        const bool up = (q4 & w) != 0;
-#pragma unroll
-                        for (int i = 0; i < w; ++i) {
-                            const float send = up ? sq[i] : sq[i + w];
-                            const float keep = up ? sq[i + w] : sq[i];
-                            sq[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
-                        }
+                    {
+                        const bool up = (q4 & 2) != 0;
+                        const float s0 = up ? sq[0] : sq[2], k0 = up ? sq[2] : sq[0];
+                        const float s1 = up ? sq[1] : sq[3], k1 = up ? sq[3] : sq[1];
+                        sq[0] = k0 + __shfl_xor_sync(0xffffffffu, s0, 2);
+                        sq[1] = k1 + __shfl_xor_sync(0xffffffffu, s1, 2);
+                        const bool up1 = (q4 & 1) != 0;
+                        const float s2 = up1 ? sq[0] : sq[1], k2 = up1 ? sq[1] : sq[0];
+                        float tot = k2 + __shfl_xor_sync(0xffffffffu, s2, 1);
+                        tot += __shfl_xor_sync(0xffffffffu, tot, 4);
+                        tot += __shfl_xor_sync(0xffffffffu, tot, 8);
+                        if ((q4 >> 2) == g4) my_sq = tot;
                     }
-                    const float tot = sq[0] + __shfl_xor_sync(0xffffffffu, sq[0], 8);
-                    if ((q4 >> 3) == g8) my_sq = tot;
                 }
             }
             const long long tc1 = (DBG && prof && rec) ? clock64() : 0;
@@ -633,8 +632,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
         if (DBG && prof && rec) { flush(pbase, 0); flush(pbase + 1, 1); if (g) { flush(PF_EPI1_WAIT_PF, 2); flush(PF_EPI1_WAIT_RE, 3); } prof[g ? PF_EPI1_TOTAL : PF_EPI0_TOTAL] = (unsigned long long)(clock64() - t_role0); }
     } else {
         // ================= output: gather, straight-through value, loss =================================
-        reg_inc<104>();
-        const int ow = warp - W_OUT;             // rows ow*32 .. ow*32+31 of the tile
+        reg_dec<72>();
+        const int ow = warp - W_OUT;             // rows ow*16 .. ow*16+15 of the tile
         const int half = lane >> 4, q4 = lane & 15;
         float dacc = 0.f;
         const bool rec = (warp == W_OUT && lane == 0);
@@ -646,22 +645,22 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
             const int64_t r0 = t * TILE_M;
             if (!(DBG && (p.dbg_skip & 1)))
 #pragma unroll 1
-            for (int b = 0; b < 2; ++b) {        // 16 rows per batch: 16 independent 16-byte loads in flight per lane
-                int kk[8];
-                float4 xv[8], qv[8];
+            for (int b = 0; b < 2; ++b) {        // 8 output warps x 16 rows; 8 rows per batch
+                int kk[4];
+                float4 xv[4], qv[4];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int r = ow * 32 + b * 16 + i * 2 + half;
+                for (int i = 0; i < 4; ++i) {
+                    const int r = ow * 16 + b * 8 + i * 2 + half;
                     kk[i] = codes_s[rs * TILE_M + r];
                     if (kk[i] >= 0) xv[i] = __ldcg(reinterpret_cast<const float4*>(p.x + (r0 + r) * TC_D + q4 * 4));
                 }
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
+                for (int i = 0; i < 4; ++i)
                     if (kk[i] >= 0) qv[i] = __ldcg(reinterpret_cast<const float4*>(p.cbT + (size_t)kk[i] * TC_D + q4 * 4));
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
+                for (int i = 0; i < 4; ++i) {
                     if (kk[i] < 0) continue;
-                    const int r = ow * 32 + b * 16 + i * 2 + half;
+                    const int r = ow * 16 + b * 8 + i * 2 + half;
                     float4 d, o;
                     d.x = qv[i].x - xv[i].x; d.y = qv[i].y - xv[i].y; d.z = qv[i].z - xv[i].z; d.w = qv[i].w - xv[i].w;
                     o.x = xv[i].x + d.x; o.y = xv[i].y + d.y; o.z = xv[i].z + d.z; o.w = xv[i].w + d.w;
