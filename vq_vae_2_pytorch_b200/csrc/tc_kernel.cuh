@@ -95,6 +95,48 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// ---- 2-CTA (cta_group::2) variants: one CTA pair = one cluster; the leader (rank 0) issues the MMAs ----------
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {   // address from mapa_rank()
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {   // local barrier, remote arrivals
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
+    }
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {     // arrives on the barrier at this offset in BOTH CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -135,6 +177,8 @@ __device__ __forceinline__ uint64_t desc_sw32(uint32_t saddr) {    // rows of 32
 }
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, K-major both, N=256, M=128
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(UNIT_N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+// same with M = 256 for cta_group::2 (each CTA of the pair owns 128 of the 256 rows and 128 of the 256 B rows)
+constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(UNIT_N >> 3) << 17) | ((uint32_t)((2 * TILE_M) >> 4) << 24);
 
 // byte offset of bf16 element (row, col) inside a 128B-swizzled K-major block (Swizzle<3,4,3>)
 __host__ __device__ __forceinline__ uint32_t sw128_off(uint32_t row, uint32_t col) {
@@ -307,13 +351,14 @@ __device__ __forceinline__ int scan_unit(uint32_t lane_addr, float& m1, float& m
 // ---------------------------------------------------------------------------------------------------
 // shared-memory plan
 // ---------------------------------------------------------------------------------------------------
-template <int NSPLIT, int AS, int XS>
+template <int NSPLIT, int AS, int XS, bool CTA2 = false>
 struct Plan {
     static constexpr uint32_t A_STAGE = (NSPLIT == 3 ? 2u : 1u) * 16384u + 4096u;
     static constexpr uint32_t X_STAGE = TILE_M * TC_D * 4;
-    __host__ __device__ static uint32_t b_bytes(int K) { return (uint32_t)K * (NSPLIT == 3 ? 256u : 128u) + (uint32_t)K * 32u; }
-    __host__ __device__ static uint32_t off_b_lo(int K) { return (uint32_t)K * 128u; }
-    __host__ __device__ static uint32_t off_b_misc(int K) { return (uint32_t)K * (NSPLIT == 3 ? 256u : 128u); }
+    static constexpr uint32_t BDIV = CTA2 ? 2u : 1u;          // a CTA of a pair holds half of the codes of every unit
+    __host__ __device__ static uint32_t b_bytes(int K) { return ((uint32_t)K * (NSPLIT == 3 ? 256u : 128u) + (uint32_t)K * 32u) / BDIV; }
+    __host__ __device__ static uint32_t off_b_lo(int K) { return (uint32_t)K * 128u / BDIV; }
+    __host__ __device__ static uint32_t off_b_misc(int K) { return (uint32_t)K * (NSPLIT == 3 ? 256u : 128u) / BDIV; }
     __host__ __device__ static uint32_t off_a(int K) { return b_bytes(K); }
     __host__ __device__ static uint32_t off_x(int K) { return off_a(K) + AS * A_STAGE; }
     __host__ __device__ static uint32_t off_small(int K) { return off_x(K) + XS * X_STAGE; }
@@ -350,11 +395,16 @@ enum ProfSlot { PF_PROD_WAIT_XE = 0, PF_MMA_WAIT_AF, PF_MMA_WAIT_TE, PF_MMA_TOTA
                 PROF_SLOTS = 24 };
 
 enum BarId { BAR_B = 0, BAR_XF = 1, BAR_XE = 5, BAR_AF = 9, BAR_AE = 13, BAR_TF = 17, BAR_TE = 19, BAR_RF = 21, BAR_RE = 23,
-             BAR_PF = 25, BAR_PE = 27, BAR_COUNT = 29 };
+             BAR_PF = 25, BAR_PE = 27, BAR_PB = 29, BAR_COUNT = 30 };
 
-template <int NSPLIT, int AS, int XS, bool DBG>
+// CTA2 = true: launched as clusters of two CTAs (one SM pair).  Each CTA converts, scans and writes its own 128-row
+// tile, but the pair shares ONE tcgen05.mma.cta_group::2 stream (M = 256) issued by the leader CTA, and each CTA
+// holds only half of the codebook operand image (the B rows of its half of every 256-code unit).  That halves the
+// image's shared-memory footprint (144 KB -> 72 KB at K = 512), which is what pays for double-buffered A and x
+// stages, and halves the operand bandwidth each SM's tensor core draws from shared memory.
+template <int NSPLIT, int AS, int XS, bool DBG, bool CTA2>
 __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
-    using P = Plan<NSPLIT, AS, XS>;
+    using P = Plan<NSPLIT, AS, XS, CTA2>;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -373,6 +423,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
     auto bar = [&](int id) { return bars + 8u * (uint32_t)id; };
 
     const int64_t n_tiles = (p.n_rows + TILE_M - 1) / TILE_M;
+    const uint32_t crank = CTA2 ? cluster_ctarank() : 0u;
+    // both CTAs of a pair run the same number of trips (the pair's second tile may lie past the end on the last one)
+    const int64_t first_tile = CTA2 ? (int64_t)(blockIdx.x & ~1u) : (int64_t)blockIdx.x;
+    const uint32_t n_iter = first_tile < n_tiles ? (uint32_t)((n_tiles - first_tile + gridDim.x - 1) / gridDim.x) : 0u;
+    constexpr uint32_t PAIR_THREADS = CTA2 ? 256u : 128u;     // arrivals on the barriers the MMA issuer waits on
     unsigned long long* prof = (DBG && p.prof) ? p.prof + (size_t)blockIdx.x * PROF_SLOTS : nullptr;
     const long long t_kernel0 = clock64();
     // timed barrier wait: accumulates the stall into a REGISTER counter when profiling is on (flushed to
@@ -393,13 +448,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
     if (threadIdx.x == 0) {
         mbar_init(bar(BAR_B), 1);
         for (int s = 0; s < XS; ++s) { mbar_init(bar(BAR_XF + s), 1); mbar_init(bar(BAR_XE + s), 128); }
-        for (int s = 0; s < AS; ++s) { mbar_init(bar(BAR_AF + s), 128); mbar_init(bar(BAR_AE + s), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(bar(BAR_TF + s), 1); mbar_init(bar(BAR_TE + s), 128); }
+        for (int s = 0; s < AS; ++s) { mbar_init(bar(BAR_AF + s), PAIR_THREADS); mbar_init(bar(BAR_AE + s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(bar(BAR_TF + s), 1); mbar_init(bar(BAR_TE + s), PAIR_THREADS); }
+        mbar_init(bar(BAR_PB), 1);
         for (int s = 0; s < RES_RING; ++s) { mbar_init(bar(BAR_RF + s), 128); mbar_init(bar(BAR_RE + s), 256); }
         for (int s = 0; s < 2; ++s) { mbar_init(bar(BAR_PF + s), 128); mbar_init(bar(BAR_PE + s), 128); }
         fence_barrier_init();
     }
-    if (warp == W_MMA) tmem_alloc(smem_u32(tmem_ptr_s), 512);
+    if (warp == W_MMA) { if (CTA2) tmem_alloc2(smem_u32(tmem_ptr_s), 512); else tmem_alloc(smem_u32(tmem_ptr_s), 512); }
     // constant part of the A "misc" blocks: [1 1 1 | o1 o2 o3 | nx 1 | 0 x8]; zero chunk 1 once
     for (int i = threadIdx.x; i < AS * TILE_M; i += THREADS) {
         int s = i / TILE_M, r = i % TILE_M;
@@ -415,7 +471,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
     }
     tc_fence_before();
     const bool cb_bad = __syncthreads_or(bad) != 0;
+    if (CTA2) cluster_sync_all();                 // the peer's barriers exist before anybody arrives on them remotely
     tc_fence_after();
+    // barriers the (leader's) MMA issuer waits on live in the leader CTA; both CTAs arrive there
+    auto arrive_mma_side = [&](int id) {
+        if (CTA2) mbar_arrive_cluster(mapa_rank(bar(id), 0)); else mbar_arrive(bar(id));
+    };
     const uint32_t tmem_base = *tmem_ptr_s;
 
     if (warp == W_PROD) {
@@ -424,19 +485,24 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
         if (lane == 0) {
             const uint32_t bbytes = P::b_bytes(K);
             mbar_expect_tx(bar(BAR_B), bbytes);
-            // eh [, el], misc : three contiguous pieces of the image
-            bulk_g2s(sB, p.image, (uint32_t)K * 128u, bar(BAR_B));
-            if (NSPLIT == 3) bulk_g2s(sB + P::off_b_lo(K), p.image + image_off_lo(K), (uint32_t)K * 128u, bar(BAR_B));
-            bulk_g2s(sB + P::off_b_misc(K), p.image + image_off_misc(K), (uint32_t)K * 32u, bar(BAR_B));
-            uint32_t it = 0;
-            for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+            // per 256-code unit: the rows this CTA feeds to the MMA (all 256, or its half of them in a pair)
+            constexpr uint32_t UROWS = UNIT_N / P::BDIV;
+            for (int u = 0; u < U; ++u) {
+                const size_t krow = (size_t)u * UNIT_N + (size_t)crank * UROWS;
+                bulk_g2s(sB + (uint32_t)u * UROWS * 128u, p.image + krow * 128, UROWS * 128u, bar(BAR_B));
+                if (NSPLIT == 3)
+                    bulk_g2s(sB + P::off_b_lo(K) + (uint32_t)u * UROWS * 128u, p.image + image_off_lo(K) + krow * 128, UROWS * 128u, bar(BAR_B));
+                bulk_g2s(sB + P::off_b_misc(K) + (uint32_t)u * UROWS * 32u, p.image + image_off_misc(K) + krow * 32, UROWS * 32u, bar(BAR_B));
+            }
+            for (uint32_t it = 0; it < n_iter; ++it) {
+                const int64_t t = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
                 const uint32_t s = it % XS, ph = (it / XS) & 1u;
                 wait_t(BAR_XE + s, ph ^ 1u, 0, true);
                 const int64_t r0 = t * TILE_M;
-                const uint32_t rows = (uint32_t)min((int64_t)TILE_M, p.n_rows - r0);
+                const uint32_t rows = (uint32_t)max((int64_t)0, min((int64_t)TILE_M, p.n_rows - r0));
                 const uint32_t bytes = rows * TC_D * 4u;
                 mbar_expect_tx(bar(BAR_XF + s), bytes);
-                bulk_g2s(sX + s * P::X_STAGE, p.x + r0 * TC_D, bytes, bar(BAR_XF + s));
+                if (bytes) bulk_g2s(sX + s * P::X_STAGE, p.x + r0 * TC_D, bytes, bar(BAR_XF + s));
             }
             if (DBG && prof) flush(PF_PROD_WAIT_XE, 0);
         }
@@ -444,44 +510,48 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
         // ================= MMA issuer ==================================================================
         reg_dec<24>();
         mbar_wait(bar(BAR_B), 0);
+        if (CTA2) {
+            if (crank != 0) { if (lane == 0) mbar_arrive_cluster(mapa_rank(bar(BAR_PB), 0)); }   // my half of B has landed
+            else mbar_wait_cluster(bar(BAR_PB), 0);
+        }
         const long long t_role0 = clock64();
-        uint32_t it = 0, uc = 0;
-        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        uint32_t uc = 0;
+        for (uint32_t it = 0; it < (crank == 0 ? n_iter : 0u); ++it) {     // the leader issues for the pair
             const uint32_t sa = it % AS, pha = (it / AS) & 1u;
-            wait_t(BAR_AF + sa, pha, 0, lane == 0);
+            if (CTA2) mbar_wait_cluster(bar(BAR_AF + sa), pha); else wait_t(BAR_AF + sa, pha, 0, lane == 0);
             tc_fence_after();
             const uint32_t a0 = sA + sa * P::A_STAGE;
             for (int u = 0; u < U; ++u, ++uc) {
                 const uint32_t buf = uc & 1u, pht = (uc >> 1) & 1u;
-                wait_t(BAR_TE + buf, pht ^ 1u, 1, lane == 0);
+                if (CTA2) mbar_wait_cluster(bar(BAR_TE + buf), pht ^ 1u); else wait_t(BAR_TE + buf, pht ^ 1u, 1, lane == 0);
                 tc_fence_after();
+                auto mma = [&](uint64_t ad, uint64_t bd, uint32_t acc) {
+                    if (CTA2) umma_bf16_2cta(tmem_base + buf * UNIT_N, ad, bd, IDESC2, acc);
+                    else umma_bf16(tmem_base + buf * UNIT_N, ad, bd, IDESC, acc);
+                };
                 if (lane == 0 && !(DBG && (p.dbg_skip & 8))) {
-                    const uint32_t d_tmem = tmem_base + buf * UNIT_N;
-                    const uint32_t b_hi = sB + (uint32_t)u * UNIT_N * 128u;
-                    const uint32_t b_lo = sB + P::off_b_lo(K) + (uint32_t)u * UNIT_N * 128u;
-                    const uint32_t b_mi = sB + P::off_b_misc(K) + (uint32_t)u * UNIT_N * 32u;
-                    uint32_t acc = 0;
+                    constexpr uint32_t UROWS = UNIT_N / P::BDIV;
+                    const uint32_t b_hi = sB + (uint32_t)u * UROWS * 128u;
+                    const uint32_t b_lo = sB + P::off_b_lo(K) + (uint32_t)u * UROWS * 128u;
+                    const uint32_t b_mi = sB + P::off_b_misc(K) + (uint32_t)u * UROWS * 32u;
                     // misc block first (bias, offset, error bound), then the split products
-                    umma_bf16(d_tmem, desc_sw32(a0 + (P::A_STAGE - 4096u)), desc_sw32(b_mi), IDESC, acc);
-                    acc = 1;
+                    mma(desc_sw32(a0 + (P::A_STAGE - 4096u)), desc_sw32(b_mi), 0u);
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks)      // xh . eh
-                        umma_bf16(d_tmem, desc_sw128(a0) + 2u * ks, desc_sw128(b_hi) + 2u * ks, IDESC, acc);
+                        mma(desc_sw128(a0) + 2u * ks, desc_sw128(b_hi) + 2u * ks, 1u);
                     if (NSPLIT == 3) {
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks)  // xl . eh
-                            umma_bf16(d_tmem, desc_sw128(a0 + 16384u) + 2u * ks, desc_sw128(b_hi) + 2u * ks, IDESC, acc);
+                            mma(desc_sw128(a0 + 16384u) + 2u * ks, desc_sw128(b_hi) + 2u * ks, 1u);
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks)  // xh . el
-                            umma_bf16(d_tmem, desc_sw128(a0) + 2u * ks, desc_sw128(b_lo) + 2u * ks, IDESC, acc);
+                            mma(desc_sw128(a0) + 2u * ks, desc_sw128(b_lo) + 2u * ks, 1u);
                     }
-                    umma_commit(bar(BAR_TF + buf));
-                } else if (lane == 0) {
-                    umma_commit(bar(BAR_TF + buf));
                 }
+                if (lane == 0) { if (CTA2) umma_commit_2cta(bar(BAR_TF + buf)); else umma_commit(bar(BAR_TF + buf)); }
                 __syncwarp();
             }
-            if (lane == 0) umma_commit(bar(BAR_AE + sa));
+            if (lane == 0) { if (CTA2) umma_commit_2cta(bar(BAR_AE + sa)); else umma_commit(bar(BAR_AE + sa)); }
             __syncwarp();
         }
         if (DBG && prof && lane == 0) { flush(PF_MMA_WAIT_AF, 0); flush(PF_MMA_WAIT_TE, 1); prof[PF_MMA_TOTAL] = (unsigned long long)(clock64() - t_role0); }
@@ -494,8 +564,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
         const int half = lane >> 4, q4 = lane & 15;
         const bool rec = (warp == W_CONV && lane == 0);
         const long long t_role0 = clock64();
-        uint32_t it = 0;
-        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        for (uint32_t it = 0; it < n_iter; ++it) {
+            const int64_t t = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
             const uint32_t sx = it % XS, phx = (it / XS) & 1u, sa = it % AS, pha = (it / AS) & 1u;
             wait_t(BAR_XF + sx, phx, 0, rec);
             wait_t(BAR_AE + sa, pha ^ 1u, 1, rec);
@@ -555,7 +625,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
             }
             const long long tc2 = (DBG && prof && rec) ? clock64() : 0;
             fence_async_smem();
-            mbar_arrive(bar(BAR_AF + sa));
+            arrive_mma_side(BAR_AF + sa);
             mbar_arrive(bar(BAR_XE + sx));
             if (DBG && prof && rec) {
                 const long long tc3 = clock64();
@@ -575,8 +645,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
         const bool rec = ((warp & 3) == 0 && lane == 0);      // first warp of each group
         const int pbase = g ? PF_EPI1_WAIT_TF : PF_EPI0_WAIT_TF;
         const long long t_role0 = clock64();
-        uint32_t it = 0;
-        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        for (uint32_t it = 0; it < n_iter; ++it) {
+            const int64_t t = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
             if (U == 1 && (int)(it & 1u) != g) continue;
             const uint32_t pht = (U == 2) ? (it & 1u) : ((it >> 1) & 1u);
             const int64_t grow = t * TILE_M + row_in_tile;
@@ -589,7 +659,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
             jbest = scan_unit<DBG>(lane_addr, m1, m2, (DBG && p.dbg_scores && grow < p.n_rows) ? p.dbg_scores + grow * K + g * (U == 2 ? UNIT_N : 0) : nullptr);
             if (DBG && prof && rec) pacc[1] += clock64() - t_scan0;
             tc_fence_before();
-            mbar_arrive(bar(BAR_TE + g));
+            arrive_mma_side(BAR_TE + g);
             int k1 = jbest;
             if (U == 2) {
                 const uint32_t ps = it & 1u, php = (it >> 1) & 1u;
@@ -638,8 +708,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
         float dacc = 0.f;
         const bool rec = (warp == W_OUT && lane == 0);
         const long long t_role0 = clock64();
-        uint32_t it = 0;
-        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        for (uint32_t it = 0; it < n_iter; ++it) {
+            const int64_t t = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
             const uint32_t rs = it % RES_RING, phr = (it / RES_RING) & 1u;
             wait_t(BAR_RF + rs, phr, 0, rec);
             const int64_t r0 = t * TILE_M;
@@ -684,7 +754,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
     // ---- teardown -------------------------------------------------------------------------------------
     tc_fence_before();
     __syncthreads();
-    if (warp == W_MMA) tmem_dealloc(tmem_base, 512);
+    if (CTA2) cluster_sync_all();                 // nobody leaves while the pair still reads its smem / arrives on its barriers
+    if (warp == W_MMA) { if (CTA2) tmem_dealloc2(tmem_base, 512); else tmem_dealloc(tmem_base, 512); }
     if (DBG && prof && threadIdx.x == 0) prof[PF_KERNEL] = (unsigned long long)(clock64() - t_kernel0);
 }
 
@@ -728,10 +799,10 @@ inline int tc_prepare_codebook(const CodebookImage& cb, int dim, int n_embed, cu
     return cudaGetLastError() != cudaSuccess;
 }
 
-template <int NSPLIT, int AS, int XS, bool DBG>
+template <int NSPLIT, int AS, int XS, bool DBG, bool CTA2>
 inline int tc_launch(const tc::Params& prm, cudaStream_t st) {
-    using P = tc::Plan<NSPLIT, AS, XS>;
-    auto kern = tc::k_vq_tc<NSPLIT, AS, XS, DBG>;
+    using P = tc::Plan<NSPLIT, AS, XS, CTA2>;
+    auto kern = tc::k_vq_tc<NSPLIT, AS, XS, DBG, CTA2>;
     const int smem = (int)P::total(prm.K);
     static int configured = 0;
     if (configured < smem) {
@@ -740,8 +811,23 @@ inline int tc_launch(const tc::Params& prm, cudaStream_t st) {
     }
     int64_t n_tiles = (prm.n_rows + tc::TILE_M - 1) / tc::TILE_M;
     int grid = (int)std::min<int64_t>(n_tiles, tc_num_sms());
-    kern<<<grid, tc::THREADS, smem, st>>>(prm);
-    return cudaGetLastError() != cudaSuccess;
+    if (!CTA2) {
+        kern<<<grid, tc::THREADS, smem, st>>>(prm);
+        return cudaGetLastError() != cudaSuccess;
+    }
+    grid = std::max(2, (grid + 1) / 2 * 2);      // whole CTA pairs; 148 SMs = 74 pairs
+    if (grid > tc_num_sms()) grid = tc_num_sms() / 2 * 2;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(tc::THREADS);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, prm) != cudaSuccess;
 }
 
 // main kernel only; the caller runs the exact fix-up over the flagged rows afterwards
@@ -759,8 +845,13 @@ inline int tc_forward(const float* x, const RowLayout& L, int dim, int n_embed, 
     { const char* e = getenv("VQB200_DBG_SKIP"); prm.dbg_skip = e ? atoi(e) : 0; }
     prm.cA = tc::bound_cA(tc_nsplit()); prm.cB = tc::BOUND_CB;
     const bool dbg = dbg_scores || prof;           // diagnostics live in a separate instantiation
-    if (tc_nsplit() == 3) return dbg ? tc_launch<3, 1, 1, true>(prm, st) : tc_launch<3, 1, 1, false>(prm, st);
-    return dbg ? tc_launch<1, 2, 2, true>(prm, st) : tc_launch<1, 2, 2, false>(prm, st);
+    static const bool pair = [] { const char* e = getenv("VQB200_TC_CTA2"); return e ? atoi(e) != 0 : true; }();
+    if (tc_nsplit() == 3) {
+        if (pair && n_embed == 512)                // CTA pairs: half the operand image per CTA -> double-buffered A and x
+            return dbg ? tc_launch<3, 2, 2, true, true>(prm, st) : tc_launch<3, 2, 2, false, true>(prm, st);
+        return dbg ? tc_launch<3, 1, 1, true, false>(prm, st) : tc_launch<3, 1, 1, false, false>(prm, st);
+    }
+    return dbg ? tc_launch<1, 2, 2, true, false>(prm, st) : tc_launch<1, 2, 2, false, false>(prm, st);
 }
 
 }  // namespace vqb200
