@@ -28,7 +28,8 @@ namespace vqb200 {
 namespace tc {
 
 constexpr int TILE_M = 128;        // rows per tile = UMMA M
-constexpr int UNIT_N = 256;        // codes per MMA = UMMA N
+constexpr int UNIT_N = 128;        // codes per MMA = UMMA N; one TMEM accumulator buffer = 128 columns
+constexpr int NBUF = 4;            // TMEM buffers (4 x 128 columns = all of TMEM): the MMAs run up to 3 units ahead of the scans
 constexpr int TC_D = 64;           // supported dim: one 128-byte swizzle row of bf16
 constexpr int THREADS = 768;        // 6 warpgroups; register budgets re-balanced with setmaxnreg
 // Warp -> role map.  The SM's issue arbiter favours HIGHER warp ids (measured: the warpgroup with the higher
@@ -296,18 +297,25 @@ __device__ __forceinline__ void scan_half(const uint32_t (&v)[16], float (&rA)[8
     rB[2 * H + 1] = min8(key + 8);
 }
 
-// software-pipelined walk over the 16 column groups of a unit: the TMEM load of group H+1 is in flight while
-// group H is reduced (fully unrolled so the 32 class-B minima stay in registers)
-template <int H, bool DBG>
+// software-pipelined walk over the 8 column groups (16 columns each) of one 128-column TMEM buffer: the load of
+// group H+1 is in flight while group H is reduced.  HB = index of the buffer's first group within the warpgroup's
+// 256 virtual columns (0 or 8), so the class-B minima land in fixed registers.
+template <int H, int HB, bool DBG>
 __device__ __forceinline__ void scan_pairs(uint32_t lane_addr, uint32_t (&va)[16], uint32_t (&vb)[16],
                                            float (&rA)[8], float (&rB)[32], float* dbg) {
     tmem_ld_wait16(va);
     tmem_ld16(lane_addr + (H + 1) * 16, vb);
-    scan_half<H, DBG>(va, rA, rB, dbg);
+    scan_half<HB + H, DBG>(va, rA, rB, dbg);
     tmem_ld_wait16(vb);
-    if constexpr (H + 2 < 16) tmem_ld16(lane_addr + (H + 2) * 16, va);
-    scan_half<H + 1, DBG>(vb, rA, rB, dbg);
-    if constexpr (H + 2 < 16) scan_pairs<H + 2, DBG>(lane_addr, va, vb, rA, rB, dbg);
+    if constexpr (H + 2 < 8) tmem_ld16(lane_addr + (H + 2) * 16, va);
+    scan_half<HB + H + 1, DBG>(vb, rA, rB, dbg);
+    if constexpr (H + 2 < 8) scan_pairs<H + 2, HB, DBG>(lane_addr, va, vb, rA, rB, dbg);
+}
+template <int HB, bool DBG>
+__device__ __forceinline__ void scan_buffer(uint32_t lane_addr, float (&rA)[8], float (&rB)[32], float* dbg) {
+    uint32_t va[16], vb[16];
+    tmem_ld16(lane_addr, va);
+    scan_pairs<0, HB, DBG>(lane_addr, va, vb, rA, rB, dbg);
 }
 
 // min over the entries != m1, the index of the entry == m1, and how many entries equal m1
@@ -329,16 +337,9 @@ __device__ __forceinline__ float min_excluding(const float (&r)[N], float m1, in
     return m;
 }
 
-// returns the winning column (0..255) of the unit, its score m1 and the runner-up score m2 (m2 == m1 on exact
-// ties and NaN scores -> never certified)
-template <bool DBG>
-__device__ __forceinline__ int scan_unit(uint32_t lane_addr, float& m1, float& m2, float* dbg) {
-    float rA[8], rB[32];
-#pragma unroll
-    for (int a = 0; a < 8; ++a) rA[a] = INFINITY;
-    uint32_t va[16], vb[16];
-    tmem_ld16(lane_addr, va);
-    scan_pairs<0, DBG>(lane_addr, va, vb, rA, rB, dbg);
+// after the warpgroup's (up to) 256 virtual columns went through scan_buffer: winning virtual column, its score m1
+// and the runner-up score m2 (m2 == m1 on exact ties and NaN scores -> never certified)
+__device__ __forceinline__ int scan_finish(const float (&rA)[8], const float (&rB)[32], float& m1, float& m2) {
     m1 = min8(rA);
     int a_star, b_star, hits_a, hits_b;
     const float ea = min_excluding<8>(rA, m1, a_star, hits_a);
@@ -394,8 +395,8 @@ enum ProfSlot { PF_PROD_WAIT_XE = 0, PF_MMA_WAIT_AF, PF_MMA_WAIT_TE, PF_MMA_TOTA
                 PF_EPI1_WAIT_RE, PF_EPI1_TOTAL, PF_OUT_WAIT_RF, PF_OUT_TOTAL, PF_KERNEL, PF_CONV_LOOP, PF_CONV_TAIL, PF_CONV_FENCE,
                 PROF_SLOTS = 24 };
 
-enum BarId { BAR_B = 0, BAR_XF = 1, BAR_XE = 5, BAR_AF = 9, BAR_AE = 13, BAR_TF = 17, BAR_TE = 19, BAR_RF = 21, BAR_RE = 23,
-             BAR_PF = 25, BAR_PE = 27, BAR_PB = 29, BAR_COUNT = 30 };
+enum BarId { BAR_B = 0, BAR_XF = 1, BAR_XE = 5, BAR_AF = 9, BAR_AE = 13, BAR_TF = 17, BAR_TE = 21, BAR_RF = 25, BAR_RE = 27,
+             BAR_PF = 29, BAR_PE = 31, BAR_PB = 33, BAR_COUNT = 34 };
 
 // CTA2 = true: launched as clusters of two CTAs (one SM pair).  Each CTA converts, scans and writes its own 128-row
 // tile, but the pair shares ONE tcgen05.mma.cta_group::2 stream (M = 256) issued by the leader CTA, and each CTA
@@ -449,7 +450,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
         mbar_init(bar(BAR_B), 1);
         for (int s = 0; s < XS; ++s) { mbar_init(bar(BAR_XF + s), 1); mbar_init(bar(BAR_XE + s), 128); }
         for (int s = 0; s < AS; ++s) { mbar_init(bar(BAR_AF + s), PAIR_THREADS); mbar_init(bar(BAR_AE + s), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(bar(BAR_TF + s), 1); mbar_init(bar(BAR_TE + s), PAIR_THREADS); }
+        for (int s = 0; s < NBUF; ++s) { mbar_init(bar(BAR_TF + s), 1); mbar_init(bar(BAR_TE + s), PAIR_THREADS); }
         mbar_init(bar(BAR_PB), 1);
         for (int s = 0; s < RES_RING; ++s) { mbar_init(bar(BAR_RF + s), 128); mbar_init(bar(BAR_RE + s), 256); }
         for (int s = 0; s < 2; ++s) { mbar_init(bar(BAR_PF + s), 128); mbar_init(bar(BAR_PE + s), 128); }
@@ -522,7 +523,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
             tc_fence_after();
             const uint32_t a0 = sA + sa * P::A_STAGE;
             for (int u = 0; u < U; ++u, ++uc) {
-                const uint32_t buf = uc & 1u, pht = (uc >> 1) & 1u;
+                const uint32_t buf = uc % NBUF, pht = (uc / NBUF) & 1u;
                 if (CTA2) mbar_wait_cluster(bar(BAR_TE + buf), pht ^ 1u); else wait_t(BAR_TE + buf, pht ^ 1u, 1, lane == 0);
                 tc_fence_after();
                 auto mma = [&](uint64_t ad, uint64_t bd, uint32_t acc) {
@@ -635,45 +636,67 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
         if (DBG && prof && rec) { flush(PF_CONV_WAIT_XF, 0); flush(PF_CONV_WAIT_AE, 1); flush(PF_CONV_LOOP, 2); flush(PF_CONV_TAIL, 3); flush(PF_CONV_FENCE, 4); prof[PF_CONV_TOTAL] = (unsigned long long)(clock64() - t_role0); }
     } else if (warp < W_OUT) {
         // ================= epilogue: TMEM -> two-class min scan -> certified arg-min =====================
-        // warpgroup g owns TMEM buffer g.  n_embed = 512: unit 0 of every tile lands in buffer 0, unit 1 in
-        // buffer 1, so both groups work on the same tile and group 1 merges.  n_embed = 256: tiles alternate.
+        // The codes of a tile come as U = K/128 accumulator units of 128 columns; group g takes units g, g+2 (its
+        // "256 virtual columns"), the two groups work on the same tile concurrently and group 1 merges.
         reg_inc<128>();
         const int g = warp >> 2;
         const int wq = warp & 3;                 // TMEM lane quarter this warp may access
         const int row_in_tile = wq * 32 + lane;
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)g * UNIT_N;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(wq * 32) << 16);
         const bool rec = ((warp & 3) == 0 && lane == 0);      // first warp of each group
         const int pbase = g ? PF_EPI1_WAIT_TF : PF_EPI0_WAIT_TF;
         const long long t_role0 = clock64();
+        // units u = g, g+2, ... of every tile belong to this group (U = K/128 units per tile: 2 or 4); unit counter
+        // uc = it*U + u selects TMEM buffer uc % 4 and its phase
         for (uint32_t it = 0; it < n_iter; ++it) {
             const int64_t t = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
-            if (U == 1 && (int)(it & 1u) != g) continue;
-            const uint32_t pht = (U == 2) ? (it & 1u) : ((it >> 1) & 1u);
             const int64_t grow = t * TILE_M + row_in_tile;
-            wait_t(BAR_TF + g, pht, 0, rec);
-            tc_fence_after();
-            float m1, m2;
+            float rA[8], rB[32];
+#pragma unroll
+            for (int a = 0; a < 8; ++a) rA[a] = INFINITY;
+#pragma unroll
+            for (int b = 0; b < 32; ++b) rB[b] = INFINITY;
+            float* dbg = (DBG && p.dbg_scores && grow < p.n_rows) ? p.dbg_scores + grow * K : nullptr;
             const long long t_scan0 = clock64();
-            int jbest = 0;
-            if (DBG && (p.dbg_skip & 4)) { m1 = 1.f; m2 = 1e9f; } else
-            jbest = scan_unit<DBG>(lane_addr, m1, m2, (DBG && p.dbg_scores && grow < p.n_rows) ? p.dbg_scores + grow * K + g * (U == 2 ? UNIT_N : 0) : nullptr);
+            {   // first unit of the group
+                const uint32_t uc = it * (uint32_t)U + (uint32_t)g, buf = uc % NBUF, pht = (uc / NBUF) & 1u;
+                wait_t(BAR_TF + buf, pht, 0, rec);
+                tc_fence_after();
+                if (!(DBG && (p.dbg_skip & 4))) scan_buffer<0, DBG>(lane_base + buf * UNIT_N, rA, rB, dbg ? dbg + g * UNIT_N - 0 : nullptr);
+                tc_fence_before();
+                arrive_mma_side(BAR_TE + buf);
+            }
+            if (U == 4) {   // second unit (codes 128*(g+2) ..)
+                const uint32_t uc = it * 4u + (uint32_t)g + 2u, buf = uc % NBUF, pht = (uc / NBUF) & 1u;
+                wait_t(BAR_TF + buf, pht, 0, rec);
+                tc_fence_after();
+                if (!(DBG && (p.dbg_skip & 4))) scan_buffer<8, DBG>(lane_base + buf * UNIT_N, rA, rB, dbg ? dbg + (g + 2) * UNIT_N - 8 * 16 : nullptr);
+                tc_fence_before();
+                arrive_mma_side(BAR_TE + buf);
+            }
+            float m1, m2;
+            int k1;
+            {
+                const int v = scan_finish(rA, rB, m1, m2);        // virtual column 0..255 of this group
+                k1 = (v < UNIT_N ? g : g + 2) * UNIT_N + (v & (UNIT_N - 1));
+                if (DBG && (p.dbg_skip & 4)) { m1 = 1.f; m2 = 1e9f; k1 = 0; }
+            }
             if (DBG && prof && rec) pacc[1] += clock64() - t_scan0;
-            tc_fence_before();
-            arrive_mma_side(BAR_TE + g);
-            int k1 = jbest;
-            if (U == 2) {
+            {
                 const uint32_t ps = it & 1u, php = (it >> 1) & 1u;
-                if (g == 0) {                    // hand the unit-0 result to group 1
+                if (g == 0) {                    // hand this group's result to group 1
                     mbar_wait(bar(BAR_PE + ps), php ^ 1u);
-                    part_s[ps * TILE_M + row_in_tile] = make_float4(m1, m2, __int_as_float(jbest), 0.f);
+                    part_s[ps * TILE_M + row_in_tile] = make_float4(m1, m2, __int_as_float(k1), 0.f);
                     mbar_arrive(bar(BAR_PF + ps));
                     continue;
                 }
                 wait_t(BAR_PF + ps, php, 2, rec);
                 const float4 o = part_s[ps * TILE_M + row_in_tile];
                 mbar_arrive(bar(BAR_PE + ps));
+                const int ko = __float_as_int(o.z);
                 m2 = fminf(fminf(o.y, m2), fmaxf(o.x, m1));
-                if (m1 < o.x) { k1 = UNIT_N + jbest; } else { m1 = o.x; k1 = __float_as_int(o.z); }   // tie: lower unit, gap 0 -> flagged
+                const bool take_other = (o.x < m1) || (o.x == m1 && ko < k1);   // equal scores: lowest code (gap 0 -> flagged anyway)
+                if (take_other) { m1 = o.x; k1 = ko; }
             }
             // certificate: every other code's lower bound must clear the winner's upper bound
             const float xn = rownorm_s[(it % NORM_RING) * TILE_M + row_in_tile];
