@@ -108,7 +108,7 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
     return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {   // address from mapa_rank()
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {   // local barrier, remote arrivals
     uint32_t ok = 0;
@@ -428,7 +428,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
     // both CTAs of a pair run the same number of trips (the pair's second tile may lie past the end on the last one)
     const int64_t first_tile = CTA2 ? (int64_t)(blockIdx.x & ~1u) : (int64_t)blockIdx.x;
     const uint32_t n_iter = first_tile < n_tiles ? (uint32_t)((n_tiles - first_tile + gridDim.x - 1) / gridDim.x) : 0u;
-    constexpr uint32_t PAIR_THREADS = CTA2 ? 256u : 128u;     // arrivals on the barriers the MMA issuer waits on
+    constexpr uint32_t PAIR_THREADS = CTA2 ? 8u : 4u;         // arriving WARPS on the barriers the MMA issuer waits on
     unsigned long long* prof = (DBG && p.prof) ? p.prof + (size_t)blockIdx.x * PROF_SLOTS : nullptr;
     const long long t_kernel0 = clock64();
     // timed barrier wait: accumulates the stall into a REGISTER counter when profiling is on (flushed to
@@ -448,12 +448,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
     // ---- one-time setup -----------------------------------------------------------------------------
     if (threadIdx.x == 0) {
         mbar_init(bar(BAR_B), 1);
-        for (int s = 0; s < XS; ++s) { mbar_init(bar(BAR_XF + s), 1); mbar_init(bar(BAR_XE + s), 128); }
+        for (int s = 0; s < XS; ++s) { mbar_init(bar(BAR_XF + s), 1); mbar_init(bar(BAR_XE + s), 4); }
         for (int s = 0; s < AS; ++s) { mbar_init(bar(BAR_AF + s), PAIR_THREADS); mbar_init(bar(BAR_AE + s), 1); }
         for (int s = 0; s < NBUF; ++s) { mbar_init(bar(BAR_TF + s), 1); mbar_init(bar(BAR_TE + s), PAIR_THREADS); }
         mbar_init(bar(BAR_PB), 1);
-        for (int s = 0; s < RES_RING; ++s) { mbar_init(bar(BAR_RF + s), 128); mbar_init(bar(BAR_RE + s), 256); }
-        for (int s = 0; s < 2; ++s) { mbar_init(bar(BAR_PF + s), 128); mbar_init(bar(BAR_PE + s), 128); }
+        for (int s = 0; s < RES_RING; ++s) { mbar_init(bar(BAR_RF + s), 4); mbar_init(bar(BAR_RE + s), 8); }
+        for (int s = 0; s < 2; ++s) { mbar_init(bar(BAR_PF + s), 4); mbar_init(bar(BAR_PE + s), 4); }
         fence_barrier_init();
     }
     if (warp == W_MMA) { if (CTA2) tmem_alloc2(smem_u32(tmem_ptr_s), 512); else tmem_alloc(smem_u32(tmem_ptr_s), 512); }
@@ -626,8 +626,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
             }
             const long long tc2 = (DBG && prof && rec) ? clock64() : 0;
             fence_async_smem();
-            arrive_mma_side(BAR_AF + sa);
-            mbar_arrive(bar(BAR_XE + sx));
+            __syncwarp();
+            if (lane == 0) { arrive_mma_side(BAR_AF + sa); mbar_arrive(bar(BAR_XE + sx)); }
             if (DBG && prof && rec) {
                 const long long tc3 = clock64();
                 pacc[2] += tc1 - tc0; pacc[3] += tc2 - tc1; pacc[4] += tc3 - tc2;
@@ -664,7 +664,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
                 tc_fence_after();
                 if (!(DBG && (p.dbg_skip & 4))) scan_buffer<0, DBG>(lane_base + buf * UNIT_N, rA, rB, dbg ? dbg + g * UNIT_N - 0 : nullptr);
                 tc_fence_before();
-                arrive_mma_side(BAR_TE + buf);
+                __syncwarp();
+                if (lane == 0) arrive_mma_side(BAR_TE + buf);
             }
             if (U == 4) {   // second unit (codes 128*(g+2) ..)
                 const uint32_t uc = it * 4u + (uint32_t)g + 2u, buf = uc % NBUF, pht = (uc / NBUF) & 1u;
@@ -672,7 +673,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
                 tc_fence_after();
                 if (!(DBG && (p.dbg_skip & 4))) scan_buffer<8, DBG>(lane_base + buf * UNIT_N, rA, rB, dbg ? dbg + (g + 2) * UNIT_N - 8 * 16 : nullptr);
                 tc_fence_before();
-                arrive_mma_side(BAR_TE + buf);
+                __syncwarp();
+                if (lane == 0) arrive_mma_side(BAR_TE + buf);
             }
             float m1, m2;
             int k1;
@@ -687,12 +689,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
                 if (g == 0) {                    // hand this group's result to group 1
                     mbar_wait(bar(BAR_PE + ps), php ^ 1u);
                     part_s[ps * TILE_M + row_in_tile] = make_float4(m1, m2, __int_as_float(k1), 0.f);
-                    mbar_arrive(bar(BAR_PF + ps));
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar(BAR_PF + ps));
                     continue;
                 }
                 wait_t(BAR_PF + ps, php, 2, rec);
                 const float4 o = part_s[ps * TILE_M + row_in_tile];
-                mbar_arrive(bar(BAR_PE + ps));
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(BAR_PE + ps));
                 const int ko = __float_as_int(o.z);
                 m2 = fminf(fminf(o.y, m2), fmaxf(o.x, m1));
                 const bool take_other = (o.x < m1) || (o.x == m1 && ko < k1);   // equal scores: lowest code (gap 0 -> flagged anyway)
@@ -720,7 +724,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
                 basei = __shfl_sync(0xffffffffu, basei, leader);
                 if (code == -1) p.flagged_rows[basei + __popc(fl & ((1u << lane) - 1u))] = (int)grow;
             }
-            mbar_arrive(bar(BAR_RF + rs));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(BAR_RF + rs));
         }
         if (DBG && prof && rec) { flush(pbase, 0); flush(pbase + 1, 1); if (g) { flush(PF_EPI1_WAIT_PF, 2); flush(PF_EPI1_WAIT_RE, 3); } prof[g ? PF_EPI1_TOTAL : PF_EPI0_TOTAL] = (unsigned long long)(clock64() - t_role0); }
     } else {
@@ -765,7 +770,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
                     }
                 }
             }
-            mbar_arrive(bar(BAR_RE + rs));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(BAR_RE + rs));
         }
         if (DBG && prof && rec) { flush(PF_OUT_WAIT_RF, 0); prof[PF_OUT_TOTAL] = (unsigned long long)(clock64() - t_role0); }
         if (p.diff_acc) {
