@@ -144,7 +144,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tcgen05"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tcgen05", "tcgen05_bf16"])
     ap.add_argument("--dist", default="clustered", choices=["clustered", "randn"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -189,8 +189,17 @@ def main():
         return q(xs[i % 3])
 
     def reset():
-        q.embed.data.copy_(embed0); q.embed_avg.data.copy_(embed0); q.cluster_size.data.zero_()
+        # EMA steady state of a trained codebook: cluster_size = expected rows per code, embed_avg = embed * cluster_size,
+        # so training steps keep the codes where the (clustered) data are instead of replaying the reference's
+        # start-up transient (cluster_size starts at 0 -> never-hit codes blow up ~1e5x after the first update)
+        q.embed.data.copy_(embed0)
+        if args.dist == "clustered":
+            q.cluster_size.data.fill_(float(world * N_ROWS) / K)
+            q.embed_avg.data.copy_(embed0 * (float(world * N_ROWS) / K))
+        else:
+            q.embed_avg.data.copy_(embed0); q.cluster_size.data.zero_()
 
+    reset()
     for i in range(warmup):
         step(i)
     reset()
@@ -228,6 +237,8 @@ def main():
     diff = torch.empty((), device=dev)
     stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     eng = _native.ENGINES[args.engine]
+    if args.engine == "auto":                 # time the kernel variant the module's precision policy settled on
+        eng = _native.ENGINE_TCGEN05_BF16 if q._filter["mode"] == "bf16" else _native.ENGINE_TCGEN05
     reset()
     _native.check(lib.vqb200_codebook_prepare(_native.ptr(q.embed), D, K, _native.ptr(ws["image"]), stream), "prepare")
 
@@ -318,6 +329,7 @@ def main():
                 "config": {"workload": "cfg-2: bottom quantizer, x=[128,64,64,64] fp32 per GPU, D=64, K=512, train fwd+EMA",
                            "rows_per_gpu": N_ROWS, "dim": D, "n_embed": K, "distribution": args.dist, "engine": args.engine,
                            "l2_policy": "3 rotating 134 MB input batches (each larger than the 126 MB L2)",
+                           "codebook_state": "EMA steady state (cluster_size = N/K, embed_avg = embed*N/K)" if args.dist == "clustered" else "reference init",
                            "parallelism": f"dp{world}"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches,
                 "roofline": roofline, "cpu_baseline": cpu}

@@ -47,6 +47,7 @@ extern "C" {
 #define VQB200_ENGINE_AUTO    0   /* tcgen05 path when the shape is covered, else exact SIMT        */
 #define VQB200_ENGINE_SIMT    1   /* exact fp32 SIMT distance kernel                                */
 #define VQB200_ENGINE_TCGEN05 2   /* TMA + tcgen05 split-bf16 filter with exact fp32 re-score       */
+#define VQB200_ENGINE_TCGEN05_BF16 3 /* same kernel, plain-bf16 filter: 1/3 of the MMAs, wider bound (more exact re-scores) */
 
 int         vqb200_abi_version(void);
 const char* vqb200_error_string(int code);
@@ -56,7 +57,9 @@ uint64_t    vqb200_launch_count(void);         /* kernels launched by this libra
 /* ---- workspace sizes (bytes) ------------------------------------------------------------------ */
 /* prepared codebook image: code-major fp32 copy, ||e_k||^2, tensor-core operand images            */
 size_t vqb200_codebook_bytes(int32_t dim, int32_t n_embed);
-/* per-call scratch of the forward (diff accumulator, flagged-row list, counters)                   */
+/* per-call scratch of the forward (diff accumulator, flagged-row list, counters).  Layout contract used
+ * by adaptive callers: int32 at byte offset 16 = number of rows the last tcgen05 forward sent to the
+ * exact re-score.                                                                                   */
 size_t vqb200_forward_scratch_bytes(int64_t n_rows, int32_t dim, int32_t n_embed);
 /* packed codebook statistics: n_embed*dim per-code sums (code-major), then n_embed counts, then 4
  * spare floats the EMA kernels use as scalars; only the first n_embed*(dim+1) floats are all-reduced */
@@ -116,8 +119,11 @@ int vqb200_debug_tc_scores(const float* d_x, int64_t n_rows, int32_t dim, int32_
  * the caller; slot meaning = enum ProfSlot in csrc/tc_kernel.cuh (pipeline bubble analysis for profiles/). */
 int vqb200_debug_tc_profile(const float* d_x, int64_t n_rows, int32_t dim, int32_t n_embed,
                             const void* d_codebook, float* d_quantize, int64_t* d_embed_ind,
-                            void* d_scratch, uint64_t* d_prof, void* stream);
+                            void* d_scratch, uint64_t* d_prof, int32_t engine, void* stream);
 int vqb200_tc_profile_slots(void);
+/* 1 when vqb200_quantize_forward would take the tcgen05 engine for this shape / layout / pointer alignment */
+int vqb200_tc_supported(const float* d_x, int64_t n_rows, int32_t dim, int32_t n_embed,
+                        int64_t rows_per_image, int64_t image_stride, int64_t row_stride, int64_t col_stride);
 int vqb200_tc_split(void);   /* 3 = split-bf16 filter (default), 1 = plain bf16 (env VQB200_TC_SPLIT) */
 
 /* ---- host-buffer convenience path (what bench.py's `e2e` times) -------------------------------- */

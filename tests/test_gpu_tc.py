@@ -148,3 +148,83 @@ def test_tc_nonfinite_rows_do_not_poison_neighbours():
     keep[17] = keep[130] = False
     assert torch.equal(ind[keep], ind_ref[keep])
     assert int(ind.min()) >= 0 and int(ind.max()) < 512
+
+
+def test_tc_plain_bf16_filter_is_exact_after_rescore():
+    """engine='tcgen05_bf16': the cheap filter certifies few rows on N(0,1) inputs; the exact re-score must make the
+    result identical to the SIMT engine anyway (heavy use of the flagged-row path)."""
+    torch.manual_seed(21)
+    D, K, N = 64, 512, 128 * 150 + 9
+    a = vq.Quantize(D, K, engine="tcgen05_bf16").to(DEV).train()
+    b = vq.Quantize(D, K, engine="simt").to(DEV).train()
+    b.load_state_dict(a.state_dict())
+    x = torch.randn(N, D, device=DEV, generator=torch.Generator(device=DEV).manual_seed(6))
+    qa, da, ia = a(x)
+    qb, db, ib = b(x)
+    assert int((ia != ib).sum()) == 0
+    assert torch.equal(qa, qb)
+    assert abs(float(da) - float(db)) <= 1e-6 * float(db)
+    assert col_rel_err(a.embed_avg.cpu().numpy(), b.embed_avg.cpu().numpy()) <= REL_TOL
+
+
+def test_auto_engine_adapts_filter_precision_without_changing_results():
+    import copy
+    torch.manual_seed(22)
+    D, K, N = 64, 512, 128 * 150
+    q = vq.Quantize(D, K).to(DEV).eval()
+    ref = vq.Quantize(D, K, engine="simt").to(DEV).eval()
+    ref.load_state_dict(q.state_dict())
+    x = torch.randn(N, D, device=DEV)                      # many near-ties -> the policy must leave the bf16 filter
+    modes = []
+    for _ in range(4):
+        _, _, ind = q(x)
+        torch.cuda.synchronize()
+        modes.append(q._filter["mode"])
+        assert torch.equal(ind, ref(x)[2])
+    assert "split" in modes
+    q2 = copy.deepcopy(q)                                  # pending CUDA event / workspaces must not break deepcopy
+    assert torch.equal(q2(x)[2], ref(x)[2])
+
+
+@pytest.mark.parametrize("K", [512, 256])
+def test_tc_many_trips_per_cta(K):
+    """More tiles than 3x the SM count: every persistent CTA makes several trips, so the stage / TMEM-buffer
+    phase logic (and the CTA-pair tail, where the second tile of the last pair lies past the end) is exercised."""
+    torch.manual_seed(11)
+    D, N = 64, 128 * 148 * 3 + 128 + 77
+    a = vq.Quantize(D, K, engine="tcgen05").to(DEV).eval()
+    b = vq.Quantize(D, K, engine="simt").to(DEV).eval()
+    b.load_state_dict(a.state_dict())
+    x = torch.randn(N, D, device=DEV, generator=torch.Generator(device=DEV).manual_seed(5))
+    qa, da, ia = a(x)
+    qb, db, ib = b(x)
+    _, nbad, _ = tie_tolerant_index_mismatches(x.cpu().numpy(), b.embed.cpu().numpy(), ia.cpu().numpy(), ib.cpu().numpy())
+    assert nbad == 0
+    if int((ia != ib).sum()) == 0:
+        assert torch.equal(qa, qb)
+        assert abs(float(da) - float(db)) <= 1e-6 * float(db)
+
+
+@pytest.mark.parametrize("engine", ["tcgen05", "tcgen05_bf16"])
+@pytest.mark.parametrize("live_codes", [1, 3, 40])
+def test_tc_fused_statistics_with_skewed_codes(engine, live_codes):
+    """Heavily skewed assignments (collapsed codebook: a handful of live codes): the per-code sums and
+    counts behind the tensor-core engine must equal the float64 segmented sums."""
+    torch.manual_seed(31)
+    D, K, N = 64, 512, 128 * 301 + 17
+    q = vq.Quantize(D, K, engine=engine).to(DEV).train()
+    embed0 = q.embed.clone()
+    live = torch.randperm(K, device=DEV)[:live_codes]
+    pick = live[torch.randint(0, live_codes, (N,), device=DEV)]
+    x = (embed0.t()[pick] + 0.05 * torch.randn(N, D, device=DEV)).contiguous()
+    _, _, ind = q(x)
+    assert torch.equal(ind, pick)
+    # float64 segmented sums of what the kernel must have accumulated
+    sums = torch.zeros(K, D, dtype=torch.float64, device=DEV).index_add_(0, ind, x.double())
+    counts = torch.bincount(ind, minlength=K).double()
+    decay = 0.99
+    want_cs = counts * (1 - decay)
+    want_avg = embed0.double() * decay + sums.t() * (1 - decay)
+    assert torch.allclose(q.cluster_size.double(), want_cs, rtol=1e-6, atol=0)
+    err = (q.embed_avg.double() - want_avg).abs().max(0).values / want_avg.abs().max(0).values
+    assert float(err.max()) <= REL_TOL

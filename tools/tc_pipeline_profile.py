@@ -16,6 +16,7 @@ SLOTS = ["prod_wait_xe", "mma_wait_af", "mma_wait_te", "mma_total", "conv_wait_x
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 128 * 64 * 64
+    eng = _native.ENGINES[sys.argv[2]] if len(sys.argv) > 2 else _native.ENGINE_TCGEN05
     lib = _native.load()
     dev = "cuda:0"
     D, K = 64, 512
@@ -33,12 +34,12 @@ def main():
     for rep in range(3):
         prof = torch.zeros(160, ns, dtype=torch.int64, device=dev)
         _native.check(lib.vqb200_debug_tc_profile(_native.ptr(x), n, D, K, _native.ptr(image), _native.ptr(quant),
-                                                  _native.ptr(ind), _native.ptr(scratch), _native.ptr(prof), st), "profile")
+                                                  _native.ptr(ind), _native.ptr(scratch), _native.ptr(prof), eng, st), "profile")
         torch.cuda.synchronize()
     p = prof.cpu().double()
     p = p[p[:, SLOTS.index("kernel")] > 0]
     tiles = (n + 127) // 128
-    print(f"split={lib.vqb200_tc_split()} rows={n} tiles={tiles} ctas={p.shape[0]} tiles/cta~{tiles / p.shape[0]:.1f}")
+    print(f"engine={eng} rows={n} tiles={tiles} ctas={p.shape[0]} tiles/cta~{tiles / p.shape[0]:.1f}")
     print(f"{'slot':16s} {'mean cyc/CTA':>14s} {'per tile':>10s} {'% kernel':>9s}")
     kern = p[:, SLOTS.index("kernel")].mean()
     for i, name in enumerate(SLOTS):

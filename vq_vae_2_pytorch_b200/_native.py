@@ -11,8 +11,8 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvqb200.so")
 
-ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1, 2
-ENGINES = {"auto": ENGINE_AUTO, "simt": ENGINE_SIMT, "tcgen05": ENGINE_TCGEN05}
+ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05, ENGINE_TCGEN05_BF16 = 0, 1, 2, 3
+ENGINES = {"auto": ENGINE_AUTO, "simt": ENGINE_SIMT, "tcgen05": ENGINE_TCGEN05, "tcgen05_bf16": ENGINE_TCGEN05_BF16}
 
 _p = C.c_void_p
 _i32, _i64, _f32, _sz = C.c_int32, C.c_int64, C.c_float, C.c_size_t
@@ -33,7 +33,8 @@ SIGNATURES = {
     "vqb200_embed_code": (C.c_int, [_p, _i64, _p, _i32, _i32, _p, _p, _p]),
     "vqb200_debug_tc_scores": (C.c_int, [_p, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p]),
     "vqb200_tc_split": (C.c_int, []),
-    "vqb200_debug_tc_profile": (C.c_int, [_p, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p]),
+    "vqb200_tc_supported": (C.c_int, [_p, _i64, _i32, _i32, _i64, _i64, _i64, _i64]),
+    "vqb200_debug_tc_profile": (C.c_int, [_p, _i64, _i32, _i32, _p, _p, _p, _p, _p, _i32, _p]),
     "vqb200_tc_profile_slots": (C.c_int, []),
     "vqb200_host_ctx_create": (C.c_int, [_i64, _i32, _i32, C.POINTER(_p)]),
     "vqb200_host_ctx_destroy": (None, [_p]),

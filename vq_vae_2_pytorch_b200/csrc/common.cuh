@@ -36,7 +36,7 @@ __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a -
 // tensor-core operand image (tc_kernel.cuh): per code 2 x dim bf16 (hi, lo) + 32 B misc row + fp32 norm
 __host__ __device__ inline size_t tc_image_bytes(int dim, int n_embed) {
     size_t dpad = (size_t)(dim + 63) / 64 * 64;
-    return (size_t)n_embed * (dpad * 4 + 32 + 4) + 1024;
+    return (size_t)n_embed * (dpad * 4 + 32 + 4 + 32) + 1024;
 }
 
 __host__ __device__ inline size_t codebook_bytes(int dim, int n_embed) {

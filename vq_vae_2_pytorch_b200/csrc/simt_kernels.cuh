@@ -329,21 +329,31 @@ k_code_stats(const float* __restrict__ x, RowLayout L, int D, int K, const int64
     for (int i = tid; i < K; i += CS_THREADS) out[(size_t)K * D + i] = (float)cnt_total[i];
 }
 
-// stats[i] = sum over CTAs of partials[c][i], fixed order (deterministic for a fixed grid)
-__global__ void k_stats_reduce(const float* __restrict__ partials, int n_parts, int n, float* __restrict__ stats) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float s = 0.f;
-    int c = 0;
-    for (; c + 8 <= n_parts; c += 8) {                 // 8 independent loads in flight, fixed summation order
+// stats[i] += sum over CTAs of partials[c][i].  block = (32, 4): 128 consecutive elements per block, four 32-wide
+// column groups; thread-row y sums the tables c = y, y+4, ... (8 independent loads in flight), the four partial
+// sums are folded in a fixed order -> deterministic for a fixed grid.
+__global__ void k_stats_fold(const float* __restrict__ partials, int n_parts, int n, float* __restrict__ stats) {
+    __shared__ float part[4][4][32];
+    const int col = threadIdx.x, y = threadIdx.y;
+    const int i0 = blockIdx.x * 128;
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = y; c < n_parts; c += 8) {
+        const int c2 = c + 4;
         float v[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = __ldcs(partials + (size_t)(c + u) * n + i);
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * 32 + col;
+            v[u] = i < n ? __ldcs(partials + (size_t)c * n + i) : 0.f;
+            v[4 + u] = (i < n && c2 < n_parts) ? __ldcs(partials + (size_t)c2 * n + i) : 0.f;
+        }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) s += v[u];
+        for (int u = 0; u < 4; ++u) s[u] += v[u] + v[4 + u];
     }
-    for (; c < n_parts; ++c) s += partials[(size_t)c * n + i];
-    stats[i] = s;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) part[y][u][col] = s[u];
+    __syncthreads();
+    const int u = y, i = i0 + u * 32 + col;
+    if (i < n) stats[i] += (part[0][u][col] + part[1][u][col]) + (part[2][u][col] + part[3][u][col]);
 }
 
 __host__ __device__ inline size_t code_stats_smem_bytes(int D, int K) {

@@ -211,11 +211,12 @@ __device__ __forceinline__ void split3(float f, float& a, float& b, float& c) {
 __host__ __device__ inline size_t image_off_lo(int K) { return (size_t)K * 128; }
 __host__ __device__ inline size_t image_off_misc(int K) { return (size_t)K * 256; }
 __host__ __device__ inline size_t image_off_enorm(int K) { return (size_t)K * 288; }
-__host__ __device__ inline size_t image_bytes(int K) { return (size_t)K * 288 + (size_t)K * 4; }
+__host__ __device__ inline size_t image_off_misc1(int K) { return (size_t)K * 292; }     // misc block carrying the plain-bf16 bound
+__host__ __device__ inline size_t image_bytes(int K) { return (size_t)K * 292 + (size_t)K * 32; }
 
 // one thread per (code, 8-dim chunk); requires D == 64
 __global__ void k_tc_image(const float* __restrict__ cbT, const float* __restrict__ ee, unsigned char* __restrict__ img,
-                           int K, float cA, float cB) {
+                           int K, float cA, float cA1, float cB) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     int k = t >> 3, c = t & 7;
     if (k >= K) return;
@@ -243,6 +244,12 @@ __global__ void k_tc_image(const float* __restrict__ cbT, const float* __restric
             make_uint4(pack_bf16(b1, b2), pack_bf16(b3, 1.f), pack_bf16(1.f, 1.f), pack_bf16(t6, t7));
         *reinterpret_cast<uint4*>(m + sw32_chunk_off((uint32_t)k, 1)) = make_uint4(0, 0, 0, 0);
         reinterpret_cast<float*>(img + image_off_enorm(K))[k] = ne;
+        // same row with the wider bound of the plain-bf16 filter (one image serves both filter precisions)
+        const float t6b = -bf16_round(cA1 * ne * 1.0078125f);
+        unsigned char* m1 = img + image_off_misc1(K);
+        *reinterpret_cast<uint4*>(m1 + sw32_chunk_off((uint32_t)k, 0)) =
+            make_uint4(pack_bf16(b1, b2), pack_bf16(b3, 1.f), pack_bf16(1.f, 1.f), pack_bf16(t6b, t7));
+        *reinterpret_cast<uint4*>(m1 + sw32_chunk_off((uint32_t)k, 1)) = make_uint4(0, 0, 0, 0);
     }
 }
 
@@ -493,7 +500,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
                 bulk_g2s(sB + (uint32_t)u * UROWS * 128u, p.image + krow * 128, UROWS * 128u, bar(BAR_B));
                 if (NSPLIT == 3)
                     bulk_g2s(sB + P::off_b_lo(K) + (uint32_t)u * UROWS * 128u, p.image + image_off_lo(K) + krow * 128, UROWS * 128u, bar(BAR_B));
-                bulk_g2s(sB + P::off_b_misc(K) + (uint32_t)u * UROWS * 32u, p.image + image_off_misc(K) + krow * 32, UROWS * 32u, bar(BAR_B));
+                bulk_g2s(sB + P::off_b_misc(K) + (uint32_t)u * UROWS * 32u, p.image + (NSPLIT == 3 ? image_off_misc(K) : image_off_misc1(K)) + krow * 32, UROWS * 32u, bar(BAR_B));
             }
             for (uint32_t it = 0; it < n_iter; ++it) {
                 const int64_t t = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
@@ -824,8 +831,18 @@ inline bool tc_supported(const RowLayout& L, const float* x, int dim, int n_embe
 inline int tc_prepare_codebook(const CodebookImage& cb, int dim, int n_embed, cudaStream_t st) {
     if (!tc_shape_ok(dim, n_embed)) return 0;
     int threads = n_embed * 8;
-    tc::k_tc_image<<<(threads + 255) / 256, 256, 0, st>>>(cb.cbT, cb.ee, cb.tc, n_embed, tc::bound_cA(tc_nsplit()), tc::BOUND_CB);
+    tc::k_tc_image<<<(threads + 255) / 256, 256, 0, st>>>(cb.cbT, cb.ee, cb.tc, n_embed, tc::bound_cA(3), tc::bound_cA(1), tc::BOUND_CB);
     return cudaGetLastError() != cudaSuccess;
+}
+
+// CTAs the tensor-core kernel runs for n_rows rows (= number of private statistics tables it fills)
+inline int tc_grid(int64_t n_rows, bool pair) {
+    int64_t n_tiles = (n_rows + tc::TILE_M - 1) / tc::TILE_M;
+    int grid = (int)std::min<int64_t>(n_tiles, tc_num_sms());
+    if (!pair) return grid;
+    grid = std::max(2, (grid + 1) / 2 * 2);      // whole CTA pairs; 148 SMs = 74 pairs
+    if (grid > tc_num_sms()) grid = tc_num_sms() / 2 * 2;
+    return grid;
 }
 
 template <int NSPLIT, int AS, int XS, bool DBG, bool CTA2>
@@ -838,14 +855,11 @@ inline int tc_launch(const tc::Params& prm, cudaStream_t st) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 1;
         configured = smem;
     }
-    int64_t n_tiles = (prm.n_rows + tc::TILE_M - 1) / tc::TILE_M;
-    int grid = (int)std::min<int64_t>(n_tiles, tc_num_sms());
+    const int grid = tc_grid(prm.n_rows, CTA2);
     if (!CTA2) {
         kern<<<grid, tc::THREADS, smem, st>>>(prm);
         return cudaGetLastError() != cudaSuccess;
     }
-    grid = std::max(2, (grid + 1) / 2 * 2);      // whole CTA pairs; 148 SMs = 74 pairs
-    if (grid > tc_num_sms()) grid = tc_num_sms() / 2 * 2;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(tc::THREADS);
@@ -863,7 +877,8 @@ inline int tc_launch(const tc::Params& prm, cudaStream_t st) {
 inline int tc_forward(const float* x, const RowLayout& L, int dim, int n_embed, const CodebookImage& cb,
                       float* quantize, int64_t* embed_ind, const ForwardScratch& sc, double* diff_acc,
                       float* sums, float* counts, float* dbg_scores, cudaStream_t st,
-                      unsigned long long* prof = nullptr) {
+                      unsigned long long* prof = nullptr, int nsplit = 0, int* grid_out = nullptr) {
+    if (nsplit != 1 && nsplit != 3) nsplit = tc_nsplit();
     (void)dim;
     tc::Params prm;
     prm.x = x; prm.n_rows = L.n_rows; prm.K = n_embed; prm.image = cb.tc; prm.cbT = cb.cbT;
@@ -872,14 +887,19 @@ inline int tc_forward(const float* x, const RowLayout& L, int dim, int n_embed, 
     prm.flagged_count = sc.flagged_count; prm.flagged_rows = sc.flagged_rows; prm.dbg_scores = dbg_scores;
     prm.prof = prof;
     { const char* e = getenv("VQB200_DBG_SKIP"); prm.dbg_skip = e ? atoi(e) : 0; }
-    prm.cA = tc::bound_cA(tc_nsplit()); prm.cB = tc::BOUND_CB;
+    prm.cA = tc::bound_cA(nsplit); prm.cB = tc::BOUND_CB;
     const bool dbg = dbg_scores || prof;           // diagnostics live in a separate instantiation
     static const bool pair = [] { const char* e = getenv("VQB200_TC_CTA2"); return e ? atoi(e) != 0 : true; }();
-    if (tc_nsplit() == 3) {
+    static const bool pair1 = [] { const char* e = getenv("VQB200_TC_CTA2_BF16"); return e ? atoi(e) != 0 : false; }();
+    const bool use_pair = n_embed == 512 && (nsplit == 3 ? pair : pair1);
+    if (grid_out) *grid_out = tc_grid(L.n_rows, use_pair);
+    if (nsplit == 3) {
         if (pair && n_embed == 512)                // CTA pairs: half the operand image per CTA -> double-buffered A and x
             return dbg ? tc_launch<3, 2, 2, true, true>(prm, st) : tc_launch<3, 2, 2, false, true>(prm, st);
         return dbg ? tc_launch<3, 1, 1, true, false>(prm, st) : tc_launch<3, 1, 1, false, false>(prm, st);
     }
+    if (pair1 && n_embed == 512)
+        return dbg ? tc_launch<1, 2, 3, true, true>(prm, st) : tc_launch<1, 2, 3, false, true>(prm, st);
     return dbg ? tc_launch<1, 2, 2, true, false>(prm, st) : tc_launch<1, 2, 2, false, false>(prm, st);
 }
 

@@ -76,9 +76,10 @@ int forward_impl(const float* d_x, const RowLayout& L, int dim, int n_embed, con
     }
     if (L.n_rows > 0) {
         bool use_tc = false;
-        if (engine == VQB200_ENGINE_TCGEN05 || engine == VQB200_ENGINE_AUTO)
+        if (engine == VQB200_ENGINE_TCGEN05 || engine == VQB200_ENGINE_TCGEN05_BF16 || engine == VQB200_ENGINE_AUTO)
             use_tc = tc_supported(L, d_x, dim, n_embed);
-        if (engine == VQB200_ENGINE_TCGEN05 && !use_tc) return VQB200_EUNSUPPORTED;
+        if ((engine == VQB200_ENGINE_TCGEN05 || engine == VQB200_ENGINE_TCGEN05_BF16) && !use_tc) return VQB200_EUNSUPPORTED;
+        const int nsplit = engine == VQB200_ENGINE_TCGEN05_BF16 ? 1 : (engine == VQB200_ENGINE_TCGEN05 ? 3 : 0);
         // statistics: private-table segmented reduction when [K][D] fp32 fits in shared memory, else the
         // gather kernels fall back to global atomics
         const size_t cs_smem = code_stats_smem_bytes(dim, n_embed);
@@ -94,7 +95,7 @@ int forward_impl(const float* d_x, const RowLayout& L, int dim, int n_embed, con
             // tensor-core filter + fused output for certified rows; flagged rows -> exact SIMT fix-up
             VQ_CUDA(cudaMemsetAsync(sc.flagged_count, 0, sizeof(int), st));
             int rc = tc_forward(d_x, L, dim, n_embed, cb, d_quantize, d_ind, sc, d_diff ? sc.diff_acc : nullptr, sums,
-                                counts, dbg_scores, st, prof);
+                                counts, dbg_scores, st, prof, nsplit);
             g_launches.fetch_add(1);
             if (rc) return cuda_fail(cudaGetLastError());
             k_assign_exact<<<sms * 2, AS_THREADS, 0, st>>>(d_x, L, dim, n_embed, cb.cbT, cb.ee, d_ind,
@@ -119,14 +120,10 @@ int forward_impl(const float* d_x, const RowLayout& L, int dim, int n_embed, con
                 VQ_LAUNCH_CHECK();
             }
         }
-    }
-    if (L.n_rows > 0 && d_stats) {
-        const size_t cs_smem = code_stats_smem_bytes(dim, n_embed);
-        if (cs_smem <= 200 * 1024 && n_embed <= 65535) {
-            // accumulate into d_stats across calls when zero_first == false (host-buffer chunking)
+        if (stats_kernel) {
             VQ_CUDA(cudaFuncSetAttribute(k_code_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs_smem));
             // rows per trip chosen so the trips divide evenly over the SMs (one CTA per SM, private table each)
-            const int sms_cs = std::min(tc_num_sms(), STAT_PARTS - 1);
+            const int sms_cs = std::min(tc_num_sms(), STAT_PARTS);
             int64_t waves = (L.n_rows + (int64_t)sms_cs * CS_CHUNK - 1) / ((int64_t)sms_cs * CS_CHUNK);
             int64_t chunk = (L.n_rows + sms_cs * waves - 1) / (sms_cs * waves);
             chunk = std::min<int64_t>(CS_CHUNK, std::max<int64_t>(256, (chunk + 31) / 32 * 32));
@@ -134,12 +131,9 @@ int forward_impl(const float* d_x, const RowLayout& L, int dim, int n_embed, con
             int parts = (int)std::min<int64_t>(n_chunks, sms_cs);
             k_code_stats<<<parts, CS_THREADS, cs_smem, st>>>(d_x, L, dim, n_embed, d_ind, sc.stat_partials, (int)chunk);
             VQ_LAUNCH_CHECK();
-            int n = n_embed * (dim + 1);
-            // the running total lives in partial slot [parts] so chunked calls keep accumulating
-            float* prev = sc.stat_partials + (size_t)parts * n;
-            if (zero_first) VQ_CUDA(cudaMemsetAsync(prev, 0, (size_t)n * 4, st));
-            else VQ_CUDA(cudaMemcpyAsync(prev, d_stats, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
-            k_stats_reduce<<<(n + 63) / 64, 64, 0, st>>>(sc.stat_partials, parts + 1, n, d_stats);
+            // d_stats += sum of the per-CTA tables (d_stats was cleared when zero_first, else keeps accumulating)
+            const int nstat = n_embed * (dim + 1);
+            k_stats_fold<<<(nstat + 127) / 128, dim3(32, 4), 0, st>>>(sc.stat_partials, parts, nstat, d_stats);
             VQ_LAUNCH_CHECK();
         }
     }
@@ -219,7 +213,7 @@ int vqb200_quantize_forward(const float* d_x, int64_t n_rows, int32_t dim, int32
     if (!d_codebook || !d_scratch || dim <= 0 || n_embed <= 0 || n_rows < 0) return VQB200_EINVAL;
     if (n_rows > 0 && (!d_x || !d_embed_ind)) return VQB200_EINVAL;
     if (n_rows > (int64_t)INT32_MAX) return VQB200_EUNSUPPORTED;
-    if (engine < VQB200_ENGINE_AUTO || engine > VQB200_ENGINE_TCGEN05) return VQB200_EINVAL;
+    if (engine < VQB200_ENGINE_AUTO || engine > VQB200_ENGINE_TCGEN05_BF16) return VQB200_EINVAL;
     if (n_rows > 0 && !layout_ok(n_rows, dim, rows_per_image, image_stride, row_stride, col_stride))
         return VQB200_EUNSUPPORTED;
     RowLayout L{n_rows, rows_per_image > 0 ? rows_per_image : 1, image_stride, row_stride, col_stride};
@@ -286,13 +280,22 @@ int vqb200_debug_tc_scores(const float* d_x, int64_t n_rows, int32_t dim, int32_
 
 int vqb200_tc_split(void) { return tc_nsplit(); }
 
+int vqb200_tc_supported(const float* d_x, int64_t n_rows, int32_t dim, int32_t n_embed, int64_t rows_per_image,
+                        int64_t image_stride, int64_t row_stride, int64_t col_stride) {
+    if (n_rows <= 0 || rows_per_image <= 0) return 0;
+    RowLayout L{n_rows, rows_per_image, image_stride, row_stride, col_stride};
+    return tc_supported(L, d_x, dim, n_embed) ? 1 : 0;
+}
+
 int vqb200_debug_tc_profile(const float* d_x, int64_t n_rows, int32_t dim, int32_t n_embed, const void* d_codebook,
-                            float* d_quantize, int64_t* d_embed_ind, void* d_scratch, uint64_t* d_prof, void* stream) {
+                            float* d_quantize, int64_t* d_embed_ind, void* d_scratch, uint64_t* d_prof, int32_t engine,
+                            void* stream) {
     if (!d_x || !d_codebook || !d_embed_ind || !d_scratch || !d_prof || n_rows <= 0) return VQB200_EINVAL;
+    if (engine != VQB200_ENGINE_TCGEN05 && engine != VQB200_ENGINE_TCGEN05_BF16) return VQB200_EINVAL;
     RowLayout L{n_rows, n_rows, 0, dim, 1};
     if (!tc_supported(L, d_x, dim, n_embed)) return VQB200_EUNSUPPORTED;
     return forward_impl(d_x, L, dim, n_embed, d_codebook, d_quantize, d_embed_ind, nullptr, nullptr, d_scratch,
-                        VQB200_ENGINE_TCGEN05, true, false, n_rows, (cudaStream_t)stream, nullptr, -1,
+                        engine, true, false, n_rows, (cudaStream_t)stream, nullptr, -1,
                         reinterpret_cast<unsigned long long*>(d_prof));
 }
 int vqb200_tc_profile_slots(void) { return (int)tc::PROF_SLOTS; }

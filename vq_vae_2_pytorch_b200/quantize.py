@@ -10,6 +10,7 @@ There is no CPU or PyTorch fallback: non-CUDA tensors raise.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 from torch import nn
@@ -102,7 +103,8 @@ class Quantize(nn.Module):
     """Vector-quantisation layer with EMA codebook (reference vqvae.py:28-78).
 
     Extra keyword (not in the reference, defaults keep reference behaviour):
-      engine: "auto" | "simt" | "tcgen05" -- which assignment kernel the C ABI uses.
+      engine: "auto" | "simt" | "tcgen05" | "tcgen05_bf16" -- which assignment kernel the C ABI uses; "auto"
+              picks the tcgen05 engine when the shape is covered and adapts its filter precision (see _pick_engine).
     """
 
     def __init__(self, dim, n_embed, decay=0.99, eps=1e-5, engine="auto"):
@@ -122,6 +124,15 @@ class Quantize(nn.Module):
         self.register_buffer("embed_avg", embed.clone())                  # vqvae.py:40
         # private device workspaces (never in the state_dict)
         self._ws = {}
+        # adaptive filter precision of the tcgen05 engine (engine="auto"): speed only, results are exact either way
+        self._filter = {"mode": "bf16", "cooldown": 0, "pending": None}
+
+    def __getstate__(self):
+        # device workspaces / CUDA events are neither pickled nor deep-copied; they are rebuilt on first use
+        state = self.__dict__.copy()
+        state["_ws"] = {}
+        state["_filter"] = {"mode": "bf16", "cooldown": 0, "pending": None}
+        return state
 
     # ------------------------------------------------------------------ workspaces
     def _workspace(self, device, n_rows):
@@ -137,6 +148,46 @@ class Quantize(nn.Module):
                                         dtype=torch.uint8, device=device)
             ws["rows"] = n_rows
         return ws
+
+    # ------------------------------------------------------------------ filter precision policy
+    # The plain-bf16 tensor-core filter needs 1/3 of the MMAs of the split-bf16 one but certifies fewer rows when
+    # the two nearest codes are almost equidistant (e.g. N(0,1) inputs against a random codebook); uncertified rows
+    # cost an exact fp32 re-score.  The number of re-scored rows of a call is read back asynchronously (no sync) and
+    # decides the precision of later calls.  Either way the returned indices are the exact arg-min.
+    FLAG_SWITCH_FRACTION = 3e-3
+    SPLIT_COOLDOWN_CALLS = 64
+
+    def _pick_engine(self, x, lay):
+        if self.engine != "auto" or os.environ.get("VQB200_TC_SPLIT"):
+            return _native.ENGINES[self.engine]
+        lib = _native.load()
+        n, rpi, img, row, col = lay
+        if not lib.vqb200_tc_supported(_native.ptr(x), n, self.dim, self.n_embed, rpi, img, row, col):
+            return _native.ENGINE_AUTO
+        f = self._filter
+        pend = f["pending"]
+        if pend is not None and pend[0].query():
+            _, host_count, rows, mode_used = pend
+            f["pending"] = None
+            if mode_used == "bf16" and int(host_count[0]) > self.FLAG_SWITCH_FRACTION * rows:
+                f["mode"], f["cooldown"] = "split", self.SPLIT_COOLDOWN_CALLS
+        if f["mode"] == "split":
+            f["cooldown"] -= 1
+            if f["cooldown"] <= 0:
+                f["mode"] = "bf16"                # probe the cheap filter again
+        return _native.ENGINE_TCGEN05_BF16 if f["mode"] == "bf16" else _native.ENGINE_TCGEN05
+
+    def _note_flagged(self, ws, n, eng, dev):
+        f = self._filter
+        if eng not in (_native.ENGINE_TCGEN05_BF16, _native.ENGINE_TCGEN05) or f["pending"] is not None or n == 0:
+            return
+        host = ws.get("flag_host")
+        if host is None:
+            host = ws["flag_host"] = torch.zeros(1, dtype=torch.int32).pin_memory()
+        host.copy_(ws["scratch"][16:20].view(torch.int32), non_blocking=True)   # vqb200.h: int32 at byte 16 of the scratch
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))
+        f["pending"] = (ev, host, n, "bf16" if eng == _native.ENGINE_TCGEN05_BF16 else "split")
 
     def _check_input(self, x):
         if not isinstance(x, torch.Tensor):
@@ -167,7 +218,7 @@ class Quantize(nn.Module):
         diff = torch.empty((), dtype=torch.float32, device=dev)
         stats = ws["stats"] if self.training else None
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        eng = _native.ENGINES[self.engine]
+        eng = self._pick_engine(x, lay)
         with torch.cuda.device(dev):
             # the codebook image is re-derived from `embed` on every call: external writes to the buffer
             # (load_state_dict, .data.copy_, DDP buffer broadcast) can never leave it stale
@@ -177,6 +228,7 @@ class Quantize(nn.Module):
                 _native.ptr(x), n, self.dim, self.n_embed, rpi, img, row, col, _native.ptr(image),
                 _native.ptr(quantize), _native.ptr(ind), _native.ptr(diff), _native.ptr(stats),
                 _native.ptr(ws["scratch"]), eng, stream), "vqb200_quantize_forward")
+            self._note_flagged(ws, n, eng, dev)
             if self.training:
                 dist_fn.all_reduce(stats[: self.n_embed * (self.dim + 1)])  # vqvae.py:58-59 (one packed call)
                 _native.check(lib.vqb200_ema_update(
