@@ -737,43 +737,65 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
         if (DBG && prof && rec) { flush(pbase, 0); flush(pbase + 1, 1); if (g) { flush(PF_EPI1_WAIT_PF, 2); flush(PF_EPI1_WAIT_RE, 3); } prof[g ? PF_EPI1_TOTAL : PF_EPI0_TOTAL] = (unsigned long long)(clock64() - t_role0); }
     } else {
         // ================= output: gather, straight-through value, loss =================================
+        // 8 warps x 16 rows; a half-warp handles one row per instruction (16 lanes x 16 bytes = one 256-byte row), 8 rows
+        // per batch with all loads in flight together.  Fast path (every row of the batch certified, the common case):
+        // straight-line code, row addresses are compile-time offsets from one per-tile pointer.
         reg_dec<72>();
         const int ow = warp - W_OUT;             // rows ow*16 .. ow*16+15 of the tile
         const int half = lane >> 4, q4 = lane & 15;
         float dacc = 0.f;
         const bool rec = (warp == W_OUT && lane == 0);
+        constexpr int RQ = TC_D / 4;             // float4 per row
+        const size_t my_off = (size_t)(ow * 16 + half) * RQ + q4;       // my first row of a tile, my 16-byte column
+        const float4* cb4 = reinterpret_cast<const float4*>(p.cbT) + q4;
         const long long t_role0 = clock64();
         for (uint32_t it = 0; it < n_iter; ++it) {
             const int64_t t = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
             const uint32_t rs = it % RES_RING, phr = (it / RES_RING) & 1u;
             wait_t(BAR_RF + rs, phr, 0, rec);
-            const int64_t r0 = t * TILE_M;
+            const float4* xt = reinterpret_cast<const float4*>(p.x) + (size_t)t * TILE_M * RQ + my_off;
+            float4* qt = p.quantize ? reinterpret_cast<float4*>(p.quantize) + (size_t)t * TILE_M * RQ + my_off : nullptr;
+            const int* cs = codes_s + rs * TILE_M + ow * 16 + half;
             if (!(DBG && (p.dbg_skip & 1)))
-#pragma unroll 1
-            for (int b = 0; b < 2; ++b) {        // 8 output warps x 16 rows; 8 rows per batch
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
                 int kk[4];
                 float4 xv[4], qv[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int r = ow * 16 + b * 8 + i * 2 + half;
-                    kk[i] = codes_s[rs * TILE_M + r];
-                    if (kk[i] >= 0) xv[i] = __ldcg(reinterpret_cast<const float4*>(p.x + (r0 + r) * TC_D + q4 * 4));
-                }
+                for (int i = 0; i < 4; ++i) kk[i] = cs[b * 8 + i * 2];
+                const bool all_ok = __all_sync(0xffffffffu, (kk[0] | kk[1] | kk[2] | kk[3]) >= 0);
+                if (all_ok && !p.stat_sums) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    if (kk[i] >= 0) qv[i] = __ldcg(reinterpret_cast<const float4*>(p.cbT + (size_t)kk[i] * TC_D + q4 * 4));
+                    for (int i = 0; i < 4; ++i) xv[i] = __ldcg(xt + (b * 8 + i * 2) * RQ);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    if (kk[i] < 0) continue;
-                    const int r = ow * 16 + b * 8 + i * 2 + half;
-                    float4 d, o;
-                    d.x = qv[i].x - xv[i].x; d.y = qv[i].y - xv[i].y; d.z = qv[i].z - xv[i].z; d.w = qv[i].w - xv[i].w;
-                    o.x = xv[i].x + d.x; o.y = xv[i].y + d.y; o.z = xv[i].z + d.z; o.w = xv[i].w + d.w;
-                    dacc = fmaf(d.x, d.x, fmaf(d.y, d.y, fmaf(d.z, d.z, fmaf(d.w, d.w, dacc))));
-                    if (p.quantize) __stcs(reinterpret_cast<float4*>(p.quantize + (r0 + r) * TC_D + q4 * 4), o);
-                    if (p.stat_sums) {           // only when the caller has no room for the segmented-reduction kernel
-                        red_add_v4(p.stat_sums + (size_t)kk[i] * TC_D + q4 * 4, xv[i]);
-                        if (q4 == 0) red_add_f32(p.stat_counts + kk[i], 1.0f);
+                    for (int i = 0; i < 4; ++i) qv[i] = __ldcg(cb4 + (uint32_t)kk[i] * RQ);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float4 d, o;
+                        d.x = qv[i].x - xv[i].x; d.y = qv[i].y - xv[i].y; d.z = qv[i].z - xv[i].z; d.w = qv[i].w - xv[i].w;
+                        o.x = xv[i].x + d.x; o.y = xv[i].y + d.y; o.z = xv[i].z + d.z; o.w = xv[i].w + d.w;
+                        dacc = fmaf(d.x, d.x, fmaf(d.y, d.y, fmaf(d.z, d.z, fmaf(d.w, d.w, dacc))));
+                        if (qt) __stcs(qt + (b * 8 + i * 2) * RQ, o);
+                    }
+                } else {                         // some row flagged / past the end (or the atomics fallback for statistics)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (kk[i] >= 0) {
+                            xv[i] = __ldcg(xt + (b * 8 + i * 2) * RQ);
+                            qv[i] = __ldcg(cb4 + (uint32_t)kk[i] * RQ);
+                        }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (kk[i] < 0) continue;
+                        float4 d, o;
+                        d.x = qv[i].x - xv[i].x; d.y = qv[i].y - xv[i].y; d.z = qv[i].z - xv[i].z; d.w = qv[i].w - xv[i].w;
+                        o.x = xv[i].x + d.x; o.y = xv[i].y + d.y; o.z = xv[i].z + d.z; o.w = xv[i].w + d.w;
+                        dacc = fmaf(d.x, d.x, fmaf(d.y, d.y, fmaf(d.z, d.z, fmaf(d.w, d.w, dacc))));
+                        if (qt) __stcs(qt + (b * 8 + i * 2) * RQ, o);
+                        if (p.stat_sums) {       // only when the caller has no room for the segmented-reduction kernel
+                            red_add_v4(p.stat_sums + (size_t)kk[i] * TC_D + q4 * 4, xv[i]);
+                            if (q4 == 0) red_add_f32(p.stat_counts + kk[i], 1.0f);
+                        }
                     }
                 }
             }
