@@ -255,14 +255,14 @@ __global__ void k_tc_image(const float* __restrict__ cbT, const float* __restric
 
 
 // ---------------------------------------------------------------------------------------------------
-// epilogue scan of one 256-column accumulator unit (thread = row).
-// Every score feeds two families of running minima: class A = j mod 8 (8 registers) and class B = j div 8
-// (32 registers), each updated with one 3-input minimum per two scores -> ONE ALU op per score, no index
-// bookkeeping in the hot loop.  A and B together identify a column (j = 8 b + a), so afterwards
-//   m1  = the global minimum, found in exactly one A-class a* and one B-class b*  (arg-min = 8 b* + a*),
-//   m2  = min( min over A-classes != a*, min over B-classes != b* ) = the exact runner-up value,
-// because any other column differs from the winner in its A-class or its B-class.  If the minimum value
-// occurs in several classes (exact tie) the row is reported with m2 = m1 and goes to the exact re-score.
+// epilogue scan (thread = row).  A warpgroup sees up to 256 "virtual" columns per tile (two 128-column accumulator
+// units).  Every score feeds two families of running minima: class A = column mod 16 (16 registers) and class
+// B = column div 16 (16 registers), each updated with one 3-input minimum per two scores -> ONE ALU op per score, no
+// index bookkeeping in the hot loop.  A and B together identify a column (j = 16 b + a), so afterwards
+//   m1  = the global minimum, found in one A-class a* and one B-class b*  (arg-min = 16 b* + a*),
+//   m2  = min( second-smallest A-class minimum, second-smallest B-class minimum ) = the exact runner-up value,
+// because any other column differs from the winner in its A-class or its B-class.  "Second smallest" counts
+// duplicates, so an exact tie gives m2 == m1 and the row goes to the exact re-score.
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float fmin3(float a, float b, float c) { return fminf(a, fminf(b, c)); }
 
@@ -284,76 +284,143 @@ __device__ __forceinline__ void tmem_ld_wait16(uint32_t (&v)[16]) {
 template <int REGS> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
 template <int REGS> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
 
-__device__ __forceinline__ float min8(const float* e) {
-    return fmin3(fmin3(e[0], e[1], e[2]), fmin3(e[3], e[4], e[5]), fminf(e[6], e[7]));
+__device__ __forceinline__ float min16(const float* e) {
+    return fminf(fmin3(fmin3(e[0], e[1], e[2]), fmin3(e[3], e[4], e[5]), fmin3(e[6], e[7], e[8])),
+                 fmin3(fmin3(e[9], e[10], e[11]), fmin3(e[12], e[13], e[14]), e[15]));
 }
 
-// 16 scores of columns 16H .. 16H+15: class A = j mod 8 (rA[8]), class B = j div 8 (rB[32])
-template <int H, bool DBG>
-__device__ __forceinline__ void scan_half(const uint32_t (&v)[16], float (&rA)[8], float (&rB)[32], float* dbg) {
-    float key[16];
+// 32 scores of columns 32C .. 32C+31: class A = j mod 16 (rA[16]), class B = j div 16 (rB[16])
+template <int C, bool DBG>
+__device__ __forceinline__ void scan_chunk(const uint32_t (&v)[32], float (&rA)[16], float (&rB)[16], float* dbg) {
+    float key[32];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) key[i] = __uint_as_float(v[i]);
+    for (int i = 0; i < 32; ++i) key[i] = __uint_as_float(v[i]);
     if (DBG && dbg) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) dbg[H * 16 + j] = key[j];
+        for (int j = 0; j < 32; ++j) dbg[C * 32 + j] = key[j];
     }
 #pragma unroll
-    for (int a = 0; a < 8; ++a) rA[a] = fmin3(rA[a], key[a], key[a + 8]);
-    rB[2 * H] = min8(key);
-    rB[2 * H + 1] = min8(key + 8);
+    for (int a = 0; a < 16; ++a) rA[a] = fmin3(rA[a], key[a], key[a + 16]);
+    rB[2 * C] = min16(key);
+    rB[2 * C + 1] = min16(key + 16);
 }
 
-// software-pipelined walk over the 8 column groups (16 columns each) of one 128-column TMEM buffer: the load of
-// group H+1 is in flight while group H is reduced.  HB = index of the buffer's first group within the warpgroup's
-// 256 virtual columns (0 or 8), so the class-B minima land in fixed registers.
-template <int H, int HB, bool DBG>
-__device__ __forceinline__ void scan_pairs(uint32_t lane_addr, uint32_t (&va)[16], uint32_t (&vb)[16],
-                                           float (&rA)[8], float (&rB)[32], float* dbg) {
-    tmem_ld_wait16(va);
-    tmem_ld16(lane_addr + (H + 1) * 16, vb);
-    scan_half<HB + H, DBG>(va, rA, rB, dbg);
-    tmem_ld_wait16(vb);
-    if constexpr (H + 2 < 8) tmem_ld16(lane_addr + (H + 2) * 16, va);
-    scan_half<HB + H + 1, DBG>(vb, rA, rB, dbg);
-    if constexpr (H + 2 < 8) scan_pairs<H + 2, HB, DBG>(lane_addr, va, vb, rA, rB, dbg);
-}
-template <int HB, bool DBG>
-__device__ __forceinline__ void scan_buffer(uint32_t lane_addr, float (&rA)[8], float (&rB)[32], float* dbg) {
-    uint32_t va[16], vb[16];
-    tmem_ld16(lane_addr, va);
-    scan_pairs<0, HB, DBG>(lane_addr, va, vb, rA, rB, dbg);
+// software-pipelined walk over the 4 chunks (32 columns each) of one 128-column TMEM buffer: the load of chunk c+1 is in
+// flight while chunk c is reduced.  CB = index of the buffer's first chunk within the warpgroup's 256 virtual columns
+// (0 or 4), so the class-B minima land in fixed registers.
+template <int CB, bool DBG>
+__device__ __forceinline__ void scan_buffer(uint32_t lane_addr, float (&rA)[16], float (&rB)[16], float* dbg) {
+    uint32_t va[32], vb[32];
+    tmem_ld32(lane_addr, va);
+    tmem_ld_wait(va);
+    tmem_ld32(lane_addr + 32, vb);
+    scan_chunk<CB + 0, DBG>(va, rA, rB, dbg);
+    tmem_ld_wait(vb);
+    tmem_ld32(lane_addr + 64, va);
+    scan_chunk<CB + 1, DBG>(vb, rA, rB, dbg);
+    tmem_ld_wait(va);
+    tmem_ld32(lane_addr + 96, vb);
+    scan_chunk<CB + 2, DBG>(va, rA, rB, dbg);
+    tmem_ld_wait(vb);
+    scan_chunk<CB + 3, DBG>(vb, rA, rB, dbg);
 }
 
-// min over the entries != m1, the index of the entry == m1, and how many entries equal m1
-template <int N>
-__device__ __forceinline__ float min_excluding(const float (&r)[N], float m1, int& where, int& hits) {
-    float e[N];
-    where = 0;
-    hits = 0;
+// smallest and second-smallest (duplicates count) of 16 values: tournament on (lo, hi) pairs
+__device__ __forceinline__ void two_smallest16(const float (&r)[16], float& lo, float& hi) {
+    float l[8], h[8];
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-        const bool eq = (r[i] == m1);
-        e[i] = eq ? INFINITY : r[i];
-        where = eq ? i : where;
-        hits += eq ? 1 : 0;
+    for (int i = 0; i < 8; ++i) { l[i] = fminf(r[2 * i], r[2 * i + 1]); h[i] = fmaxf(r[2 * i], r[2 * i + 1]); }
+#pragma unroll
+    for (int n = 4; n >= 1; n >>= 1) {
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            const float nl = fminf(l[2 * i], l[2 * i + 1]);
+            const float nh = fmin3(fmaxf(l[2 * i], l[2 * i + 1]), h[2 * i], h[2 * i + 1]);
+            l[i] = nl; h[i] = nh;
+        }
     }
-    float m = min8(e);
+    lo = l[0]; hi = h[0];
+}
+// index (0..15) of the smallest of 16 values: the index rides in the 4 low mantissa bits through a min tree.  Values that
+// differ only in those bits may resolve to either index -- such rows have a runner-up gap of <= 16 ulp and are never
+// certified (the certificate needs more than cB (||x||^2 + ||e||^2) >> 16 ulp of any score).  Unused classes hold +inf,
+// which the tag turns into NaN: fminf ignores them.
+__device__ __forceinline__ int argmin16(const float (&r)[16]) {
+    float t[16];
 #pragma unroll
-    for (int g = 8; g < N; g += 8) m = fminf(m, min8(e + g));
-    return m;
+    for (int i = 0; i < 16; ++i) t[i] = __uint_as_float((__float_as_uint(r[i]) & 0xFFFFFFF0u) | (uint32_t)i);
+    return (int)(__float_as_uint(min16(t)) & 15u);
 }
 
 // after the warpgroup's (up to) 256 virtual columns went through scan_buffer: winning virtual column, its score m1
-// and the runner-up score m2 (m2 == m1 on exact ties and NaN scores -> never certified)
-__device__ __forceinline__ int scan_finish(const float (&rA)[8], const float (&rB)[32], float& m1, float& m2) {
-    m1 = min8(rA);
-    int a_star, b_star, hits_a, hits_b;
-    const float ea = min_excluding<8>(rA, m1, a_star, hits_a);
-    const float eb = min_excluding<32>(rB, m1, b_star, hits_b);
-    m2 = fminf(ea, eb);
-    if (hits_a != 1 || hits_b != 1) m2 = m1;
-    return 8 * b_star + a_star;
+// and the runner-up score m2 (m2 == m1 on exact ties; NaN / inf rows are never certified)
+__device__ __forceinline__ int scan_finish(const float (&rA)[16], const float (&rB)[16], float& m1, float& m2) {
+    float loA, hiA, loB, hiB;
+    two_smallest16(rA, loA, hiA);
+    two_smallest16(rB, loB, hiB);
+    m1 = fminf(loA, loB);
+    m2 = fminf(hiA, hiB);
+    return 16 * argmin16(rB) + argmin16(rA);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// MMA issue.  The issuer's own instruction stream is on the critical path (one thread, dependent uniform-datapath
+// instructions of ~10 cycles each), so all MMAs of one accumulator unit and the commit go out in ONE asm block,
+// executed by the converged warp with the tcgen05 instructions predicated on elect.sync (inside a divergent
+// `if (lane == 0)` the compiler wraps every UTCHMMA in an elect-and-retry loop), and the shared-memory descriptors are
+// assembled from 32-bit halves: lo = (address >> 4) | LBO, hi = constant per swizzle mode.
+//   unit = misc.misc (overwrite)  +  4 x xh.eh  [+ 4 x xl.eh + 4 x xh.el when NSPLIT == 3]   (K = 16 per MMA)
+// ---------------------------------------------------------------------------------------------------
+constexpr uint32_t DESC_HI_SW128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+constexpr uint32_t DESC_HI_SW32 = (256u >> 4) | (1u << 14) | (6u << 29);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+
+#define VQ_MMA_OP(CG) "@pe tcgen05.mma.cta_group::" CG ".kind::f16 [%0], da, db, %7, "
+#define VQ_MMA_KS(CG, A, B, KS)                                                              \
+    "add.u32 ta, " A ", " KS ";\n\tadd.u32 tb, " B ", " KS ";\n\t"                            \
+    "mov.b64 da, {ta, %6};\n\tmov.b64 db, {tb, %6};\n\t" VQ_MMA_OP(CG) "pt;\n\t"
+#define VQ_MMA_BLOCK4(CG, A, B) VQ_MMA_KS(CG, A, B, "0") VQ_MMA_KS(CG, A, B, "2") VQ_MMA_KS(CG, A, B, "4") VQ_MMA_KS(CG, A, B, "6")
+#define VQ_MMA_HEAD(CG)                                                                      \
+    "{\n\t.reg .pred pf, pt, pe;\n\t.reg .b64 da, db;\n\t.reg .b32 ta, tb;\n\t"               \
+    "elect.sync _|pe, 0xffffffff;\n\t"                                                       \
+    "setp.ne.b32 pf, %7, %7;\n\tsetp.eq.b32 pt, %7, %7;\n\t"                                  \
+    "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t" VQ_MMA_OP(CG) "pf;\n\t"
+#define VQ_COMMIT1 "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t}"
+#define VQ_COMMIT2 "@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%8], %11;\n\t}"
+
+template <bool CTA2>
+__device__ __forceinline__ void commit_elected(uint32_t bar) {
+    if constexpr (CTA2)
+        asm volatile("{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
+                     "@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+                     :: "r"(bar), "h"((uint16_t)3) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
+                     "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+                     :: "r"(bar) : "memory");
+}
+
+template <int NSPLIT, bool CTA2>
+__device__ __forceinline__ void issue_unit(uint32_t d_tmem, uint32_t am_lo, uint32_t bm_lo, uint32_t a_lo, uint32_t b_lo,
+                                           uint32_t al_lo, uint32_t bl_lo, uint32_t bar_tf) {
+    const uint32_t idesc = CTA2 ? IDESC2 : IDESC;
+    if constexpr (NSPLIT == 3 && CTA2) {
+        asm volatile(VQ_MMA_HEAD("2") VQ_MMA_BLOCK4("2", "%3", "%4") VQ_MMA_BLOCK4("2", "%9", "%4") VQ_MMA_BLOCK4("2", "%3", "%10") VQ_COMMIT2
+                     :: "r"(d_tmem), "r"(am_lo), "r"(bm_lo), "r"(a_lo), "r"(b_lo), "r"(DESC_HI_SW32), "r"(DESC_HI_SW128), "r"(idesc),
+                        "r"(bar_tf), "r"(al_lo), "r"(bl_lo), "h"((uint16_t)3) : "memory");
+    } else if constexpr (NSPLIT == 3) {
+        asm volatile(VQ_MMA_HEAD("1") VQ_MMA_BLOCK4("1", "%3", "%4") VQ_MMA_BLOCK4("1", "%9", "%4") VQ_MMA_BLOCK4("1", "%3", "%10") VQ_COMMIT1
+                     :: "r"(d_tmem), "r"(am_lo), "r"(bm_lo), "r"(a_lo), "r"(b_lo), "r"(DESC_HI_SW32), "r"(DESC_HI_SW128), "r"(idesc),
+                        "r"(bar_tf), "r"(al_lo), "r"(bl_lo) : "memory");
+    } else if constexpr (CTA2) {
+        asm volatile(VQ_MMA_HEAD("2") VQ_MMA_BLOCK4("2", "%3", "%4") VQ_COMMIT2
+                     :: "r"(d_tmem), "r"(am_lo), "r"(bm_lo), "r"(a_lo), "r"(b_lo), "r"(DESC_HI_SW32), "r"(DESC_HI_SW128), "r"(idesc),
+                        "r"(bar_tf), "r"(al_lo), "r"(bl_lo), "h"((uint16_t)3) : "memory");
+    } else {
+        asm volatile(VQ_MMA_HEAD("1") VQ_MMA_BLOCK4("1", "%3", "%4") VQ_COMMIT1
+                     :: "r"(d_tmem), "r"(am_lo), "r"(bm_lo), "r"(a_lo), "r"(b_lo), "r"(DESC_HI_SW32), "r"(DESC_HI_SW128), "r"(idesc),
+                        "r"(bar_tf) : "memory");
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -515,7 +582,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
             if (DBG && prof) flush(PF_PROD_WAIT_XE, 0);
         }
     } else if (warp == W_MMA) {
-        // ================= MMA issuer ==================================================================
+        // ================= MMA issuer (converged warp, tcgen05 instructions predicated on one elected lane) ===========
         reg_dec<24>();
         mbar_wait(bar(BAR_B), 0);
         if (CTA2) {
@@ -523,46 +590,35 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
             else mbar_wait_cluster(bar(BAR_PB), 0);
         }
         const long long t_role0 = clock64();
-        uint32_t uc = 0;
+        const bool mrec = lane == 0;
+        constexpr uint32_t UROWS = UNIT_N / P::BDIV;
+        constexpr uint32_t B_STEP = (UROWS * 128u) >> 4, BM_STEP = (UROWS * 32u) >> 4;   // per unit, in descriptor units
+        const uint32_t b_lo0 = desc_lo(sB), bl_lo0 = desc_lo(sB + P::off_b_lo(K)), bm_lo0 = desc_lo(sB + P::off_b_misc(K));
         for (uint32_t it = 0; it < (crank == 0 ? n_iter : 0u); ++it) {     // the leader issues for the pair
             const uint32_t sa = it % AS, pha = (it / AS) & 1u;
-            if (CTA2) mbar_wait_cluster(bar(BAR_AF + sa), pha); else wait_t(BAR_AF + sa, pha, 0, lane == 0);
+            if (CTA2) mbar_wait_cluster(bar(BAR_AF + sa), pha); else wait_t(BAR_AF + sa, pha, 0, mrec);
             tc_fence_after();
             const uint32_t a0 = sA + sa * P::A_STAGE;
-            for (int u = 0; u < U; ++u, ++uc) {
+            const uint32_t a_lo = desc_lo(a0), al_lo = desc_lo(a0 + 16384u), am_lo = desc_lo(a0 + (P::A_STAGE - 4096u));
+            for (int u = 0; u < U; ++u) {
+                const uint32_t uc = it * (uint32_t)U + (uint32_t)u;
                 const uint32_t buf = uc % NBUF, pht = (uc / NBUF) & 1u;
-                if (CTA2) mbar_wait_cluster(bar(BAR_TE + buf), pht ^ 1u); else wait_t(BAR_TE + buf, pht ^ 1u, 1, lane == 0);
+                if (CTA2) mbar_wait_cluster(bar(BAR_TE + buf), pht ^ 1u); else wait_t(BAR_TE + buf, pht ^ 1u, 1, mrec);
                 tc_fence_after();
-                auto mma = [&](uint64_t ad, uint64_t bd, uint32_t acc) {
-                    if (CTA2) umma_bf16_2cta(tmem_base + buf * UNIT_N, ad, bd, IDESC2, acc);
-                    else umma_bf16(tmem_base + buf * UNIT_N, ad, bd, IDESC, acc);
-                };
-                if (lane == 0 && !(DBG && (p.dbg_skip & 8))) {
-                    constexpr uint32_t UROWS = UNIT_N / P::BDIV;
-                    const uint32_t b_hi = sB + (uint32_t)u * UROWS * 128u;
-                    const uint32_t b_lo = sB + P::off_b_lo(K) + (uint32_t)u * UROWS * 128u;
-                    const uint32_t b_mi = sB + P::off_b_misc(K) + (uint32_t)u * UROWS * 32u;
-                    // misc block first (bias, offset, error bound), then the split products
-                    mma(desc_sw32(a0 + (P::A_STAGE - 4096u)), desc_sw32(b_mi), 0u);
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)      // xh . eh
-                        mma(desc_sw128(a0) + 2u * ks, desc_sw128(b_hi) + 2u * ks, 1u);
-                    if (NSPLIT == 3) {
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks)  // xl . eh
-                            mma(desc_sw128(a0 + 16384u) + 2u * ks, desc_sw128(b_hi) + 2u * ks, 1u);
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks)  // xh . el
-                            mma(desc_sw128(a0) + 2u * ks, desc_sw128(b_lo) + 2u * ks, 1u);
-                    }
+                if (DBG && (p.dbg_skip & 8)) {
+                    if (lane == 0) { if (CTA2) umma_commit_2cta(bar(BAR_TF + buf)); else umma_commit(bar(BAR_TF + buf)); }
+                    __syncwarp();
+                } else {
+                    // misc block first (bias, offset, error bound: overwrites the accumulator), then the products
+                    issue_unit<NSPLIT, CTA2>(tmem_base + buf * UNIT_N, am_lo, bm_lo0 + (uint32_t)u * BM_STEP, a_lo,
+                                             b_lo0 + (uint32_t)u * B_STEP, al_lo, bl_lo0 + (uint32_t)u * B_STEP, bar(BAR_TF + buf));
                 }
-                if (lane == 0) { if (CTA2) umma_commit_2cta(bar(BAR_TF + buf)); else umma_commit(bar(BAR_TF + buf)); }
-                __syncwarp();
             }
-            if (lane == 0) { if (CTA2) umma_commit_2cta(bar(BAR_AE + sa)); else umma_commit(bar(BAR_AE + sa)); }
-            __syncwarp();
+            // the elected lane of issue_unit and lane 0 may differ: tcgen05.commit tracks the MMAs of the executing
+            // thread, so the stage release is committed by an elected lane as well
+            commit_elected<CTA2>(bar(BAR_AE + sa));
         }
-        if (DBG && prof && lane == 0) { flush(PF_MMA_WAIT_AF, 0); flush(PF_MMA_WAIT_TE, 1); prof[PF_MMA_TOTAL] = (unsigned long long)(clock64() - t_role0); }
+        if (DBG && prof && mrec) { flush(PF_MMA_WAIT_AF, 0); flush(PF_MMA_WAIT_TE, 1); prof[PF_MMA_TOTAL] = (unsigned long long)(clock64() - t_role0); }
     } else if (warp > W_MMA) {
         reg_dec<24>();                           // spare warps of the producer/MMA warpgroup
     } else if (warp >= W_CONV) {
@@ -658,11 +714,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
         for (uint32_t it = 0; it < n_iter; ++it) {
             const int64_t t = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
             const int64_t grow = t * TILE_M + row_in_tile;
-            float rA[8], rB[32];
+            float rA[16], rB[16];
 #pragma unroll
-            for (int a = 0; a < 8; ++a) rA[a] = INFINITY;
-#pragma unroll
-            for (int b = 0; b < 32; ++b) rB[b] = INFINITY;
+            for (int a = 0; a < 16; ++a) { rA[a] = INFINITY; rB[a] = INFINITY; }
             float* dbg = (DBG && p.dbg_scores && grow < p.n_rows) ? p.dbg_scores + grow * K : nullptr;
             const long long t_scan0 = clock64();
             {   // first unit of the group
@@ -678,7 +732,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
                 const uint32_t uc = it * 4u + (uint32_t)g + 2u, buf = uc % NBUF, pht = (uc / NBUF) & 1u;
                 wait_t(BAR_TF + buf, pht, 0, rec);
                 tc_fence_after();
-                if (!(DBG && (p.dbg_skip & 4))) scan_buffer<8, DBG>(lane_base + buf * UNIT_N, rA, rB, dbg ? dbg + (g + 2) * UNIT_N - 8 * 16 : nullptr);
+                if (!(DBG && (p.dbg_skip & 4))) scan_buffer<4, DBG>(lane_base + buf * UNIT_N, rA, rB, dbg ? dbg + (g + 2) * UNIT_N - 4 * 32 : nullptr);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) arrive_mma_side(BAR_TE + buf);
