@@ -62,7 +62,9 @@ size_t vqb200_codebook_bytes(int32_t dim, int32_t n_embed);
  * exact re-score.                                                                                   */
 size_t vqb200_forward_scratch_bytes(int64_t n_rows, int32_t dim, int32_t n_embed);
 /* packed codebook statistics: n_embed*dim per-code sums (code-major), then n_embed counts, then 4
- * spare floats the EMA kernels use as scalars; only the first n_embed*(dim+1) floats are all-reduced */
+ * spare words the EMA kernel uses as scalars; only the first n_embed*(dim+1) floats are all-reduced.
+ * The spare words must be zero when vqb200_ema_update starts: vqb200_quantize_forward leaves them zero
+ * and so does vqb200_ema_update.                                                                    */
 size_t vqb200_stats_bytes(int32_t dim, int32_t n_embed);
 
 /* ---- codebook ---------------------------------------------------------------------------------- */

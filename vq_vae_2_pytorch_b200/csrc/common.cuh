@@ -61,6 +61,7 @@ __host__ __device__ inline CodebookImage codebook_view(void* base, int dim, int 
 struct ForwardScratch {
     double* diff_acc;      // 1 double: sum (q-x)^2
     int* flagged_count;    // 1 int: rows sent to the exact re-score
+    unsigned int* ticket;  // 1 word: last-block-done ticket of the fix-up / gather kernels (kept zero between launches)
     int* flagged_rows;     // [n_rows] row ids
     float* stat_partials;  // [STAT_PARTS][K*(D+1)] per-CTA statistics tables
 };
@@ -73,6 +74,7 @@ __host__ __device__ inline ForwardScratch scratch_view(void* base, int64_t n_row
     ForwardScratch s;
     s.diff_acc = (double*)p;
     s.flagged_count = (int*)(p + 16);
+    s.ticket = (unsigned int*)(p + 32);
     s.flagged_rows = (int*)(p + 256);
     s.stat_partials = (float*)(p + 256 + align_up((size_t)n_rows * 4, 256));
     return s;

@@ -1,0 +1,159 @@
+// Small-kernel fusions for the shapes the tcgen05 engine covers (D = 64): at the headline shape the step is ~100 us, so
+// every extra launch (~2.5 us each) shows.  One launch each for: the codebook image, the flagged-row fix-up with the
+// loss finalisation, and the EMA update with the next image.
+#pragma once
+#include "common.cuh"
+#include "simt_kernels.cuh"
+#include "tc_kernel.cuh"
+
+namespace vqb200 {
+
+constexpr int PREP_CODES = 8;      // codes per block of the image / EMA kernels (one warp per code)
+
+// ------------------------------------------------------------------------------------------------
+// codebook image in one launch: embed [64, K] -> cbT [K, 64], ||e_k||^2 (same summation order as
+// k_codebook_norms) and the tensor-core operand image.  grid = K / 8, block = 256.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_prepare64(const float* __restrict__ embed, float* __restrict__ cbT,
+                                                    float* __restrict__ ee, unsigned char* __restrict__ img, int K,
+                                                    float cA, float cA1, float cB) {
+    __shared__ float es[PREP_CODES][65];
+    __shared__ float e2s[PREP_CODES];
+    const int k0 = blockIdx.x * PREP_CODES, tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < 64 * PREP_CODES; i += 256) {          // 32-byte segments of 8 consecutive codes per dim
+        const int d = i >> 3, j = i & 7;
+        es[j][d] = embed[(size_t)d * K + k0 + j];
+    }
+    __syncthreads();
+    const float v0 = es[w][lane], v1 = es[w][lane + 32];
+    cbT[(size_t)(k0 + w) * 64 + lane] = v0;
+    cbT[(size_t)(k0 + w) * 64 + lane + 32] = v1;
+    float s = fmaf(v0, v0, 0.f);
+    s = fmaf(v1, v1, s);
+    s = warp_sum(s);
+    if (lane == 0) { ee[k0 + w] = s; e2s[w] = s; }
+    __syncthreads();
+    if (tid < 8 * PREP_CODES) tc::tc_image_rows(&es[tid >> 3][0], e2s[tid >> 3], img, K, k0 + (tid >> 3), tid & 7, cA, cA1, cB);
+}
+
+// ------------------------------------------------------------------------------------------------
+// EMA update + Laplace-smoothed renormalisation (vqvae.py:61-70) + next codebook image in one launch.
+// grid = K / 8, block = 256.  Every block derives n = sum_k cluster_size_new[k] from the OLD cluster sizes,
+// which nobody overwrites until the last block to finish (ticket) stores the new ones.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_ema64(const float* __restrict__ stats, float* __restrict__ cluster_size,
+                                                float* __restrict__ embed_avg, float* __restrict__ embed,
+                                                float* __restrict__ cbT, float* __restrict__ ee,
+                                                unsigned char* __restrict__ img, int K, float decay,
+                                                float one_minus_decay, float eps, float cA, float cA1, float cB,
+                                                unsigned int* __restrict__ ticket) {
+    __shared__ float es[PREP_CODES][65];
+    __shared__ float e2s[PREP_CODES];
+    __shared__ float part[8];
+    __shared__ float n_s;
+    __shared__ unsigned int last_s;
+    const float* sums = stats;
+    const float* counts = stats + (size_t)K * 64;
+    const int k0 = blockIdx.x * PREP_CODES, tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    float s = 0.f;
+    for (int k = tid; k < K; k += 256) {
+        float c = cluster_size[k] * decay;
+        c = c + counts[k] * one_minus_decay;                    // vqvae.py:61-63
+        s += c;
+    }
+    s = warp_sum(s);
+    if (lane == 0) part[w] = s;
+    __syncthreads();
+    if (tid == 0) {
+        float n = 0.f;
+        for (int i = 0; i < 8; ++i) n += part[i];
+        n_s = n;                                                // vqvae.py:65
+    }
+    __syncthreads();
+    const float n = n_s;
+    const float denom = n + (float)((double)K * (double)eps);
+    for (int i = tid; i < 64 * PREP_CODES; i += 256) {
+        const int d = i >> 3, j = i & 7, k = k0 + j;
+        float c = cluster_size[k] * decay;
+        c = c + counts[k] * one_minus_decay;
+        const float cs = (c + eps) / denom * n;                 // vqvae.py:66-68
+        const size_t o = (size_t)d * K + k;
+        float a = embed_avg[o] * decay;
+        a = a + sums[(size_t)k * 64 + d] * one_minus_decay;     // vqvae.py:64
+        embed_avg[o] = a;
+        const float e = a / cs;                                 // vqvae.py:69-70
+        embed[o] = e;
+        es[j][d] = e;
+    }
+    __syncthreads();
+    const float v0 = es[w][lane], v1 = es[w][lane + 32];
+    if (cbT) {
+        cbT[(size_t)(k0 + w) * 64 + lane] = v0;
+        cbT[(size_t)(k0 + w) * 64 + lane + 32] = v1;
+    }
+    float s2 = fmaf(v0, v0, 0.f);
+    s2 = fmaf(v1, v1, s2);
+    s2 = warp_sum(s2);
+    if (lane == 0) { if (ee) ee[k0 + w] = s2; e2s[w] = s2; }
+    __syncthreads();
+    if (img && tid < 8 * PREP_CODES)
+        tc::tc_image_rows(&es[tid >> 3][0], e2s[tid >> 3], img, K, k0 + (tid >> 3), tid & 7, cA, cA1, cB);
+    // ---- deferred cluster_size store: only after every block has read the old values
+    __threadfence();
+    if (tid == 0) last_s = (atomicAdd(ticket, 1u) == gridDim.x - 1u) ? 1u : 0u;
+    __syncthreads();
+    if (last_s) {
+        for (int k = tid; k < K; k += 256) {
+            float c = cluster_size[k] * decay;
+            c = c + counts[k] * one_minus_decay;
+            cluster_size[k] = c;
+        }
+        if (tid == 0) *ticket = 0u;                             // clean for the next launch
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// flagged-row fix-up of the tcgen05 engine in one launch: exact fp32 re-score (assign_chunk), then gather /
+// straight-through value / loss / statistics (gather_chunk) of the same rows by the same block, then -- by the last
+// block to finish -- the loss finalisation diff = acc * inv_count.  Exits after the ticket when no row was flagged.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(AS_THREADS)
+k_fixup(const float* __restrict__ x, RowLayout L, int D, int K, const float* __restrict__ cbT,
+        const float* __restrict__ ee, int64_t* __restrict__ embed_ind, float* __restrict__ quantize,
+        double* __restrict__ diff_acc, float* __restrict__ stat_sums, float* __restrict__ stat_counts,
+        const int* __restrict__ row_list, const int* __restrict__ row_count, int want_gather,
+        float* __restrict__ diff, double inv_count, unsigned int* __restrict__ ticket) {
+    extern __shared__ float gs_tile[];
+    __shared__ float warp_part[AS_THREADS / 32];
+    __shared__ unsigned int last_s;
+    const int64_t total = (int64_t)(*row_count);
+    float acc = 0.f;
+    for (int64_t n0 = (int64_t)blockIdx.x * AS_BM; n0 < total; n0 += (int64_t)gridDim.x * AS_BM) {
+        assign_chunk(x, L, D, K, cbT, ee, embed_ind, row_list, total, n0);
+        if (want_gather) {
+            __syncthreads();                                    // the chunk's indices are written (same block reads them)
+            for (int64_t g0 = n0; g0 < min(total, n0 + AS_BM); g0 += GS_BM)
+                gather_chunk(x, L, D, cbT, embed_ind, quantize, stat_sums, stat_counts, row_list, total, g0, gs_tile, acc);
+        }
+    }
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (want_gather && diff_acc) {
+        acc = warp_sum(acc);
+        if (lane == 0) warp_part[warp] = acc;
+        __syncthreads();
+        if (tid == 0) {
+            float s = 0.f;
+            for (int w = 0; w < AS_THREADS / 32; ++w) s += warp_part[w];
+            if (s != 0.f) atomicAdd(diff_acc, (double)s);
+        }
+    }
+    __threadfence();
+    if (tid == 0) last_s = (atomicAdd(ticket, 1u) == gridDim.x - 1u) ? 1u : 0u;
+    __syncthreads();
+    if (last_s && tid == 0) {
+        *ticket = 0u;
+        if (diff) diff[0] = (float)(*reinterpret_cast<volatile double*>(diff_acc) * inv_count);
+    }
+}
+
+}  // namespace vqb200

@@ -42,21 +42,18 @@ __global__ void k_codebook_norms(const float* __restrict__ cbT, float* __restric
 // ------------------------------------------------------------------------------------------------
 constexpr int AS_BM = 64, AS_BN = 64, AS_DC = 32, AS_THREADS = 256;
 
-// rows come either from [0, n_rows) or, when row_list != nullptr, from row_list[0 .. *row_count)
-__global__ void __launch_bounds__(AS_THREADS)
-k_assign_exact(const float* __restrict__ x, RowLayout L, int D, int K,
-               const float* __restrict__ cbT, const float* __restrict__ ee,
-               int64_t* __restrict__ embed_ind,
-               const int* __restrict__ row_list, const int* __restrict__ row_count) {
-    __shared__ float xs[AS_DC][AS_BM + 4];
-    __shared__ float es[AS_DC][AS_BN + 4];
+// one chunk of AS_BM rows starting at position n0; rows come either from [0, total) or, when row_list != nullptr,
+// from row_list[0 .. total)
+__device__ __forceinline__ void assign_chunk(const float* __restrict__ x, const RowLayout& L, int D, int K,
+                                             const float* __restrict__ cbT, const float* __restrict__ ee,
+                                             int64_t* __restrict__ embed_ind, const int* __restrict__ row_list,
+                                             int64_t total, int64_t n0) {
+    __shared__ __align__(16) float xs[AS_DC][AS_BM + 4];
+    __shared__ __align__(16) float es[AS_DC][AS_BN + 4];
     __shared__ int64_t row_off[AS_BM];
     __shared__ int row_id[AS_BM];
-
-    const int64_t total = row_list ? (int64_t)(*row_count) : L.n_rows;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  for (int64_t n0 = (int64_t)blockIdx.x * AS_BM; n0 < total; n0 += (int64_t)gridDim.x * AS_BM) {
-    __syncthreads();                              // previous tile's row_id / row_off readers are done
+    __syncthreads();                              // previous chunk's row_id / row_off readers are done
     if (tid < AS_BM) {
         int64_t i = n0 + tid;
         int64_t n = -1;
@@ -137,7 +134,16 @@ k_assign_exact(const float* __restrict__ x, RowLayout L, int D, int K,
         int r = ty * 4 + i;
         if (tx == 0 && row_id[r] >= 0) embed_ind[row_id[r]] = (int64_t)bk;
     }
-  }
+}
+
+__global__ void __launch_bounds__(AS_THREADS)
+k_assign_exact(const float* __restrict__ x, RowLayout L, int D, int K,
+               const float* __restrict__ cbT, const float* __restrict__ ee,
+               int64_t* __restrict__ embed_ind,
+               const int* __restrict__ row_list, const int* __restrict__ row_count) {
+    const int64_t total = row_list ? (int64_t)(*row_count) : L.n_rows;
+    for (int64_t n0 = (int64_t)blockIdx.x * AS_BM; n0 < total; n0 += (int64_t)gridDim.x * AS_BM)
+        assign_chunk(x, L, D, K, cbT, ee, embed_ind, row_list, total, n0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -146,23 +152,18 @@ k_assign_exact(const float* __restrict__ x, RowLayout L, int D, int K,
 // ------------------------------------------------------------------------------------------------
 constexpr int GS_BM = 32, GS_THREADS = 256;
 
-__global__ void __launch_bounds__(GS_THREADS)
-k_gather_stats(const float* __restrict__ x, RowLayout L, int D, int K,
-               const float* __restrict__ cbT, const int64_t* __restrict__ embed_ind,
-               float* __restrict__ quantize, double* __restrict__ diff_acc,
-               float* __restrict__ stat_sums, float* __restrict__ stat_counts,
-               const int* __restrict__ row_list, const int* __restrict__ row_count) {
-    extern __shared__ float tile[];              // [GS_BM][D + 1]
+// one chunk of GS_BM rows starting at position n0 (tile = dynamic shared memory, GS_BM x (D+1) floats)
+__device__ __forceinline__ void gather_chunk(const float* __restrict__ x, const RowLayout& L, int D,
+                                             const float* __restrict__ cbT, const int64_t* __restrict__ embed_ind,
+                                             float* __restrict__ quantize, float* __restrict__ stat_sums,
+                                             float* __restrict__ stat_counts, const int* __restrict__ row_list,
+                                             int64_t total, int64_t n0, float* tile, float& acc) {
     __shared__ int64_t row_off[GS_BM];
     __shared__ int code[GS_BM];
-    __shared__ float warp_part[GS_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ld = D + 1;
-    const int64_t total = row_list ? (int64_t)(*row_count) : L.n_rows;
-    float acc = 0.f;
-  for (int64_t n0 = (int64_t)blockIdx.x * GS_BM; n0 < total; n0 += (int64_t)gridDim.x * GS_BM) {
     const int rows = (int)min((int64_t)GS_BM, total - n0);
-    __syncthreads();                              // previous tile fully written out
+    __syncthreads();                              // previous chunk fully written out
     if (tid < GS_BM) {
         bool ok = tid < rows;
         int64_t n = ok ? (row_list ? (int64_t)row_list[n0 + tid] : n0 + tid) : 0;
@@ -197,7 +198,25 @@ k_gather_stats(const float* __restrict__ x, RowLayout L, int D, int K,
             if (r < rows) quantize[row_off[r] + (int64_t)d * L.col_stride] = tile[r * ld + d];
         }
     }
-  }
+}
+
+// diff (may be null) is finalised by the last block to finish: diff = diff_acc * inv_count  (vqvae.py:72 mean)
+__global__ void __launch_bounds__(GS_THREADS)
+k_gather_stats(const float* __restrict__ x, RowLayout L, int D, int K,
+               const float* __restrict__ cbT, const int64_t* __restrict__ embed_ind,
+               float* __restrict__ quantize, double* __restrict__ diff_acc,
+               float* __restrict__ stat_sums, float* __restrict__ stat_counts,
+               const int* __restrict__ row_list, const int* __restrict__ row_count,
+               float* __restrict__ diff, double inv_count, unsigned int* __restrict__ ticket) {
+    extern __shared__ float tile[];              // [GS_BM][D + 1]
+    __shared__ float warp_part[GS_THREADS / 32];
+    __shared__ unsigned int last_s;
+    (void)K;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t total = row_list ? (int64_t)(*row_count) : L.n_rows;
+    float acc = 0.f;
+    for (int64_t n0 = (int64_t)blockIdx.x * GS_BM; n0 < total; n0 += (int64_t)gridDim.x * GS_BM)
+        gather_chunk(x, L, D, cbT, embed_ind, quantize, stat_sums, stat_counts, row_list, total, n0, tile, acc);
     acc = warp_sum(acc);
     if (lane == 0) warp_part[warp] = acc;
     __syncthreads();
@@ -205,6 +224,15 @@ k_gather_stats(const float* __restrict__ x, RowLayout L, int D, int K,
         float s = 0.f;
         for (int w = 0; w < GS_THREADS / 32; ++w) s += warp_part[w];
         atomicAdd(diff_acc, (double)s);
+    }
+    if (ticket) {
+        __threadfence();
+        if (tid == 0) last_s = (atomicAdd(ticket, 1u) == gridDim.x - 1u) ? 1u : 0u;
+        __syncthreads();
+        if (last_s && tid == 0) {
+            *ticket = 0u;
+            if (diff && diff_acc) diff[0] = (float)(*reinterpret_cast<volatile double*>(diff_acc) * inv_count);
+        }
     }
 }
 
@@ -329,10 +357,12 @@ k_code_stats(const float* __restrict__ x, RowLayout L, int D, int K, const int64
     for (int i = tid; i < K; i += CS_THREADS) out[(size_t)K * D + i] = (float)cnt_total[i];
 }
 
-// stats[i] += sum over CTAs of partials[c][i].  block = (32, 4): 128 consecutive elements per block, four 32-wide
+// stats[i] (+)= sum over CTAs of partials[c][i].  block = (32, 4): 128 consecutive elements per block, four 32-wide
 // column groups; thread-row y sums the tables c = y, y+4, ... (8 independent loads in flight), the four partial
-// sums are folded in a fixed order -> deterministic for a fixed grid.
-__global__ void k_stats_fold(const float* __restrict__ partials, int n_parts, int n, float* __restrict__ stats) {
+// sums are folded in a fixed order -> deterministic for a fixed grid.  accumulate == 0 overwrites stats (no memset
+// needed before); the spare words behind the n elements (EMA ticket) are cleared either way.
+__global__ void k_stats_fold(const float* __restrict__ partials, int n_parts, int n, float* __restrict__ stats,
+                             int accumulate) {
     __shared__ float part[4][4][32];
     const int col = threadIdx.x, y = threadIdx.y;
     const int i0 = blockIdx.x * 128;
@@ -353,7 +383,11 @@ __global__ void k_stats_fold(const float* __restrict__ partials, int n_parts, in
     for (int u = 0; u < 4; ++u) part[y][u][col] = s[u];
     __syncthreads();
     const int u = y, i = i0 + u * 32 + col;
-    if (i < n) stats[i] += (part[0][u][col] + part[1][u][col]) + (part[2][u][col] + part[3][u][col]);
+    if (i < n) {
+        const float t = (part[0][u][col] + part[1][u][col]) + (part[2][u][col] + part[3][u][col]);
+        stats[i] = accumulate ? stats[i] + t : t;
+    }
+    if (blockIdx.x == 0 && y == 0 && col < 4) stats[n + col] = 0.f;
 }
 
 __host__ __device__ inline size_t code_stats_smem_bytes(int D, int K) {

@@ -214,13 +214,10 @@ __host__ __device__ inline size_t image_off_enorm(int K) { return (size_t)K * 28
 __host__ __device__ inline size_t image_off_misc1(int K) { return (size_t)K * 292; }     // misc block carrying the plain-bf16 bound
 __host__ __device__ inline size_t image_bytes(int K) { return (size_t)K * 292 + (size_t)K * 32; }
 
-// one thread per (code, 8-dim chunk); requires D == 64
-__global__ void k_tc_image(const float* __restrict__ cbT, const float* __restrict__ ee, unsigned char* __restrict__ img,
-                           int K, float cA, float cA1, float cB) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    int k = t >> 3, c = t & 7;
-    if (k >= K) return;
-    const float* e = cbT + (size_t)k * TC_D + c * 8;
+// operand-image rows of code k, 8-dim chunk c (0..7): e = the code's 64 fp32 components, e2 = ||e_k||^2; requires D == 64
+__device__ __forceinline__ void tc_image_rows(const float* e_row, float e2, unsigned char* __restrict__ img, int K, int k, int c,
+                                              float cA, float cA1, float cB) {
+    const float* e = e_row + c * 8;
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -234,7 +231,6 @@ __global__ void k_tc_image(const float* __restrict__ cbT, const float* __restric
     *reinterpret_cast<uint4*>(img + image_off_lo(K) + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     if (c == 0) {
         float b1, b2, b3;
-        float e2 = ee[k];
         split3(e2, b1, b2, b3);
         float ne = sqrtf(e2);
         float t6 = -bf16_round(cA * ne * 1.0078125f);           // rounded up in magnitude
@@ -901,14 +897,6 @@ inline bool tc_supported(const RowLayout& L, const float* x, int dim, int n_embe
     if (L.col_stride != 1 || L.row_stride != dim) return false;                 // contiguous rows only (for now)
     if (L.n_rows > L.rows_per_image && L.image_stride != L.rows_per_image * dim) return false;
     return (reinterpret_cast<uintptr_t>(x) & 15u) == 0;                          // bulk copies need 16-byte alignment
-}
-
-// builds the tensor-core operand image next to cbT / ee (no-op for shapes the kernel does not cover)
-inline int tc_prepare_codebook(const CodebookImage& cb, int dim, int n_embed, cudaStream_t st) {
-    if (!tc_shape_ok(dim, n_embed)) return 0;
-    int threads = n_embed * 8;
-    tc::k_tc_image<<<(threads + 255) / 256, 256, 0, st>>>(cb.cbT, cb.ee, cb.tc, n_embed, tc::bound_cA(3), tc::bound_cA(1), tc::BOUND_CB);
-    return cudaGetLastError() != cudaSuccess;
 }
 
 // CTAs the tensor-core kernel runs for n_rows rows (= number of private statistics tables it fills)

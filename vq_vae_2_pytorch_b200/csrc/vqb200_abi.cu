@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "simt_kernels.cuh"
 #include "tc_kernel.cuh"
+#include "fused_kernels.cuh"
 
 using namespace vqb200;
 
@@ -48,6 +49,12 @@ bool layout_ok(int64_t n_rows, int32_t dim, int64_t rpi, int64_t img_stride, int
 
 int prepare_codebook(const float* d_embed, int dim, int n_embed, void* d_codebook, cudaStream_t st) {
     CodebookImage cb = codebook_view(d_codebook, dim, n_embed);
+    if (tc_shape_ok(dim, n_embed)) {              // one launch: transpose + norms + tensor-core operand image
+        k_prepare64<<<n_embed / PREP_CODES, 256, 0, st>>>(d_embed, cb.cbT, cb.ee, cb.tc, n_embed, tc::bound_cA(3),
+                                                           tc::bound_cA(1), tc::BOUND_CB);
+        VQ_LAUNCH_CHECK();
+        return VQB200_OK;
+    }
     dim3 grid((n_embed + 31) / 32, (dim + 31) / 32), block(32, 8);
     k_codebook_transpose<<<grid, block, 0, st>>>(d_embed, cb.cbT, dim, n_embed);
     VQ_LAUNCH_CHECK();
@@ -55,7 +62,7 @@ int prepare_codebook(const float* d_embed, int dim, int n_embed, void* d_codeboo
     k_codebook_norms<<<(n_embed + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(
         cb.cbT, cb.ee, dim, n_embed);
     VQ_LAUNCH_CHECK();
-    return tc_prepare_codebook(cb, dim, n_embed, st) ? cuda_fail(cudaGetLastError()) : VQB200_OK;
+    return VQB200_OK;
 }
 
 // The forward, split so the host-buffer path can stream row chunks through it:
@@ -70,43 +77,48 @@ int forward_impl(const float* d_x, const RowLayout& L, int dim, int n_embed, con
     ForwardScratch sc = scratch_view(d_scratch, scratch_rows);
     float* sums = d_stats;
     float* counts = d_stats ? d_stats + (size_t)n_embed * dim : nullptr;
+    const double inv = total_rows > 0 ? 1.0 / ((double)total_rows * (double)dim)
+                                      : std::numeric_limits<double>::quiet_NaN();   // mean over zero elements is NaN in the reference
+    float* fin_diff = (finalize && d_diff) ? d_diff : nullptr;
+    bool finalized = false;
+    bool use_tc = false;
+    if (L.n_rows > 0 && (engine == VQB200_ENGINE_TCGEN05 || engine == VQB200_ENGINE_TCGEN05_BF16 || engine == VQB200_ENGINE_AUTO))
+        use_tc = tc_supported(L, d_x, dim, n_embed);
+    if (L.n_rows > 0 && (engine == VQB200_ENGINE_TCGEN05 || engine == VQB200_ENGINE_TCGEN05_BF16) && !use_tc)
+        return VQB200_EUNSUPPORTED;
+    // statistics: private-table segmented reduction when [K][D] fp32 fits in shared memory (its fold kernel writes
+    // d_stats, no memset needed), else the gather kernels fall back to global atomics on a cleared d_stats
+    const size_t cs_smem = code_stats_smem_bytes(dim, n_embed);
+    const bool stats_kernel = d_stats && cs_smem <= 200 * 1024 && n_embed <= 65535;
     if (zero_first) {
-        VQ_CUDA(cudaMemsetAsync(sc.diff_acc, 0, 256, st));
-        if (d_stats) VQ_CUDA(cudaMemsetAsync(d_stats, 0, vqb200_stats_bytes(dim, n_embed), st));
+        VQ_CUDA(cudaMemsetAsync(sc.diff_acc, 0, 256, st));      // loss accumulator, flagged-row counter, ticket
+        if (d_stats && (!stats_kernel || L.n_rows == 0)) VQ_CUDA(cudaMemsetAsync(d_stats, 0, vqb200_stats_bytes(dim, n_embed), st));
+    } else if (use_tc) {
+        VQ_CUDA(cudaMemsetAsync(sc.flagged_count, 0, sizeof(int), st));
     }
     if (L.n_rows > 0) {
-        bool use_tc = false;
-        if (engine == VQB200_ENGINE_TCGEN05 || engine == VQB200_ENGINE_TCGEN05_BF16 || engine == VQB200_ENGINE_AUTO)
-            use_tc = tc_supported(L, d_x, dim, n_embed);
-        if ((engine == VQB200_ENGINE_TCGEN05 || engine == VQB200_ENGINE_TCGEN05_BF16) && !use_tc) return VQB200_EUNSUPPORTED;
         const int nsplit = engine == VQB200_ENGINE_TCGEN05_BF16 ? 1 : (engine == VQB200_ENGINE_TCGEN05 ? 3 : 0);
-        // statistics: private-table segmented reduction when [K][D] fp32 fits in shared memory, else the
-        // gather kernels fall back to global atomics
-        const size_t cs_smem = code_stats_smem_bytes(dim, n_embed);
-        const bool stats_kernel = d_stats && cs_smem <= 200 * 1024 && n_embed <= 65535;
         if (stats_kernel) { sums = nullptr; counts = nullptr; }
         const bool want_gather = d_quantize || d_diff || sums;
         const size_t gsmem = (size_t)GS_BM * (dim + 1) * sizeof(float);
         if (gsmem > 200 * 1024) return VQB200_EUNSUPPORTED;
-        if (gsmem > 48 * 1024)
+        if (gsmem > 48 * 1024) {
             VQ_CUDA(cudaFuncSetAttribute(k_gather_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+            VQ_CUDA(cudaFuncSetAttribute(k_fixup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+        }
         const int sms = tc_num_sms();
         if (use_tc) {
-            // tensor-core filter + fused output for certified rows; flagged rows -> exact SIMT fix-up
-            VQ_CUDA(cudaMemsetAsync(sc.flagged_count, 0, sizeof(int), st));
+            // tensor-core filter + fused output for certified rows; flagged rows -> exact SIMT fix-up (one launch:
+            // re-score, gather / output / loss of those rows, loss finalisation)
             int rc = tc_forward(d_x, L, dim, n_embed, cb, d_quantize, d_ind, sc, d_diff ? sc.diff_acc : nullptr, sums,
                                 counts, dbg_scores, st, prof, nsplit);
             g_launches.fetch_add(1);
             if (rc) return cuda_fail(cudaGetLastError());
-            k_assign_exact<<<sms * 2, AS_THREADS, 0, st>>>(d_x, L, dim, n_embed, cb.cbT, cb.ee, d_ind,
-                                                           sc.flagged_rows, sc.flagged_count);
+            k_fixup<<<sms, AS_THREADS, gsmem, st>>>(d_x, L, dim, n_embed, cb.cbT, cb.ee, d_ind, d_quantize,
+                                                    d_diff ? sc.diff_acc : nullptr, sums, counts, sc.flagged_rows,
+                                                    sc.flagged_count, want_gather ? 1 : 0, fin_diff, inv, sc.ticket);
             VQ_LAUNCH_CHECK();
-            if (want_gather) {
-                k_gather_stats<<<sms * 2, GS_THREADS, gsmem, st>>>(d_x, L, dim, n_embed, cb.cbT, d_ind, d_quantize,
-                                                                    d_diff ? sc.diff_acc : nullptr, sums, counts,
-                                                                    sc.flagged_rows, sc.flagged_count);
-                VQ_LAUNCH_CHECK();
-            }
+            finalized = true;
         } else {
             int64_t blocks = std::min<int64_t>((L.n_rows + AS_BM - 1) / AS_BM, (int64_t)sms * 64);
             k_assign_exact<<<(unsigned)blocks, AS_THREADS, 0, st>>>(d_x, L, dim, n_embed, cb.cbT, cb.ee, d_ind,
@@ -116,8 +128,9 @@ int forward_impl(const float* d_x, const RowLayout& L, int dim, int n_embed, con
                 int64_t gblocks = std::min<int64_t>((L.n_rows + GS_BM - 1) / GS_BM, (int64_t)sms * 64);
                 k_gather_stats<<<(unsigned)gblocks, GS_THREADS, gsmem, st>>>(
                     d_x, L, dim, n_embed, cb.cbT, d_ind, d_quantize, d_diff ? sc.diff_acc : nullptr, sums, counts,
-                    nullptr, nullptr);
+                    nullptr, nullptr, fin_diff, inv, sc.ticket);
                 VQ_LAUNCH_CHECK();
+                finalized = true;
             }
         }
         if (stats_kernel) {
@@ -131,16 +144,14 @@ int forward_impl(const float* d_x, const RowLayout& L, int dim, int n_embed, con
             int parts = (int)std::min<int64_t>(n_chunks, sms_cs);
             k_code_stats<<<parts, CS_THREADS, cs_smem, st>>>(d_x, L, dim, n_embed, d_ind, sc.stat_partials, (int)chunk);
             VQ_LAUNCH_CHECK();
-            // d_stats += sum of the per-CTA tables (d_stats was cleared when zero_first, else keeps accumulating)
+            // d_stats (+)= sum of the per-CTA tables: overwrite on the first call, accumulate on host-path continuation chunks
             const int nstat = n_embed * (dim + 1);
-            k_stats_fold<<<(nstat + 127) / 128, dim3(32, 4), 0, st>>>(sc.stat_partials, parts, nstat, d_stats);
+            k_stats_fold<<<(nstat + 127) / 128, dim3(32, 4), 0, st>>>(sc.stat_partials, parts, nstat, d_stats,
+                                                                     zero_first ? 0 : 1);
             VQ_LAUNCH_CHECK();
         }
     }
-    if (finalize && d_diff) {
-        double inv = total_rows > 0 ? 1.0 / ((double)total_rows * (double)dim) : 0.0;
-        // mean over zero elements is NaN in the reference (0/0); keep that
-        if (total_rows == 0) inv = std::numeric_limits<double>::quiet_NaN();
+    if (fin_diff && !finalized) {
         k_finalize_diff<<<1, 32, 0, st>>>(sc.diff_acc, d_diff, inv);
         VQ_LAUNCH_CHECK();
     }
@@ -149,21 +160,28 @@ int forward_impl(const float* d_x, const RowLayout& L, int dim, int n_embed, con
 
 int ema_impl(const float* d_stats, float* d_cluster_size, float* d_embed_avg, float* d_embed, int dim,
              int n_embed, float decay, float one_minus_decay, float eps, void* d_codebook, cudaStream_t st) {
-    // d_stats = [sums K*D | counts K | 1 spare float used for n = sum(cluster_size)] -- see vqb200_stats_bytes
+    // d_stats = [sums K*D | counts K | 4 spare words: n = sum(cluster_size), EMA ticket] -- see vqb200_stats_bytes
     const float* sums = d_stats;
     const float* counts = d_stats + (size_t)n_embed * dim;
-    float* n_scratch = const_cast<float*>(d_stats) + (size_t)n_embed * (dim + 1);
-    k_ema_cluster<<<1, 1024, 0, st>>>(counts, d_cluster_size, n_embed, decay, one_minus_decay, n_scratch);
-    VQ_LAUNCH_CHECK();
+    float* spare = const_cast<float*>(d_stats) + (size_t)n_embed * (dim + 1);
     CodebookImage cb{nullptr, nullptr, nullptr, nullptr};
     if (d_codebook) cb = codebook_view(d_codebook, dim, n_embed);
+    if (tc_shape_ok(dim, n_embed)) {              // one launch: EMA + renormalise + next codebook image
+        k_ema64<<<n_embed / PREP_CODES, 256, 0, st>>>(d_stats, d_cluster_size, d_embed_avg, d_embed, cb.cbT, cb.ee, cb.tc,
+                                                       n_embed, decay, one_minus_decay, eps, tc::bound_cA(3),
+                                                       tc::bound_cA(1), tc::BOUND_CB,
+                                                       reinterpret_cast<unsigned int*>(spare + 1));
+        VQ_LAUNCH_CHECK();
+        return VQB200_OK;
+    }
+    k_ema_cluster<<<1, 1024, 0, st>>>(counts, d_cluster_size, n_embed, decay, one_minus_decay, spare);
+    VQ_LAUNCH_CHECK();
     int wpb = 8;
-    k_ema_embed<<<(n_embed + wpb - 1) / wpb, wpb * 32, 0, st>>>(sums, d_cluster_size, n_scratch, d_embed_avg,
+    k_ema_embed<<<(n_embed + wpb - 1) / wpb, wpb * 32, 0, st>>>(sums, d_cluster_size, spare, d_embed_avg,
                                                                  d_embed, cb.cbT, cb.ee, dim, n_embed, decay,
                                                                  one_minus_decay, eps);
     VQ_LAUNCH_CHECK();
-    if (!d_codebook) return VQB200_OK;
-    return tc_prepare_codebook(cb, dim, n_embed, st) ? cuda_fail(cudaGetLastError()) : VQB200_OK;
+    return VQB200_OK;
 }
 
 }  // namespace

@@ -140,7 +140,7 @@ class Quantize(nn.Module):
         ws = self._ws.get(device)
         if ws is None:
             ws = {"image": torch.empty(lib.vqb200_codebook_bytes(self.dim, self.n_embed), dtype=torch.uint8, device=device),
-                  "stats": torch.empty(lib.vqb200_stats_bytes(self.dim, self.n_embed) // 4, dtype=torch.float32, device=device),
+                  "stats": torch.zeros(lib.vqb200_stats_bytes(self.dim, self.n_embed) // 4, dtype=torch.float32, device=device),
                   "scratch": None, "rows": -1}
             self._ws = {device: ws}           # one device at a time (module.to() moves it)
         if ws["rows"] < n_rows:
