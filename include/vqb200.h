@@ -95,6 +95,18 @@ int vqb200_ema_update(const float* d_stats, float* d_cluster_size, float* d_embe
                       int32_t dim, int32_t n_embed, float decay, float one_minus_decay, float eps,
                       void* d_codebook, void* stream);
 
+/* The module's whole forward in one call (fewer host round trips per step):
+ *   vqb200_codebook_prepare(d_embed) + vqb200_quantize_forward(...) and, when `ema` != 0 and d_stats != NULL,
+ *   vqb200_ema_update on the statistics of this call (single-process training).  With several ranks the caller
+ *   passes ema = 0, all-reduces d_stats (vqvae.py:58-59) and calls vqb200_ema_update itself.
+ * d_cluster_size / d_embed_avg are only touched when the EMA runs.                                    */
+int vqb200_quantize_step(const float* d_x, int64_t n_rows, int32_t dim, int32_t n_embed,
+                         int64_t rows_per_image, int64_t image_stride, int64_t row_stride, int64_t col_stride,
+                         float* d_embed, float* d_cluster_size, float* d_embed_avg, void* d_codebook,
+                         float* d_quantize, int64_t* d_embed_ind, float* d_diff, float* d_stats,
+                         void* d_scratch, int32_t engine, int32_t ema, float decay, float one_minus_decay,
+                         float eps, void* stream);
+
 /* Gradient implied by vqvae.py:72-73:  grad_x = grad_quantize + grad_diff * 2 (x - e[ind]) / (N*D).
  * d_grad_quantize (same layout as x) and d_grad_diff (1 float) may each be NULL (= zero).           */
 int vqb200_quantize_backward(const float* d_x, const int64_t* d_embed_ind, const void* d_codebook,

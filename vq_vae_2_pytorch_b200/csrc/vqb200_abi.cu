@@ -248,6 +248,22 @@ int vqb200_ema_update(const float* d_stats, float* d_cluster_size, float* d_embe
                     d_codebook, (cudaStream_t)stream);
 }
 
+int vqb200_quantize_step(const float* d_x, int64_t n_rows, int32_t dim, int32_t n_embed, int64_t rows_per_image,
+                         int64_t image_stride, int64_t row_stride, int64_t col_stride, float* d_embed,
+                         float* d_cluster_size, float* d_embed_avg, void* d_codebook, float* d_quantize,
+                         int64_t* d_embed_ind, float* d_diff, float* d_stats, void* d_scratch, int32_t engine,
+                         int32_t ema, float decay, float one_minus_decay, float eps, void* stream) {
+    if (!d_embed) return VQB200_EINVAL;
+    if (ema && d_stats && (!d_cluster_size || !d_embed_avg)) return VQB200_EINVAL;
+    int rc = vqb200_codebook_prepare(d_embed, dim, n_embed, d_codebook, stream);
+    if (rc) return rc;
+    rc = vqb200_quantize_forward(d_x, n_rows, dim, n_embed, rows_per_image, image_stride, row_stride, col_stride,
+                                 d_codebook, d_quantize, d_embed_ind, d_diff, d_stats, d_scratch, engine, stream);
+    if (rc || !ema || !d_stats) return rc;
+    return vqb200_ema_update(d_stats, d_cluster_size, d_embed_avg, d_embed, dim, n_embed, decay, one_minus_decay, eps,
+                             nullptr, stream);
+}
+
 int vqb200_quantize_backward(const float* d_x, const int64_t* d_embed_ind, const void* d_codebook,
                              const float* d_grad_quantize, const float* d_grad_diff, float* d_grad_x,
                              int64_t n_rows, int32_t dim, int32_t n_embed, int64_t rows_per_image,

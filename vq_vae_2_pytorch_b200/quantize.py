@@ -33,12 +33,26 @@ def _collapse(sizes, strides):
     return n, dims[-1][1]
 
 
+_LAYOUT_CACHE = {}
+
+
 def row_layout(x: torch.Tensor):
     """Map a [..., D] tensor to the C ABI's row layout (n_rows, rows_per_image, image_stride,
     row_stride, col_stride) without copying, or None when the strides fit neither accepted form."""
-    D = x.shape[-1]
-    lead_sizes, lead_strides = list(x.shape[:-1]), list(x.stride()[:-1])
-    col = x.stride(-1) if D > 1 else 1
+    key = (tuple(x.shape), x.stride())
+    hit = _LAYOUT_CACHE.get(key, 0)
+    if hit != 0:
+        return hit
+    lay = _row_layout(x.shape, x.stride())
+    if len(_LAYOUT_CACHE) < 4096:
+        _LAYOUT_CACHE[key] = lay
+    return lay
+
+
+def _row_layout(shape, stride):
+    D = shape[-1]
+    lead_sizes, lead_strides = list(shape[:-1]), list(stride[:-1])
+    col = stride[-1] if D > 1 else 1
     n = 1
     for s in lead_sizes:
         n *= s
@@ -156,6 +170,7 @@ class Quantize(nn.Module):
     # decides the precision of later calls.  Either way the returned indices are the exact arg-min.
     FLAG_SWITCH_FRACTION = 3e-3
     SPLIT_COOLDOWN_CALLS = 64
+    FLAG_SAMPLE_EVERY = 8                     # bf16-mode calls between two read-backs of the counter
 
     def _pick_engine(self, x, lay):
         if self.engine != "auto" or os.environ.get("VQB200_TC_SPLIT"):
@@ -179,7 +194,10 @@ class Quantize(nn.Module):
 
     def _note_flagged(self, ws, n, eng, dev):
         f = self._filter
-        if eng not in (_native.ENGINE_TCGEN05_BF16, _native.ENGINE_TCGEN05) or f["pending"] is not None or n == 0:
+        if eng != _native.ENGINE_TCGEN05_BF16 or self.engine != "auto" or f["pending"] is not None or n == 0:
+            return
+        f["calls"] = f.get("calls", 0) + 1
+        if f["calls"] % self.FLAG_SAMPLE_EVERY != 1:
             return
         host = ws.get("flag_host")
         if host is None:
@@ -217,24 +235,27 @@ class Quantize(nn.Module):
         ind = torch.empty(x.shape[:-1], dtype=torch.int64, device=dev)
         diff = torch.empty((), dtype=torch.float32, device=dev)
         stats = ws["stats"] if self.training else None
-        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        stream = torch.cuda.current_stream(dev).cuda_stream
         eng = self._pick_engine(x, lay)
-        with torch.cuda.device(dev):
-            # the codebook image is re-derived from `embed` on every call: external writes to the buffer
-            # (load_state_dict, .data.copy_, DDP buffer broadcast) can never leave it stale
-            _native.check(lib.vqb200_codebook_prepare(_native.ptr(self.embed), self.dim, self.n_embed,
-                                                      _native.ptr(image), stream), "vqb200_codebook_prepare")
-            _native.check(lib.vqb200_quantize_forward(
-                _native.ptr(x), n, self.dim, self.n_embed, rpi, img, row, col, _native.ptr(image),
-                _native.ptr(quantize), _native.ptr(ind), _native.ptr(diff), _native.ptr(stats),
-                _native.ptr(ws["scratch"]), eng, stream), "vqb200_quantize_forward")
-            self._note_flagged(ws, n, eng, dev)
-            if self.training:
-                dist_fn.all_reduce(stats[: self.n_embed * (self.dim + 1)])  # vqvae.py:58-59 (one packed call)
-                _native.check(lib.vqb200_ema_update(
-                    _native.ptr(stats), _native.ptr(self.cluster_size), _native.ptr(self.embed_avg),
-                    _native.ptr(self.embed), self.dim, self.n_embed, float(self.decay), float(1 - self.decay),
-                    float(self.eps), None, stream), "vqb200_ema_update")                      # vqvae.py:61-70
+        fused_ema = self.training and dist_fn.get_world_size() == 1
+        if torch.cuda.current_device() != dev.index:
+            torch.cuda.set_device(dev)        # kernels launch on the input's device
+        # the codebook image is re-derived from `embed` on every call: external writes to the buffer
+        # (load_state_dict, .data.copy_, DDP buffer broadcast) can never leave it stale
+        _native.check(lib.vqb200_quantize_step(
+            x.data_ptr(), n, self.dim, self.n_embed, rpi, img, row, col, self.embed.data_ptr(),
+            self.cluster_size.data_ptr(), self.embed_avg.data_ptr(), image.data_ptr(),
+            quantize.data_ptr() if quantize is not None else None, ind.data_ptr(), diff.data_ptr(),
+            stats.data_ptr() if stats is not None else None, ws["scratch"].data_ptr(), eng,
+            1 if fused_ema else 0, float(self.decay), float(1 - self.decay), float(self.eps), stream),
+            "vqb200_quantize_step")                                                           # vqvae.py:43-73
+        self._note_flagged(ws, n, eng, dev)
+        if self.training and not fused_ema:
+            dist_fn.all_reduce(stats[: self.n_embed * (self.dim + 1)])  # vqvae.py:58-59 (one packed call)
+            _native.check(lib.vqb200_ema_update(
+                stats.data_ptr(), self.cluster_size.data_ptr(), self.embed_avg.data_ptr(),
+                self.embed.data_ptr(), self.dim, self.n_embed, float(self.decay), float(1 - self.decay),
+                float(self.eps), None, stream), "vqb200_ema_update")                          # vqvae.py:61-70
         return quantize, diff, ind, image, lay
 
     def forward(self, input):
