@@ -246,6 +246,10 @@ k_gather_stats(const float* __restrict__ x, RowLayout L, int D, int K,
 // ------------------------------------------------------------------------------------------------
 constexpr int CS_THREADS = 1024, CS_CHUNK = 4096, CS_MAX_CTAS = 160;
 
+// float add on shared memory (compiles to a CAS loop): only for the <= 2 buckets per warp and chunk that straddle the
+// boundary between two warps' ranges
+__device__ __forceinline__ void smem_add(float* p, float v) { atomicAdd(p, v); }
+
 __global__ void __launch_bounds__(CS_THREADS, 1)
 k_code_stats(const float* __restrict__ x, RowLayout L, int D, int K, const int64_t* __restrict__ embed_ind,
              float* __restrict__ partials /* [gridDim.x][K*(D+1)] */, int chunk /* rows per trip, <= CS_CHUNK */) {
@@ -257,12 +261,15 @@ k_code_stats(const float* __restrict__ x, RowLayout L, int D, int K, const int64
     int* cursor = start + K + 1;                              // [K]
     int* pad = cursor + K;                                    // keeps the int64 array 8-byte aligned
     int64_t* order = reinterpret_cast<int64_t*>(pad + ((4 * K + 1) & 1));        // [CS_CHUNK] element offsets of the rows, bucketed by code
-    unsigned short* code = reinterpret_cast<unsigned short*>(order + CS_CHUNK);   // [CS_CHUNK]
+    unsigned short* code = reinterpret_cast<unsigned short*>(order + CS_CHUNK);   // [CS_CHUNK] code of row i
+    unsigned short* scode = code + CS_CHUNK;                  // [CS_CHUNK] code at sorted position p
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = CS_THREADS / 32;
 
     for (int i = tid; i < K * D; i += CS_THREADS) table[i] = 0.f;
     for (int i = tid; i < K; i += CS_THREADS) cnt_total[i] = 0;
     const int64_t n_chunks = (L.n_rows + chunk - 1) / chunk;
+    const bool fast = (D == 64 && L.col_stride == 1 && (reinterpret_cast<uintptr_t>(x) & 7u) == 0 && (L.row_stride & 1) == 0 &&
+                       (L.image_stride & 1) == 0);
     // walk the chunks from the END of x: those rows were touched last by the assignment kernel and are
     // the most likely to still sit in L2
     for (int64_t j = n_chunks - 1 - blockIdx.x; j >= 0; j -= gridDim.x) {
@@ -294,36 +301,61 @@ k_code_stats(const float* __restrict__ x, RowLayout L, int D, int K, const int64
             if (lane == 0) start[K] = carry;
         }
         __syncthreads();
-        for (int i = tid; i < rows; i += CS_THREADS) order[atomicAdd(&cursor[code[i]], 1)] = row_offset(L, r0 + i);
+        for (int i = tid; i < rows; i += CS_THREADS) {
+            const int k = code[i];
+            const int dst = atomicAdd(&cursor[k], 1);
+            order[dst] = row_offset(L, r0 + i);
+            scode[dst] = (unsigned short)k;
+        }
+        for (int k = tid; k < K; k += CS_THREADS) cnt_total[k] += hist[k];
         __syncthreads();
-        // one warp per code bucket: coalesced row reads, register accumulation, exclusive table update
-        const bool fast = (D == 64 && L.col_stride == 1 && (reinterpret_cast<uintptr_t>(x) & 7u) == 0);
-        for (int k = warp; k < K; k += nwarps) {
-            const int b0 = start[k], b1 = start[k + 1];
-            if (b0 == b1) continue;
-            if (fast) {                               // lane owns dims (2*lane, 2*lane+1): one 256-byte request per row
+        if (fast) {
+            // flattened segmented reduction: every warp streams an equal share of the sorted positions with 16 rows
+            // (256 B each, lane owns dims 2l, 2l+1) in flight, accumulates while the code stays the same and adds to
+            // the table when it changes.  A bucket that lies inside the warp's range is owned exclusively (plain
+            // add); the at most two that straddle a range boundary use a shared-memory float add.
+            const int per = (rows + nwarps - 1) / nwarps;
+            const int my_begin = warp * per, my_end = min(rows, my_begin + per);
+            if (my_begin < my_end) {
+                int cur = scode[my_begin];
                 float a0 = 0.f, a1 = 0.f;
-                int b = b0;
-                for (; b + 8 <= b1; b += 8) {
-                    float2 v[8];
+                auto flush = [&](int k) {
+                    float* t = table + (size_t)k * 64 + 2 * lane;
+                    if (start[k] >= my_begin && start[k + 1] <= my_end) {
+                        float2 tv = *reinterpret_cast<float2*>(t);
+                        tv.x += a0; tv.y += a1;
+                        *reinterpret_cast<float2*>(t) = tv;
+                    } else {
+                        smem_add(t, a0);
+                        smem_add(t + 1, a1);
+                    }
+                };
+                for (int p = my_begin; p < my_end; p += 16) {
+                    float2 v[16];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) v[u] = __ldcs(reinterpret_cast<const float2*>(x + order[b + u]) + lane);
+                    for (int u = 0; u < 16; ++u) {
+                        const int pp = p + u;
+                        v[u] = pp < my_end ? __ldcs(reinterpret_cast<const float2*>(x + order[pp]) + lane) : make_float2(0.f, 0.f);
+                    }
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) { a0 += v[u].x; a1 += v[u].y; }
+                    for (int u = 0; u < 16; ++u) {
+                        const int cd = p + u < my_end ? (int)scode[p + u] : cur;      // warp-uniform
+                        if (cd != cur) {
+                            flush(cur);
+                            a0 = 0.f; a1 = 0.f;
+                            cur = cd;
+                        }
+                        a0 += v[u].x;
+                        a1 += v[u].y;
+                    }
                 }
-                if (b < b1) {
-                    float2 v[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u)
-                        v[u] = (b + u < b1) ? __ldcs(reinterpret_cast<const float2*>(x + order[b + u]) + lane) : make_float2(0.f, 0.f);
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) { a0 += v[u].x; a1 += v[u].y; }
-                }
-                float2* trow = reinterpret_cast<float2*>(table + (size_t)k * 64) + lane;
-                float2 tv = *trow;
-                tv.x += a0; tv.y += a1;
-                *trow = tv;
-            } else {
+                flush(cur);
+            }
+        } else {
+            // one warp per code bucket: register accumulation, exclusive table update
+            for (int k = warp; k < K; k += nwarps) {
+                const int b0 = start[k], b1 = start[k + 1];
+                if (b0 == b1) continue;
                 for (int d0 = 0; d0 < D; d0 += 64) {
                     float a0 = 0.f, a1 = 0.f;
                     const int da = d0 + lane, db = d0 + 32 + lane;
@@ -348,7 +380,6 @@ k_code_stats(const float* __restrict__ x, RowLayout L, int D, int K, const int64
                     if (db < D) table[(size_t)k * D + db] += a1;
                 }
             }
-            if (lane == 0) cnt_total[k] += b1 - b0;
         }
     }
     __syncthreads();
@@ -357,18 +388,19 @@ k_code_stats(const float* __restrict__ x, RowLayout L, int D, int K, const int64
     for (int i = tid; i < K; i += CS_THREADS) out[(size_t)K * D + i] = (float)cnt_total[i];
 }
 
-// stats[i] (+)= sum over CTAs of partials[c][i].  block = (32, 4): 128 consecutive elements per block, four 32-wide
-// column groups; thread-row y sums the tables c = y, y+4, ... (8 independent loads in flight), the four partial
-// sums are folded in a fixed order -> deterministic for a fixed grid.  accumulate == 0 overwrites stats (no memset
-// needed before); the spare words behind the n elements (EMA ticket) are cleared either way.
-__global__ void k_stats_fold(const float* __restrict__ partials, int n_parts, int n, float* __restrict__ stats,
-                             int accumulate) {
-    __shared__ float part[4][4][32];
+// stats[i] (+)= sum over CTAs of partials[c][i].  block = (32, FOLD_Y): 128 consecutive elements per block as four
+// 32-wide column groups; thread-row y sums the tables c = y, y + FOLD_Y, ... (all its loads in flight together), the
+// FOLD_Y partial sums are folded in a fixed order -> deterministic for a fixed grid.  accumulate == 0 overwrites stats
+// (no memset needed before); the spare words behind the n elements (EMA ticket) are cleared either way.
+constexpr int FOLD_Y = 16;
+__global__ void __launch_bounds__(32 * FOLD_Y)
+k_stats_fold(const float* __restrict__ partials, int n_parts, int n, float* __restrict__ stats, int accumulate) {
+    __shared__ float part[FOLD_Y][4][32];
     const int col = threadIdx.x, y = threadIdx.y;
     const int i0 = blockIdx.x * 128;
     float s[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int c = y; c < n_parts; c += 8) {
-        const int c2 = c + 4;
+    for (int c = y; c < n_parts; c += 2 * FOLD_Y) {
+        const int c2 = c + FOLD_Y;
         float v[8];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -382,16 +414,20 @@ __global__ void k_stats_fold(const float* __restrict__ partials, int n_parts, in
 #pragma unroll
     for (int u = 0; u < 4; ++u) part[y][u][col] = s[u];
     __syncthreads();
-    const int u = y, i = i0 + u * 32 + col;
-    if (i < n) {
-        const float t = (part[0][u][col] + part[1][u][col]) + (part[2][u][col] + part[3][u][col]);
-        stats[i] = accumulate ? stats[i] + t : t;
+    if (y < 4) {
+        const int u = y, i = i0 + u * 32 + col;
+        if (i < n) {
+            float t = 0.f;
+#pragma unroll
+            for (int r = 0; r < FOLD_Y; ++r) t += part[r][u][col];
+            stats[i] = accumulate ? stats[i] + t : t;
+        }
     }
     if (blockIdx.x == 0 && y == 0 && col < 4) stats[n + col] = 0.f;
 }
 
 __host__ __device__ inline size_t code_stats_smem_bytes(int D, int K) {
-    return (size_t)K * D * 4 + (size_t)(4 * K + 2) * 4 + (size_t)CS_CHUNK * 8 + (size_t)CS_CHUNK * 2 + 16;
+    return (size_t)K * D * 4 + (size_t)(4 * K + 2) * 4 + (size_t)CS_CHUNK * 8 + (size_t)CS_CHUNK * 2 * 2 + 16;
 }
 
 __global__ void k_finalize_diff(const double* __restrict__ diff_acc, float* __restrict__ diff, double inv_count) {

@@ -77,6 +77,16 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// same with an L2 cache policy (createpolicy): x tiles are read again by the output warps and by the statistics kernel
+__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -565,6 +575,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
                     bulk_g2s(sB + P::off_b_lo(K) + (uint32_t)u * UROWS * 128u, p.image + image_off_lo(K) + krow * 128, UROWS * 128u, bar(BAR_B));
                 bulk_g2s(sB + P::off_b_misc(K) + (uint32_t)u * UROWS * 32u, p.image + (NSPLIT == 3 ? image_off_misc(K) : image_off_misc1(K)) + krow * 32, UROWS * 32u, bar(BAR_B));
             }
+            const uint64_t keep = l2_policy_evict_last();
             for (uint32_t it = 0; it < n_iter; ++it) {
                 const int64_t t = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
                 const uint32_t s = it % XS, ph = (it / XS) & 1u;
@@ -573,7 +584,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
                 const uint32_t rows = (uint32_t)max((int64_t)0, min((int64_t)TILE_M, p.n_rows - r0));
                 const uint32_t bytes = rows * TC_D * 4u;
                 mbar_expect_tx(bar(BAR_XF + s), bytes);
-                if (bytes) bulk_g2s(sX + s * P::X_STAGE, p.x + r0 * TC_D, bytes, bar(BAR_XF + s));
+                if (bytes) bulk_g2s_hint(sX + s * P::X_STAGE, p.x + r0 * TC_D, bytes, bar(BAR_XF + s), keep);
             }
             if (DBG && prof) flush(PF_PROD_WAIT_XE, 0);
         }

@@ -146,7 +146,7 @@ int forward_impl(const float* d_x, const RowLayout& L, int dim, int n_embed, con
             VQ_LAUNCH_CHECK();
             // d_stats (+)= sum of the per-CTA tables: overwrite on the first call, accumulate on host-path continuation chunks
             const int nstat = n_embed * (dim + 1);
-            k_stats_fold<<<(nstat + 127) / 128, dim3(32, 4), 0, st>>>(sc.stat_partials, parts, nstat, d_stats,
+            k_stats_fold<<<(nstat + 127) / 128, dim3(32, FOLD_Y), 0, st>>>(sc.stat_partials, parts, nstat, d_stats,
                                                                      zero_first ? 0 : 1);
             VQ_LAUNCH_CHECK();
         }
