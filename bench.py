@@ -146,6 +146,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tcgen05", "tcgen05_bf16"])
     ap.add_argument("--dist", default="clustered", choices=["clustered", "randn"])
+    ap.add_argument("--layout", default="dense", choices=["dense", "nchw"],
+                    help="dense: contiguous [B,H,W,D] rows (cfg-2 primary); nchw: the permute(0,2,3,1) view VQVAE.encode passes")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -183,7 +185,10 @@ def main():
             x = embed0.t()[pick] + 0.1 * torch.randn(N_ROWS, D, device=dev, generator=g)
         else:
             x = torch.randn(N_ROWS, D, device=dev, generator=g)
-        xs.append(x.reshape(B, H, W, D).contiguous())
+        x = x.reshape(B, H, W, D).contiguous()
+        if args.layout == "nchw":
+            x = x.permute(0, 3, 1, 2).contiguous().permute(0, 2, 3, 1)
+        xs.append(x)
 
     def step(i):
         return q(xs[i % 3])
@@ -233,7 +238,7 @@ def main():
     # ---- roofline of the fused forward call (the dominant launch), timed alone with events on its stream
     peak, peak_src = measured_peaks()
     ws = q._workspace(dev, N_ROWS)
-    quant = torch.empty_like(xs[0]); ind = torch.empty(B, H, W, dtype=torch.int64, device=dev)
+    quant = torch.empty(B, H, W, D, device=dev); ind = torch.empty(B, H, W, dtype=torch.int64, device=dev)
     diff = torch.empty((), device=dev)
     stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     eng = _native.ENGINES[args.engine]
@@ -242,8 +247,10 @@ def main():
     reset()
     _native.check(lib.vqb200_codebook_prepare(_native.ptr(q.embed), D, K, _native.ptr(ws["image"]), stream), "prepare")
 
+    xd = xs if args.layout == "dense" else [x.contiguous() for x in xs]      # the kernel-level timing uses dense rows
+
     def fwd_only(i, with_stats):
-        _native.check(lib.vqb200_quantize_forward(_native.ptr(xs[i % 3]), N_ROWS, D, K, N_ROWS, 0, D, 1,
+        _native.check(lib.vqb200_quantize_forward(_native.ptr(xd[i % 3]), N_ROWS, D, K, N_ROWS, 0, D, 1,
                                                   _native.ptr(ws["image"]), _native.ptr(quant), _native.ptr(ind),
                                                   _native.ptr(diff), _native.ptr(ws["stats"]) if with_stats else None,
                                                   _native.ptr(ws["scratch"]), eng, stream), "forward")
@@ -327,7 +334,7 @@ def main():
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": "cfg-2: bottom quantizer, x=[128,64,64,64] fp32 per GPU, D=64, K=512, train fwd+EMA",
-                           "rows_per_gpu": N_ROWS, "dim": D, "n_embed": K, "distribution": args.dist, "engine": args.engine,
+                           "rows_per_gpu": N_ROWS, "dim": D, "n_embed": K, "distribution": args.dist, "engine": args.engine, "layout": args.layout,
                            "l2_policy": "3 rotating 134 MB input batches (each larger than the 126 MB L2)",
                            "codebook_state": "EMA steady state (cluster_size = N/K, embed_avg = embed*N/K)" if args.dist == "clustered" else "reference init",
                            "parallelism": f"dp{world}"},

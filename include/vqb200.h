@@ -107,6 +107,14 @@ int vqb200_quantize_step(const float* d_x, int64_t n_rows, int32_t dim, int32_t 
                          void* d_scratch, int32_t engine, int32_t ema, float decay, float one_minus_decay,
                          float eps, void* stream);
 
+/* Re-pack between a strided row layout (same layout arguments as vqb200_quantize_forward; e.g. the NCHW-physical
+ * permute(0,2,3,1) view VQVAE.encode passes, vqvae.py:227,235) and dense [n_rows, dim] rows, coalesced on both sides.
+ * to_dense != 0: d_src strided -> d_dst dense;  to_dense == 0: d_src dense -> d_dst strided.  The module uses it to
+ * feed strided inputs to the tcgen05 engine (which stages dense 256-byte rows) and to write `quantize` back with the
+ * input's strides (vqvae.py:73).                                                                                    */
+int vqb200_repack_rows(const float* d_src, float* d_dst, int64_t n_rows, int32_t dim, int64_t rows_per_image,
+                       int64_t image_stride, int64_t row_stride, int64_t col_stride, int32_t to_dense, void* stream);
+
 /* Gradient implied by vqvae.py:72-73:  grad_x = grad_quantize + grad_diff * 2 (x - e[ind]) / (N*D).
  * d_grad_quantize (same layout as x) and d_grad_diff (1 float) may each be NULL (= zero).           */
 int vqb200_quantize_backward(const float* d_x, const int64_t* d_embed_ind, const void* d_codebook,

@@ -228,3 +228,25 @@ def test_tc_fused_statistics_with_skewed_codes(engine, live_codes):
     assert torch.allclose(q.cluster_size.double(), want_cs, rtol=1e-6, atol=0)
     err = (q.embed_avg.double() - want_avg).abs().max(0).values / want_avg.abs().max(0).values
     assert float(err.max()) <= REL_TOL
+
+
+@pytest.mark.parametrize("shape", [(3, 64, 5, 7), (4, 64, 32, 32)])
+def test_tc_engine_on_nchw_physical_input(shape):
+    """VQVAE.encode passes conv_output.permute(0, 2, 3, 1) (vqvae.py:227,235): rows with unit row stride.  The module
+    re-packs such inputs to dense rows for the tcgen05 engine and writes `quantize` back with the input's strides."""
+    torch.manual_seed(41)
+    B, D, H, W = shape
+    a = vq.Quantize(D, 512).to(DEV).train()
+    b = vq.Quantize(D, 512, engine="simt").to(DEV).train()
+    b.load_state_dict(a.state_dict())
+    x = torch.randn(B, D, H, W, device=DEV).permute(0, 2, 3, 1)
+    assert not x.is_contiguous()
+    qa, da, ia = a(x)
+    qb, db, ib = b(x)
+    assert qa.stride() == x.stride() and qa.shape == x.shape          # vqvae.py:73 keeps the input's strides
+    assert torch.equal(ia, ib)
+    assert torch.equal(qa, qb)
+    assert abs(float(da) - float(db)) <= 1e-6 * float(db)
+    assert col_rel_err(a.embed_avg.cpu().numpy(), b.embed_avg.cpu().numpy()) <= REL_TOL
+    assert torch.allclose(a.cluster_size, b.cluster_size, rtol=1e-6, atol=0)
+    assert _native.load().vqb200_launch_count() > 0

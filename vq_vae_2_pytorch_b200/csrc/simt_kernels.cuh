@@ -484,6 +484,44 @@ __global__ void k_ema_embed(const float* __restrict__ sums, const float* __restr
 }
 
 // ------------------------------------------------------------------------------------------------
+// re-pack between a strided row layout (e.g. the NCHW-physical permute(0,2,3,1) view VQVAE.encode passes,
+// vqvae.py:227,235) and dense [N, D] rows: the tcgen05 engine stages dense 256-byte rows with bulk copies.
+// Tiles of RP_ROWS rows go through shared memory so that both sides are coalesced.
+// ------------------------------------------------------------------------------------------------
+constexpr int RP_ROWS = 64, RP_THREADS = 256;
+
+template <bool PACK>   // PACK: strided -> dense;  !PACK: dense -> strided
+__global__ void __launch_bounds__(RP_THREADS)
+k_repack_rows(const float* __restrict__ src, float* __restrict__ dst, RowLayout L, int D) {
+    extern __shared__ float rp_tile[];           // [RP_ROWS][D + 1]
+    __shared__ int64_t roff[RP_ROWS];
+    const int tid = threadIdx.x, ld = D + 1;
+    for (int64_t n0 = (int64_t)blockIdx.x * RP_ROWS; n0 < L.n_rows; n0 += (int64_t)gridDim.x * RP_ROWS) {
+        const int rows = (int)min((int64_t)RP_ROWS, L.n_rows - n0);
+        __syncthreads();
+        if (tid < RP_ROWS) roff[tid] = tid < rows ? row_offset(L, n0 + tid) : 0;
+        __syncthreads();
+        if (PACK) {
+            for (int i = tid; i < RP_ROWS * D; i += RP_THREADS) {
+                int r, d;
+                if (L.col_stride == 1) { r = i / D; d = i % D; } else { d = i / RP_ROWS; r = i % RP_ROWS; }
+                if (r < rows) rp_tile[r * ld + d] = src[roff[r] + (int64_t)d * L.col_stride];
+            }
+            __syncthreads();
+            for (int i = tid; i < rows * D; i += RP_THREADS) dst[n0 * D + i] = rp_tile[(i / D) * ld + (i % D)];
+        } else {
+            for (int i = tid; i < rows * D; i += RP_THREADS) rp_tile[(i / D) * ld + (i % D)] = src[n0 * D + i];
+            __syncthreads();
+            for (int i = tid; i < RP_ROWS * D; i += RP_THREADS) {
+                int r, d;
+                if (L.col_stride == 1) { r = i / D; d = i % D; } else { d = i / RP_ROWS; r = i % RP_ROWS; }
+                if (r < rows) dst[roff[r] + (int64_t)d * L.col_stride] = rp_tile[r * ld + d];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // backward implied by vqvae.py:72-73
 // ------------------------------------------------------------------------------------------------
 __global__ void k_backward(const float* __restrict__ x, RowLayout L, int D,

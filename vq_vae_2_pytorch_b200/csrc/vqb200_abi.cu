@@ -264,6 +264,29 @@ int vqb200_quantize_step(const float* d_x, int64_t n_rows, int32_t dim, int32_t 
                              nullptr, stream);
 }
 
+int vqb200_repack_rows(const float* d_src, float* d_dst, int64_t n_rows, int32_t dim, int64_t rows_per_image,
+                       int64_t image_stride, int64_t row_stride, int64_t col_stride, int32_t to_dense, void* stream) {
+    if (dim <= 0 || n_rows < 0) return VQB200_EINVAL;
+    if (n_rows == 0) return VQB200_OK;
+    if (!d_src || !d_dst) return VQB200_EINVAL;
+    if (!layout_ok(n_rows, dim, rows_per_image, image_stride, row_stride, col_stride)) return VQB200_EUNSUPPORTED;
+    RowLayout L{n_rows, rows_per_image, image_stride, row_stride, col_stride};
+    const size_t smem = (size_t)RP_ROWS * (dim + 1) * sizeof(float);
+    if (smem > 200 * 1024) return VQB200_EUNSUPPORTED;
+    const int64_t tiles = (n_rows + RP_ROWS - 1) / RP_ROWS;
+    const unsigned blocks = (unsigned)std::min<int64_t>(tiles, (int64_t)tc_num_sms() * 32);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (to_dense) {
+        if (smem > 48 * 1024) VQ_CUDA(cudaFuncSetAttribute(k_repack_rows<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_repack_rows<true><<<blocks, RP_THREADS, smem, st>>>(d_src, d_dst, L, dim);
+    } else {
+        if (smem > 48 * 1024) VQ_CUDA(cudaFuncSetAttribute(k_repack_rows<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_repack_rows<false><<<blocks, RP_THREADS, smem, st>>>(d_src, d_dst, L, dim);
+    }
+    VQ_LAUNCH_CHECK();
+    return VQB200_OK;
+}
+
 int vqb200_quantize_backward(const float* d_x, const int64_t* d_embed_ind, const void* d_codebook,
                              const float* d_grad_quantize, const float* d_grad_diff, float* d_grad_x,
                              int64_t n_rows, int32_t dim, int32_t n_embed, int64_t rows_per_image,
