@@ -142,6 +142,12 @@ int vqb200_debug_tc_scores(const float* d_x, int64_t n_rows, int32_t dim, int32_
 int vqb200_debug_tc_profile(const float* d_x, int64_t n_rows, int32_t dim, int32_t n_embed,
                             const void* d_codebook, float* d_quantize, int64_t* d_embed_ind,
                             void* d_scratch, uint64_t* d_prof, int32_t engine, void* stream);
+/* The tensor-core kernel ALONE (tc::k_vq_tc: assignment + gather + straight-through value + loss partial sums), no
+ * fix-up / finalisation launches: what bench.py times with CUDA events for the roofline of the dominant kernel.  The
+ * caller prepares the codebook image and clears the first 256 bytes of d_scratch once; uncertified rows are appended
+ * to the flagged list and otherwise left untouched.                                                           */
+int vqb200_debug_tc_kernel(const float* d_x, int64_t n_rows, int32_t dim, int32_t n_embed, const void* d_codebook,
+                           float* d_quantize, int64_t* d_embed_ind, void* d_scratch, int32_t engine, void* stream);
 int vqb200_tc_profile_slots(void);
 /* 1 when vqb200_quantize_forward would take the tcgen05 engine for this shape / layout / pointer alignment */
 int vqb200_tc_supported(const float* d_x, int64_t n_rows, int32_t dim, int32_t n_embed,

@@ -39,6 +39,7 @@ SIGNATURES = {
     "vqb200_tc_supported": (C.c_int, [_p, _i64, _i32, _i32, _i64, _i64, _i64, _i64]),
     "vqb200_debug_tc_profile": (C.c_int, [_p, _i64, _i32, _i32, _p, _p, _p, _p, _p, _i32, _p]),
     "vqb200_tc_profile_slots": (C.c_int, []),
+    "vqb200_debug_tc_kernel": (C.c_int, [_p, _i64, _i32, _i32, _p, _p, _p, _p, _i32, _p]),
     "vqb200_host_ctx_create": (C.c_int, [_i64, _i32, _i32, C.POINTER(_p)]),
     "vqb200_host_ctx_destroy": (None, [_p]),
     "vqb200_host_quantize": (C.c_int, [_p, _p, _i64, _p, _p, _p, _f32, _f32, _f32, _i32, _p, _p, _p, _i32]),

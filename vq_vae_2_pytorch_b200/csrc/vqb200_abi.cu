@@ -355,6 +355,19 @@ int vqb200_debug_tc_profile(const float* d_x, int64_t n_rows, int32_t dim, int32
                         engine, true, false, n_rows, (cudaStream_t)stream, nullptr, -1,
                         reinterpret_cast<unsigned long long*>(d_prof));
 }
+int vqb200_debug_tc_kernel(const float* d_x, int64_t n_rows, int32_t dim, int32_t n_embed, const void* d_codebook,
+                           float* d_quantize, int64_t* d_embed_ind, void* d_scratch, int32_t engine, void* stream) {
+    if (!d_x || !d_codebook || !d_embed_ind || !d_scratch || n_rows <= 0) return VQB200_EINVAL;
+    if (engine != VQB200_ENGINE_TCGEN05 && engine != VQB200_ENGINE_TCGEN05_BF16) return VQB200_EINVAL;
+    RowLayout L{n_rows, n_rows, 0, dim, 1};
+    if (!tc_supported(L, d_x, dim, n_embed)) return VQB200_EUNSUPPORTED;
+    CodebookImage cb = codebook_view(const_cast<void*>(d_codebook), dim, n_embed);
+    ForwardScratch sc = scratch_view(d_scratch, n_rows);
+    int rc = tc_forward(d_x, L, dim, n_embed, cb, d_quantize, d_embed_ind, sc, sc.diff_acc, nullptr, nullptr, nullptr,
+                        (cudaStream_t)stream, nullptr, engine == VQB200_ENGINE_TCGEN05_BF16 ? 1 : 3);
+    g_launches.fetch_add(1);
+    return rc ? cuda_fail(cudaGetLastError()) : VQB200_OK;
+}
 int vqb200_tc_profile_slots(void) { return (int)tc::PROF_SLOTS; }
 
 // ---- host-buffer path ----------------------------------------------------------------------------
