@@ -218,8 +218,10 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = lib.vqb200_launch_count()
     ev0.record()
+    t_host0 = time.perf_counter()
     for i in range(steps):
         step(i)
+    host_issue_ms = (time.perf_counter() - t_host0) * 1e3 / steps      # host time to ISSUE a step (no sync inside)
     ev1.record()
     gpu_launches = int(lib.vqb200_launch_count() - launches0)
     torch.cuda.synchronize()
@@ -358,8 +360,10 @@ def main():
                            "rows_per_gpu": N_ROWS, "dim": D, "n_embed": K, "distribution": args.dist, "engine": args.engine, "layout": args.layout,
                            "l2_policy": "3 rotating 134 MB input batches (each larger than the 126 MB L2)",
                            "codebook_state": "EMA steady state (cluster_size = N/K, embed_avg = embed*N/K)" if args.dist == "clustered" else "reference init",
-                           "parallelism": f"dp{world}"},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches,
+                           "parallelism": f"dp{world}",
+                           "collective": ("none" if world == 1 else ("all-reduce fused into the EMA kernel over peer memory (NVLink P2P loads)"
+                                                                      if q._ws.get(dev, {}).get("peer") is not None else "NCCL all-reduce of the packed statistics"))},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches, "host_issue_ms_per_step": host_issue_ms,
                 "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:

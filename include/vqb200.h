@@ -95,6 +95,20 @@ int vqb200_ema_update(const float* d_stats, float* d_cluster_size, float* d_embe
                       int32_t dim, int32_t n_embed, float decay, float one_minus_decay, float eps,
                       void* d_codebook, void* stream);
 
+/* Multi-GPU form of vqb200_ema_update with the all-reduce of vqvae.py:58-59 (distributed.py:64-72) FUSED into the EMA
+ * kernel: no NCCL call and no extra launch.  Every rank keeps its packed statistics of the step in peer-mapped
+ * (symmetric) memory; h_stats_ptrs[r] / h_flag_ptrs[r] are HOST arrays of `world` DEVICE pointers, valid in THIS
+ * process, to rank r's statistics buffer of this step and to rank r's flag array (world x uint32, zero before the
+ * first step).  The kernel publishes "rank `rank` finished step `step`" to every peer (system-scope release store),
+ * waits until all ranks have published `step`, sums the per-rank statistics over NVLink in rank order (same bits on
+ * every rank) and applies vqvae.py:61-70.  `step` must grow by one per call (never 0) and the caller alternates
+ * between two statistics buffers (and two flag arrays) so that a rank one step ahead cannot overwrite what a peer
+ * still reads.  world <= 8; shapes the fused EMA kernel covers (dim 64, n_embed 256/512), else VQB200_EUNSUPPORTED. */
+int vqb200_ema_update_p2p(const void* const* h_stats_ptrs, void* const* h_flag_ptrs, int32_t rank, int32_t world,
+                          uint32_t step, float* d_cluster_size, float* d_embed_avg, float* d_embed,
+                          int32_t dim, int32_t n_embed, float decay, float one_minus_decay, float eps,
+                          void* d_codebook, void* stream);
+
 /* The module's whole forward in one call (fewer host round trips per step):
  *   vqb200_codebook_prepare(d_embed) + vqb200_quantize_forward(...) and, when `ema` != 0 and d_stats != NULL,
  *   vqb200_ema_update on the statistics of this call (single-process training).  With several ranks the caller

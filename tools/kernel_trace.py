@@ -13,13 +13,20 @@ engine = sys.argv[1] if len(sys.argv) > 1 else "auto"
 dist = sys.argv[2] if len(sys.argv) > 2 else "clustered"
 B, H, W, D, K = 128, 64, 64, 64, 512
 N = B * H * W
-dev = "cuda:0"
+import os
+world = int(os.environ.get("WORLD_SIZE", "1"))
+rank = int(os.environ.get("RANK", "0"))
+dev = f"cuda:{int(os.environ.get('LOCAL_RANK', '0'))}"
+torch.cuda.set_device(dev)
+if world > 1:
+    import torch.distributed as tdist
+    tdist.init_process_group("nccl", device_id=torch.device(dev))
 torch.manual_seed(0)
 q = vq.Quantize(D, K, engine=engine).to(dev).train()
 embed0 = q.embed.clone()
 xs = []
 for i in range(3):
-    g = torch.Generator(device=dev).manual_seed(1234 + 1000 * i)
+    g = torch.Generator(device=dev).manual_seed(1234 + 1000 * i + rank)
     if dist == "clustered":
         pick = torch.randint(0, K, (N,), device=dev, generator=g)
         x = embed0.t()[pick] + 0.1 * torch.randn(N, D, device=dev, generator=g)
@@ -27,8 +34,8 @@ for i in range(3):
         x = torch.randn(N, D, device=dev, generator=g)
     xs.append(x.reshape(B, H, W, D).contiguous())
 if dist == "clustered":
-    q.cluster_size.data.fill_(float(N) / K)
-    q.embed_avg.data.copy_(embed0 * (float(N) / K))
+    q.cluster_size.data.fill_(float(world * N) / K)
+    q.embed_avg.data.copy_(embed0 * (float(world * N) / K))
 for i in range(10):
     q(xs[i % 3])
 torch.cuda.synchronize()
@@ -44,6 +51,8 @@ for ev in prof.events():
         tot[ev.name[:70]] += ev.device_time
         cnt[ev.name[:70]] += 1
 total = sum(tot.values())
+if rank != 0:
+    sys.exit(0)
 print(f"engine={engine} dist={dist}: {total / steps:.1f} us of kernel time per step")
 for name, t in sorted(tot.items(), key=lambda kv: -kv[1]):
     print(f"{t / steps:9.2f} us/step  x{cnt[name] / steps:4.1f}  {name}")

@@ -40,25 +40,90 @@ __global__ void __launch_bounds__(256) k_prepare64(const float* __restrict__ emb
 // EMA update + Laplace-smoothed renormalisation (vqvae.py:61-70) + next codebook image in one launch.
 // grid = K / 8, block = 256.  Every block derives n = sum_k cluster_size_new[k] from the OLD cluster sizes,
 // which nobody overwrites until the last block to finish (ticket) stores the new ones.
+//
+// P2P = true fuses the all-reduce of vqvae.py:58-59 into this kernel (no NCCL call, no extra launch): every rank's
+// packed statistics live in peer-mapped (symmetric) memory, block 0 publishes "my statistics for this step are
+// complete" to all peers with a system-scope release store, every block waits for all ranks' flags and then sums the
+// per-rank statistics over NVLink in RANK ORDER (identical result on every rank, so the replicas stay bit-identical).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_ema64(const float* __restrict__ stats, float* __restrict__ cluster_size,
+constexpr int P2P_MAX_RANKS = 8;
+struct PeerStats {
+    const float* stats[P2P_MAX_RANKS];     // rank r's packed statistics of this step (this process' mapping)
+    unsigned int* flags[P2P_MAX_RANKS];    // rank r's flag array [world]: flags[r][w] = last step rank w has published
+    int rank, world;
+    unsigned int step;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// sum over the ranks, in rank order, of element i of every rank's statistics buffer.  All loads are issued before the
+// first add (one NVLink round trip instead of `world`); volatile: never from a stale local cache line, never hoisted
+// above the flag wait.
+__device__ __forceinline__ float peer_sum(const PeerStats& peers, size_t i) {
+    float v[P2P_MAX_RANKS];
+#pragma unroll
+    for (int r = 0; r < P2P_MAX_RANKS; ++r)
+        v[r] = r < peers.world ? *reinterpret_cast<const volatile float*>(peers.stats[r] + i) : 0.f;
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < P2P_MAX_RANKS; ++r) s += v[r];          // + 0.f for absent ranks: exact
+    return s;
+}
+
+template <bool P2P>
+__global__ void __launch_bounds__(256) k_ema64(const float* __restrict__ stats, PeerStats peers,
+                                                float* __restrict__ cluster_size,
                                                 float* __restrict__ embed_avg, float* __restrict__ embed,
                                                 float* __restrict__ cbT, float* __restrict__ ee,
                                                 unsigned char* __restrict__ img, int K, float decay,
                                                 float one_minus_decay, float eps, float cA, float cA1, float cB,
                                                 unsigned int* __restrict__ ticket) {
     __shared__ float es[PREP_CODES][65];
+    __shared__ float ssum[PREP_CODES][65];
+    __shared__ float cnt_s[512];                                // K <= 512 (tc_shape_ok)
     __shared__ float e2s[PREP_CODES];
     __shared__ float part[8];
     __shared__ float n_s;
     __shared__ unsigned int last_s;
-    const float* sums = stats;
-    const float* counts = stats + (size_t)K * 64;
     const int k0 = blockIdx.x * PREP_CODES, tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    if (P2P) {
+        if (blockIdx.x == 0 && tid < peers.world) {             // my statistics (written by the previous kernels) are complete
+            __threadfence_system();
+            st_release_sys(peers.flags[tid] + peers.rank, peers.step);
+        }
+        if (tid < peers.world) {
+            const unsigned int* f = peers.flags[peers.rank] + tid;
+            while ((int)(ld_acquire_sys(f) - peers.step) < 0) __nanosleep(64);
+        }
+        __syncthreads();
+
+    }
+    // counts / sums of this step (summed over the ranks in rank order) -> shared memory, all peer loads in one phase
+    float cv[2], sv[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int k = tid + 256 * u;
+        cv[u] = k < K ? (P2P ? peer_sum(peers, (size_t)K * 64 + k) : stats[(size_t)K * 64 + k]) : 0.f;
+        const int i = tid + 256 * u, j = i >> 6, d = i & 63;   // coalesced 256-byte rows of the 8 codes of this block
+        sv[u] = P2P ? peer_sum(peers, (size_t)(k0 + j) * 64 + d) : stats[(size_t)(k0 + j) * 64 + d];
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int k = tid + 256 * u;
+        if (k < K) cnt_s[k] = cv[u];
+        const int i = tid + 256 * u;
+        ssum[i >> 6][i & 63] = sv[u];
+    }
+    __syncthreads();
     float s = 0.f;
     for (int k = tid; k < K; k += 256) {
-        float c = cluster_size[k] * decay;
-        c = c + counts[k] * one_minus_decay;                    // vqvae.py:61-63
+        const float c = __fmaf_rn(cnt_s[k], one_minus_decay, __fmul_rn(cluster_size[k], decay));   // vqvae.py:61-63
         s += c;
     }
     s = warp_sum(s);
@@ -72,14 +137,12 @@ __global__ void __launch_bounds__(256) k_ema64(const float* __restrict__ stats, 
     __syncthreads();
     const float n = n_s;
     const float denom = n + (float)((double)K * (double)eps);
-    for (int i = tid; i < 64 * PREP_CODES; i += 256) {
+    for (int i = tid; i < 64 * PREP_CODES; i += 256) {          // 32-byte segments of 8 consecutive codes per dim
         const int d = i >> 3, j = i & 7, k = k0 + j;
-        float c = cluster_size[k] * decay;
-        c = c + counts[k] * one_minus_decay;
+        const float c = __fmaf_rn(cnt_s[k], one_minus_decay, __fmul_rn(cluster_size[k], decay));
         const float cs = (c + eps) / denom * n;                 // vqvae.py:66-68
         const size_t o = (size_t)d * K + k;
-        float a = embed_avg[o] * decay;
-        a = a + sums[(size_t)k * 64 + d] * one_minus_decay;     // vqvae.py:64
+        const float a = __fmaf_rn(ssum[j][d], one_minus_decay, __fmul_rn(embed_avg[o], decay));       // vqvae.py:64
         embed_avg[o] = a;
         const float e = a / cs;                                 // vqvae.py:69-70
         embed[o] = e;
@@ -104,9 +167,7 @@ __global__ void __launch_bounds__(256) k_ema64(const float* __restrict__ stats, 
     __syncthreads();
     if (last_s) {
         for (int k = tid; k < K; k += 256) {
-            float c = cluster_size[k] * decay;
-            c = c + counts[k] * one_minus_decay;
-            cluster_size[k] = c;
+            cluster_size[k] = __fmaf_rn(cnt_s[k], one_minus_decay, __fmul_rn(cluster_size[k], decay));
         }
         if (tid == 0) *ticket = 0u;                             // clean for the next launch
     }

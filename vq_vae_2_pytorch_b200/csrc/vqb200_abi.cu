@@ -158,22 +158,29 @@ int forward_impl(const float* d_x, const RowLayout& L, int dim, int n_embed, con
     return VQB200_OK;
 }
 
-int ema_impl(const float* d_stats, float* d_cluster_size, float* d_embed_avg, float* d_embed, int dim,
-             int n_embed, float decay, float one_minus_decay, float eps, void* d_codebook, cudaStream_t st) {
+int ema_impl(const float* d_stats, const PeerStats* peers, float* d_cluster_size, float* d_embed_avg, float* d_embed,
+             int dim, int n_embed, float decay, float one_minus_decay, float eps, void* d_codebook, cudaStream_t st) {
     // d_stats = [sums K*D | counts K | 4 spare words: n = sum(cluster_size), EMA ticket] -- see vqb200_stats_bytes
     const float* sums = d_stats;
     const float* counts = d_stats + (size_t)n_embed * dim;
     float* spare = const_cast<float*>(d_stats) + (size_t)n_embed * (dim + 1);
     CodebookImage cb{nullptr, nullptr, nullptr, nullptr};
     if (d_codebook) cb = codebook_view(d_codebook, dim, n_embed);
-    if (tc_shape_ok(dim, n_embed)) {              // one launch: EMA + renormalise + next codebook image
-        k_ema64<<<n_embed / PREP_CODES, 256, 0, st>>>(d_stats, d_cluster_size, d_embed_avg, d_embed, cb.cbT, cb.ee, cb.tc,
-                                                       n_embed, decay, one_minus_decay, eps, tc::bound_cA(3),
-                                                       tc::bound_cA(1), tc::BOUND_CB,
-                                                       reinterpret_cast<unsigned int*>(spare + 1));
+    if (tc_shape_ok(dim, n_embed)) {              // one launch: [all-reduce over peer memory +] EMA + renormalise + next image
+        PeerStats none{};
+        unsigned int* ticket = reinterpret_cast<unsigned int*>(spare + 1);
+        if (peers)
+            k_ema64<true><<<n_embed / PREP_CODES, 256, 0, st>>>(d_stats, *peers, d_cluster_size, d_embed_avg, d_embed, cb.cbT,
+                                                                 cb.ee, cb.tc, n_embed, decay, one_minus_decay, eps,
+                                                                 tc::bound_cA(3), tc::bound_cA(1), tc::BOUND_CB, ticket);
+        else
+            k_ema64<false><<<n_embed / PREP_CODES, 256, 0, st>>>(d_stats, none, d_cluster_size, d_embed_avg, d_embed, cb.cbT,
+                                                                  cb.ee, cb.tc, n_embed, decay, one_minus_decay, eps,
+                                                                  tc::bound_cA(3), tc::bound_cA(1), tc::BOUND_CB, ticket);
         VQ_LAUNCH_CHECK();
         return VQB200_OK;
     }
+    if (peers) return VQB200_EUNSUPPORTED;
     k_ema_cluster<<<1, 1024, 0, st>>>(counts, d_cluster_size, n_embed, decay, one_minus_decay, spare);
     VQ_LAUNCH_CHECK();
     int wpb = 8;
@@ -244,7 +251,25 @@ int vqb200_ema_update(const float* d_stats, float* d_cluster_size, float* d_embe
                       void* d_codebook, void* stream) {
     if (!d_stats || !d_cluster_size || !d_embed_avg || !d_embed || dim <= 0 || n_embed <= 0)
         return VQB200_EINVAL;
-    return ema_impl(d_stats, d_cluster_size, d_embed_avg, d_embed, dim, n_embed, decay, one_minus_decay, eps,
+    return ema_impl(d_stats, nullptr, d_cluster_size, d_embed_avg, d_embed, dim, n_embed, decay, one_minus_decay, eps,
+                    d_codebook, (cudaStream_t)stream);
+}
+
+int vqb200_ema_update_p2p(const void* const* h_stats_ptrs, void* const* h_flag_ptrs, int32_t rank, int32_t world,
+                          uint32_t step, float* d_cluster_size, float* d_embed_avg, float* d_embed, int32_t dim,
+                          int32_t n_embed, float decay, float one_minus_decay, float eps, void* d_codebook, void* stream) {
+    if (!h_stats_ptrs || !h_flag_ptrs || !d_cluster_size || !d_embed_avg || !d_embed || dim <= 0 || n_embed <= 0)
+        return VQB200_EINVAL;
+    if (world < 1 || world > P2P_MAX_RANKS || rank < 0 || rank >= world || step == 0) return VQB200_EINVAL;
+    if (!tc_shape_ok(dim, n_embed)) return VQB200_EUNSUPPORTED;
+    PeerStats ps{};
+    for (int r = 0; r < world; ++r) {
+        if (!h_stats_ptrs[r] || !h_flag_ptrs[r]) return VQB200_EINVAL;
+        ps.stats[r] = static_cast<const float*>(h_stats_ptrs[r]);
+        ps.flags[r] = static_cast<unsigned int*>(h_flag_ptrs[r]);
+    }
+    ps.rank = rank; ps.world = world; ps.step = step;
+    return ema_impl(ps.stats[rank], &ps, d_cluster_size, d_embed_avg, d_embed, dim, n_embed, decay, one_minus_decay, eps,
                     d_codebook, (cudaStream_t)stream);
 }
 
@@ -470,7 +495,7 @@ int vqb200_host_quantize(vqb200_host_ctx* c, const float* h_x, int64_t n_rows, f
     }
     if (h_diff) VQ_CUDA(cudaMemcpyAsync(h_diff, c->d_diff, 4, cudaMemcpyDeviceToHost, c->s_run));
     if (training) {
-        rc = ema_impl(c->d_stats, d_cluster_size, d_embed_avg, d_embed, D, K, decay, one_minus_decay, eps,
+        rc = ema_impl(c->d_stats, nullptr, d_cluster_size, d_embed_avg, d_embed, D, K, decay, one_minus_decay, eps,
                       c->d_codebook, c->s_run);
         if (rc) return rc;
     }

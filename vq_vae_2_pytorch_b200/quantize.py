@@ -163,6 +163,47 @@ class Quantize(nn.Module):
             ws["rows"] = n_rows
         return ws
 
+    # ------------------------------------------------------------------ peer memory for the fused all-reduce
+    def _peer_workspace(self, ws, dev):
+        """Symmetric (peer-mapped) statistics buffers of all ranks, set up collectively on the first multi-rank training
+        forward: two packed statistics buffers + two flag arrays per rank (double-buffered by step parity).  Returns None
+        (-> NCCL all-reduce + vqb200_ema_update) when peer memory is unavailable, the world is larger than 8 ranks, the
+        shape is outside the fused EMA kernel, or VQB200_NO_P2P is set."""
+        if "peer" in ws:
+            return ws["peer"]
+        ws["peer"] = None
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(), dist.get_rank()
+        ok = (world <= 8 and self.dim == 64 and self.n_embed in (256, 512) and not os.environ.get("VQB200_NO_P2P"))
+        peer = None
+        if ok:
+            try:
+                import torch.distributed._symmetric_memory as symm
+                n = _native.load().vqb200_stats_bytes(self.dim, self.n_embed) // 4
+                n_al = (n + 63) // 64 * 64
+                total = 2 * n_al + 2 * 64                      # [stats parity 0 | stats parity 1 | flags 0 | flags 1]
+                buf = symm.empty(total, dtype=torch.float32, device=dev)
+                hdl = symm.rendezvous(buf, dist.group.WORLD)
+                buf.zero_()
+                torch.cuda.synchronize(dev)
+                hdl.barrier()
+                ptrs = [int(p) for p in hdl.buffer_ptrs]
+                mk = lambda vals: (C.c_void_p * world)(*vals)
+                peer = {"buf": buf, "hdl": hdl, "rank": rank, "world": world, "step": 0, "parity": 0,
+                        "stats": [buf[0:n], buf[n_al:n_al + n]],
+                        "stats_ptrs": [mk([p + 4 * par * n_al for p in ptrs]) for par in (0, 1)],
+                        "flag_ptrs": [mk([p + 4 * (2 * n_al + 64 * par) for p in ptrs]) for par in (0, 1)]}
+            except Exception as exc:  # no peer access / unsupported build: keep the NCCL path
+                peer = None
+                self._peer_error = repr(exc)
+        # every rank must take the same path: agree collectively
+        flag = torch.tensor([1 if peer is not None else 0], device=dev, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            peer = None
+        ws["peer"] = peer
+        return peer
+
     # ------------------------------------------------------------------ filter precision policy
     # The plain-bf16 tensor-core filter needs 1/3 of the MMAs of the split-bf16 one but certifies fewer rows when
     # the two nearest codes are almost equidistant (e.g. N(0,1) inputs against a random codebook); uncertified rows
@@ -238,6 +279,12 @@ class Quantize(nn.Module):
         ind = torch.empty(x.shape[:-1], dtype=torch.int64, device=dev)
         diff = torch.empty((), dtype=torch.float32, device=dev)
         stats = ws["stats"] if self.training else None
+        if self.training and dist_fn.get_world_size() > 1:
+            peer = self._peer_workspace(ws, dev)
+            if peer is not None:              # this step's statistics go straight into peer-mapped memory
+                peer["step"] += 1
+                peer["parity"] = peer["step"] & 1
+                stats = peer["stats"][peer["parity"]]
         # Strided rows (the NCHW-physical permute(0,2,3,1) view of vqvae.py:227,235) on a shape the tcgen05 engine
         # covers: re-pack to dense rows (coalesced CUDA transpose), run the tensor-core engine, re-pack `quantize` back to
         # the input's strides (vqvae.py:73).  ~3x the HBM traffic of the dense case, still ~7x faster than the SIMT engine.
@@ -266,11 +313,19 @@ class Quantize(nn.Module):
                                                  lay[3], lay[4], 0, stream), "vqb200_repack_rows")
         self._note_flagged(ws, n, eng, dev)
         if self.training and not fused_ema:
-            dist_fn.all_reduce(stats[: self.n_embed * (self.dim + 1)])  # vqvae.py:58-59 (one packed call)
-            _native.check(lib.vqb200_ema_update(
-                stats.data_ptr(), self.cluster_size.data_ptr(), self.embed_avg.data_ptr(),
-                self.embed.data_ptr(), self.dim, self.n_embed, float(self.decay), float(1 - self.decay),
-                float(self.eps), None, stream), "vqb200_ema_update")                          # vqvae.py:61-70
+            peer = ws.get("peer")
+            if peer is not None:              # all-reduce fused into the EMA kernel over peer memory (vqvae.py:58-70)
+                _native.check(lib.vqb200_ema_update_p2p(
+                    peer["stats_ptrs"][peer["parity"]], peer["flag_ptrs"][peer["parity"]], peer["rank"], peer["world"],
+                    peer["step"], self.cluster_size.data_ptr(), self.embed_avg.data_ptr(), self.embed.data_ptr(),
+                    self.dim, self.n_embed, float(self.decay), float(1 - self.decay), float(self.eps), None, stream),
+                    "vqb200_ema_update_p2p")
+            else:
+                dist_fn.all_reduce(stats[: self.n_embed * (self.dim + 1)])  # vqvae.py:58-59 (one packed call)
+                _native.check(lib.vqb200_ema_update(
+                    stats.data_ptr(), self.cluster_size.data_ptr(), self.embed_avg.data_ptr(),
+                    self.embed.data_ptr(), self.dim, self.n_embed, float(self.decay), float(1 - self.decay),
+                    float(self.eps), None, stream), "vqb200_ema_update")                      # vqvae.py:61-70
         return quantize, diff, ind, image, lay
 
     def forward(self, input):
