@@ -63,20 +63,26 @@ struct ForwardScratch {
     int* flagged_count;    // 1 int: rows sent to the exact re-score
     unsigned int* ticket;  // 1 word: last-block-done ticket of the fix-up / gather kernels (kept zero between launches)
     int* flagged_rows;     // [n_rows] row ids
+    float4* partial;       // [n_rows] running (m1, m2, winner, ||e_winner||) of the sliced tensor-core engine (n_embed > 512), else null
     float* stat_partials;  // [STAT_PARTS][K*(D+1)] per-CTA statistics tables
 };
 constexpr int STAT_PARTS = 160;
+__host__ __device__ inline bool scratch_has_partial(int dim, int n_embed) { return dim == 64 && n_embed > 512; }
 __host__ __device__ inline size_t forward_scratch_bytes(int64_t n_rows, int dim, int n_embed) {
-    return 256 + align_up((size_t)n_rows * 4, 256) + (size_t)STAT_PARTS * n_embed * (dim + 1) * 4;
+    return 256 + align_up((size_t)n_rows * 4, 256) + (scratch_has_partial(dim, n_embed) ? align_up((size_t)n_rows * 16, 256) : 0) +
+           (size_t)STAT_PARTS * n_embed * (dim + 1) * 4;
 }
-__host__ __device__ inline ForwardScratch scratch_view(void* base, int64_t n_rows) {
+__host__ __device__ inline ForwardScratch scratch_view(void* base, int64_t n_rows, int dim, int n_embed) {
     unsigned char* p = (unsigned char*)base;
     ForwardScratch s;
     s.diff_acc = (double*)p;
     s.flagged_count = (int*)(p + 16);
     s.ticket = (unsigned int*)(p + 32);
     s.flagged_rows = (int*)(p + 256);
-    s.stat_partials = (float*)(p + 256 + align_up((size_t)n_rows * 4, 256));
+    p += 256 + align_up((size_t)n_rows * 4, 256);
+    s.partial = nullptr;
+    if (scratch_has_partial(dim, n_embed)) { s.partial = (float4*)p; p += align_up((size_t)n_rows * 16, 256); }
+    s.stat_partials = (float*)p;
     return s;
 }
 

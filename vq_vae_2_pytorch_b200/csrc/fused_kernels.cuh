@@ -16,6 +16,7 @@ constexpr int PREP_CODES = 8;      // codes per block of the image / EMA kernels
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_prepare64(const float* __restrict__ embed, float* __restrict__ cbT,
                                                     float* __restrict__ ee, unsigned char* __restrict__ img, int K,
+                                                    int slice_codes /* 0: one image of K codes; else sub-images of that many */,
                                                     float cA, float cA1, float cB) {
     __shared__ float es[PREP_CODES][65];
     __shared__ float e2s[PREP_CODES];
@@ -33,7 +34,12 @@ __global__ void __launch_bounds__(256) k_prepare64(const float* __restrict__ emb
     s = warp_sum(s);
     if (lane == 0) { ee[k0 + w] = s; e2s[w] = s; }
     __syncthreads();
-    if (tid < 8 * PREP_CODES) tc::tc_image_rows(&es[tid >> 3][0], e2s[tid >> 3], img, K, k0 + (tid >> 3), tid & 7, cA, cA1, cB);
+    if (tid < 8 * PREP_CODES) {
+        const int k = k0 + (tid >> 3);
+        if (slice_codes == 0) tc::tc_image_rows(&es[tid >> 3][0], e2s[tid >> 3], img, K, k, tid & 7, cA, cA1, cB);
+        else tc::tc_image_rows(&es[tid >> 3][0], e2s[tid >> 3], img + (size_t)(k / slice_codes) * tc::image_bytes(slice_codes),
+                               slice_codes, k % slice_codes, tid & 7, cA, cA1, cB);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

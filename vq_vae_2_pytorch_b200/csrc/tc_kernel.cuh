@@ -39,6 +39,10 @@ constexpr int THREADS = 768;        // 6 warpgroups; register budgets re-balance
 constexpr int W_EPI0 = 0, W_EPI1 = 4, W_OUT = 8, W_CONV = 16, W_PROD = 20, W_MMA = 21;
 constexpr int NORM_RING = 8;
 constexpr int RES_RING = 2;
+#ifndef VQB200_RELAX_NS
+#define VQB200_RELAX_NS 0    /* measured: 200 ns polling costs 3 us per launch (late wake-ups outweigh the freed issue slots) */
+#endif
+constexpr int RELAX_NS = VQB200_RELAX_NS;   // poll interval of the relaxed waits
 
 // error-bound constants (see DESIGN.md "certificate"): dot-product error <= c1 ||x|| ||e||
 //   split-bf16 (3 products): 3.1 * 2^-18 rounding + fp32 accumulation  -> c1 = 2^-16, cA = 2 c1
@@ -72,6 +76,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {}
+}
+// for roles with slack (producer, converters, output): poll rarely -- a waiting warp's try_wait / branch / nanosleep loop
+// was 23 % of all issued instructions (ncu), taken from the schedulers the scan warps need
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+template <int NS>
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+    if constexpr (NS == 0) mbar_wait(bar, parity);
+    else while (!mbar_test_wait(bar, parity)) __nanosleep(NS);
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -468,6 +488,12 @@ struct Params {
     unsigned long long* prof;        // optional [grid][PROF_SLOTS] cycle counters (pipeline bubble analysis)
     int dbg_skip;                    // DBG builds only: bit0 skip output work, bit1 skip conversion, bit2 skip scan, bit3 skip MMAs
     float cA, cB;
+    // codebooks larger than the resident operand image (K > 512): one launch per 512-code slice.  Scores of a row are
+    // comparable across slices (same row offset, per-code error terms), so the running (m1, m2, winner, ||e_winner||) is
+    // carried in `partial` (one float4 per row); only the last slice certifies and writes outputs.
+    int code_base;                   // global index of this launch's first code
+    float4* partial;                 // may be null (single launch)
+    int pass_first, pass_last;
 };
 // profile slots (cycles, summed over the CTA's tiles; one recording lane per role)
 enum ProfSlot { PF_PROD_WAIT_XE = 0, PF_MMA_WAIT_AF, PF_MMA_WAIT_TE, PF_MMA_TOTAL, PF_CONV_WAIT_XF, PF_CONV_WAIT_AE,
@@ -521,6 +547,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
             pacc[acc] += clock64() - t0;
         } else {
             mbar_wait(bar(id), parity);
+        }
+    };
+    auto wait_r = [&](int id, uint32_t parity, int acc, bool rec) {     // relaxed polling (roles with slack)
+        if (DBG && prof && rec) {
+            const long long t0 = clock64();
+            mbar_wait_relaxed<RELAX_NS>(bar(id), parity);
+            pacc[acc] += clock64() - t0;
+        } else {
+            mbar_wait_relaxed<RELAX_NS>(bar(id), parity);
         }
     };
     auto flush = [&](int slot, int acc) { prof[slot] = (unsigned long long)pacc[acc]; };
@@ -579,7 +614,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
             for (uint32_t it = 0; it < n_iter; ++it) {
                 const int64_t t = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
                 const uint32_t s = it % XS, ph = (it / XS) & 1u;
-                wait_t(BAR_XE + s, ph ^ 1u, 0, true);
+                wait_r(BAR_XE + s, ph ^ 1u, 0, true);
                 const int64_t r0 = t * TILE_M;
                 const uint32_t rows = (uint32_t)max((int64_t)0, min((int64_t)TILE_M, p.n_rows - r0));
                 const uint32_t bytes = rows * TC_D * 4u;
@@ -638,8 +673,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
         for (uint32_t it = 0; it < n_iter; ++it) {
             const int64_t t = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
             const uint32_t sx = it % XS, phx = (it / XS) & 1u, sa = it % AS, pha = (it / AS) & 1u;
-            wait_t(BAR_XF + sx, phx, 0, rec);
-            wait_t(BAR_AE + sa, pha ^ 1u, 1, rec);
+            wait_r(BAR_XF + sx, phx, 0, rec);
+            wait_r(BAR_AE + sa, pha ^ 1u, 1, rec);
             const unsigned char* xs = sm + P::off_x(K) + sx * P::X_STAGE;
             unsigned char* ah = sm + P::off_a(K) + sa * P::A_STAGE;
             unsigned char* al = ah + 16384u;
@@ -772,14 +807,26 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
             }
             // certificate: every other code's lower bound must clear the winner's upper bound
             const float xn = rownorm_s[(it % NORM_RING) * TILE_M + row_in_tile];
-            const float en = enorm_s[k1 < K ? k1 : 0];
-            const float need = 2.f * (p.cA * BOUND_UP * xn * en + p.cB * (BOUND_UP * en * en + xn * xn));
-            const bool certified = ((m2 - m1) > need) && (xn < 1.0e18f) && !cb_bad;   // NaN -> false
+            float en = enorm_s[k1 < K ? k1 : 0];
             const bool in_range = grow < p.n_rows;
+            k1 += p.code_base;
+            bool bad = cb_bad;
+            if (p.partial) {                     // sliced codebook: fold in the earlier slices / hand on to the later ones
+                if (!p.pass_first && in_range) {
+                    const float4 o = p.partial[grow];
+                    const int ko = __float_as_int(o.z);
+                    bad = bad || ((__float_as_uint(o.w) >> 31) != 0u);   // an earlier slice saw a non-finite codebook
+                    m2 = fminf(fminf(o.y, m2), fmaxf(o.x, m1));
+                    if ((o.x < m1) || (o.x == m1 && ko < k1)) { m1 = o.x; k1 = ko; en = fabsf(o.w); }
+                }
+                if (!p.pass_last && in_range) p.partial[grow] = make_float4(m1, m2, __int_as_float(k1), bad ? __uint_as_float(__float_as_uint(en) | 0x80000000u) : en);
+            }
+            const float need = 2.f * (p.cA * BOUND_UP * xn * en + p.cB * (BOUND_UP * en * en + xn * xn));
+            const bool certified = ((m2 - m1) > need) && (xn < 1.0e18f) && !bad;   // NaN -> false
             const uint32_t rs = it % RES_RING, phr = (it / RES_RING) & 1u;
             wait_t(BAR_RE + rs, phr ^ 1u, 3, rec);
             int code = -2;
-            if (in_range) {
+            if (in_range && p.pass_last) {
                 code = certified ? k1 : -1;
                 if (certified) p.embed_ind[grow] = (int64_t)k1;
             }
@@ -813,7 +860,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
         for (uint32_t it = 0; it < n_iter; ++it) {
             const int64_t t = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
             const uint32_t rs = it % RES_RING, phr = (it / RES_RING) & 1u;
-            wait_t(BAR_RF + rs, phr, 0, rec);
+            wait_r(BAR_RF + rs, phr, 0, rec);
             const float4* xt = reinterpret_cast<const float4*>(p.x) + (size_t)t * TILE_M * RQ + my_off;
             float4* qt = p.quantize ? reinterpret_cast<float4*>(p.quantize) + (size_t)t * TILE_M * RQ + my_off : nullptr;
             const int* cs = codes_s + rs * TILE_M + ow * 16 + half;
@@ -901,9 +948,15 @@ inline int tc_num_sms() {
 }
 
 inline bool tc_shape_ok(int dim, int n_embed) { return dim == tc::TC_D && (n_embed == 256 || n_embed == 512); }
+// larger codebooks run the same kernel once per 512-code slice (operand image = K / 512 sub-images)
+constexpr int TC_SLICE = 512;
+inline bool tc_sliced_ok(int dim, int n_embed) {
+    return dim == tc::TC_D && n_embed > TC_SLICE && n_embed % TC_SLICE == 0 && n_embed <= 16384;
+}
+inline bool tc_any_ok(int dim, int n_embed) { return tc_shape_ok(dim, n_embed) || tc_sliced_ok(dim, n_embed); }
 
 inline bool tc_supported(const RowLayout& L, const float* x, int dim, int n_embed) {
-    if (!tc_shape_ok(dim, n_embed) || L.n_rows < 1) return false;
+    if (!tc_any_ok(dim, n_embed) || L.n_rows < 1) return false;
     if (getenv("VQB200_DISABLE_TC")) return false;
     if (L.col_stride != 1 || L.row_stride != dim) return false;                 // contiguous rows only (for now)
     if (L.n_rows > L.rows_per_image && L.image_stride != L.rows_per_image * dim) return false;
@@ -955,27 +1008,41 @@ inline int tc_forward(const float* x, const RowLayout& L, int dim, int n_embed, 
                       unsigned long long* prof = nullptr, int nsplit = 0, int* grid_out = nullptr) {
     if (nsplit != 1 && nsplit != 3) nsplit = tc_nsplit();
     (void)dim;
-    tc::Params prm;
-    prm.x = x; prm.n_rows = L.n_rows; prm.K = n_embed; prm.image = cb.tc; prm.cbT = cb.cbT;
-    prm.quantize = quantize; prm.embed_ind = embed_ind; prm.diff_acc = diff_acc;
-    prm.stat_sums = sums; prm.stat_counts = counts;
-    prm.flagged_count = sc.flagged_count; prm.flagged_rows = sc.flagged_rows; prm.dbg_scores = dbg_scores;
-    prm.prof = prof;
-    { const char* e = getenv("VQB200_DBG_SKIP"); prm.dbg_skip = e ? atoi(e) : 0; }
-    prm.cA = tc::bound_cA(nsplit); prm.cB = tc::BOUND_CB;
-    const bool dbg = dbg_scores || prof;           // diagnostics live in a separate instantiation
     static const bool pair = [] { const char* e = getenv("VQB200_TC_CTA2"); return e ? atoi(e) != 0 : true; }();
     static const bool pair1 = [] { const char* e = getenv("VQB200_TC_CTA2_BF16"); return e ? atoi(e) != 0 : false; }();
-    const bool use_pair = n_embed == 512 && (nsplit == 3 ? pair : pair1);
+    const bool sliced = tc_sliced_ok(dim, n_embed);
+    const int K_launch = sliced ? TC_SLICE : n_embed;
+    const int n_slices = sliced ? n_embed / TC_SLICE : 1;
+    const bool use_pair = K_launch == 512 && (nsplit == 3 ? pair : pair1);
     if (grid_out) *grid_out = tc_grid(L.n_rows, use_pair);
-    if (nsplit == 3) {
-        if (pair && n_embed == 512)                // CTA pairs: half the operand image per CTA -> double-buffered A and x
-            return dbg ? tc_launch<3, 2, 2, true, true>(prm, st) : tc_launch<3, 2, 2, false, true>(prm, st);
-        return dbg ? tc_launch<3, 1, 1, true, false>(prm, st) : tc_launch<3, 1, 1, false, false>(prm, st);
+    const bool dbg = dbg_scores || prof;           // diagnostics live in a separate instantiation
+    if (sliced && (dbg || !sc.partial)) return 1;
+    for (int sl = 0; sl < n_slices; ++sl) {
+        tc::Params prm;
+        prm.x = x; prm.n_rows = L.n_rows; prm.K = K_launch;
+        prm.image = cb.tc + (size_t)sl * tc::image_bytes(TC_SLICE); prm.cbT = cb.cbT;
+        prm.quantize = quantize; prm.embed_ind = embed_ind; prm.diff_acc = diff_acc;
+        prm.stat_sums = sums; prm.stat_counts = counts;
+        prm.flagged_count = sc.flagged_count; prm.flagged_rows = sc.flagged_rows; prm.dbg_scores = dbg_scores;
+        prm.prof = prof;
+        { const char* e = getenv("VQB200_DBG_SKIP"); prm.dbg_skip = e ? atoi(e) : 0; }
+        prm.cA = tc::bound_cA(nsplit); prm.cB = tc::BOUND_CB;
+        prm.code_base = sl * TC_SLICE; prm.partial = sliced ? sc.partial : nullptr;
+        prm.pass_first = sl == 0; prm.pass_last = sl == n_slices - 1;
+        int rc;
+        if (nsplit == 3) {
+            if (pair && K_launch == 512)           // CTA pairs: half the operand image per CTA -> double-buffered A and x
+                rc = dbg ? tc_launch<3, 2, 2, true, true>(prm, st) : tc_launch<3, 2, 2, false, true>(prm, st);
+            else
+                rc = dbg ? tc_launch<3, 1, 1, true, false>(prm, st) : tc_launch<3, 1, 1, false, false>(prm, st);
+        } else if (pair1 && K_launch == 512) {
+            rc = dbg ? tc_launch<1, 2, 3, true, true>(prm, st) : tc_launch<1, 2, 3, false, true>(prm, st);
+        } else {
+            rc = dbg ? tc_launch<1, 2, 2, true, false>(prm, st) : tc_launch<1, 2, 2, false, false>(prm, st);
+        }
+        if (rc) return rc;
     }
-    if (pair1 && n_embed == 512)
-        return dbg ? tc_launch<1, 2, 3, true, true>(prm, st) : tc_launch<1, 2, 3, false, true>(prm, st);
-    return dbg ? tc_launch<1, 2, 2, true, false>(prm, st) : tc_launch<1, 2, 2, false, false>(prm, st);
+    return 0;
 }
 
 }  // namespace vqb200

@@ -49,8 +49,9 @@ bool layout_ok(int64_t n_rows, int32_t dim, int64_t rpi, int64_t img_stride, int
 
 int prepare_codebook(const float* d_embed, int dim, int n_embed, void* d_codebook, cudaStream_t st) {
     CodebookImage cb = codebook_view(d_codebook, dim, n_embed);
-    if (tc_shape_ok(dim, n_embed)) {              // one launch: transpose + norms + tensor-core operand image
-        k_prepare64<<<n_embed / PREP_CODES, 256, 0, st>>>(d_embed, cb.cbT, cb.ee, cb.tc, n_embed, tc::bound_cA(3),
+    if (tc_any_ok(dim, n_embed)) {                // one launch: transpose + norms + tensor-core operand image(s)
+        k_prepare64<<<n_embed / PREP_CODES, 256, 0, st>>>(d_embed, cb.cbT, cb.ee, cb.tc, n_embed,
+                                                           tc_sliced_ok(dim, n_embed) ? TC_SLICE : 0, tc::bound_cA(3),
                                                            tc::bound_cA(1), tc::BOUND_CB);
         VQ_LAUNCH_CHECK();
         return VQB200_OK;
@@ -74,7 +75,7 @@ int forward_impl(const float* d_x, const RowLayout& L, int dim, int n_embed, con
                  float* dbg_scores = nullptr, int64_t scratch_rows = -1, unsigned long long* prof = nullptr) {
     if (scratch_rows < 0) scratch_rows = total_rows;
     CodebookImage cb = codebook_view(const_cast<void*>(d_codebook), dim, n_embed);
-    ForwardScratch sc = scratch_view(d_scratch, scratch_rows);
+    ForwardScratch sc = scratch_view(d_scratch, scratch_rows, dim, n_embed);
     float* sums = d_stats;
     float* counts = d_stats ? d_stats + (size_t)n_embed * dim : nullptr;
     const double inv = total_rows > 0 ? 1.0 / ((double)total_rows * (double)dim)
@@ -355,7 +356,7 @@ int vqb200_debug_tc_scores(const float* d_x, int64_t n_rows, int32_t dim, int32_
                           VQB200_ENGINE_TCGEN05, true, false, n_rows, st, d_scores);
     if (rc) return rc;
     if (d_flagged_count)
-        VQ_CUDA(cudaMemcpyAsync(d_flagged_count, scratch_view(d_scratch, n_rows).flagged_count, sizeof(int),
+        VQ_CUDA(cudaMemcpyAsync(d_flagged_count, scratch_view(d_scratch, n_rows, dim, n_embed).flagged_count, sizeof(int),
                                 cudaMemcpyDeviceToDevice, st));
     return VQB200_OK;
 }
@@ -387,7 +388,7 @@ int vqb200_debug_tc_kernel(const float* d_x, int64_t n_rows, int32_t dim, int32_
     RowLayout L{n_rows, n_rows, 0, dim, 1};
     if (!tc_supported(L, d_x, dim, n_embed)) return VQB200_EUNSUPPORTED;
     CodebookImage cb = codebook_view(const_cast<void*>(d_codebook), dim, n_embed);
-    ForwardScratch sc = scratch_view(d_scratch, n_rows);
+    ForwardScratch sc = scratch_view(d_scratch, n_rows, dim, n_embed);
     int rc = tc_forward(d_x, L, dim, n_embed, cb, d_quantize, d_embed_ind, sc, sc.diff_acc, nullptr, nullptr, nullptr,
                         (cudaStream_t)stream, nullptr, engine == VQB200_ENGINE_TCGEN05_BF16 ? 1 : 3);
     g_launches.fetch_add(1);
