@@ -551,6 +551,27 @@ __global__ void k_backward(const float* __restrict__ x, RowLayout L, int D,
     }
 }
 
+// dense rows, D % 4 == 0, 16-byte aligned pointers: 128-bit accesses, one 64-bit division per thread and trip
+// (grad = grad_q + c (x - e[ind]); three streams of N*D*4 bytes -> HBM-bound)
+__global__ void __launch_bounds__(256)
+k_backward_dense(const float4* __restrict__ x, int64_t n_vec /* N*D/4 */, int vec_per_row, const int64_t* __restrict__ embed_ind,
+                 const float4* __restrict__ cbT, const float4* __restrict__ grad_q, const float* __restrict__ grad_diff,
+                 float4* __restrict__ grad_x, double two_over_count) {
+    const float c = grad_diff ? (float)(two_over_count * (double)grad_diff[0]) : 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 g = grad_q ? __ldcs(grad_q + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c != 0.f) {
+            const int64_t n = i / vec_per_row;
+            const int v = (int)(i - n * vec_per_row);
+            const float4 xv = __ldcs(x + i);
+            const float4 q = __ldg(cbT + (size_t)embed_ind[n] * vec_per_row + v);
+            g.x = fmaf(c, xv.x - q.x, g.x); g.y = fmaf(c, xv.y - q.y, g.y);
+            g.z = fmaf(c, xv.z - q.z, g.z); g.w = fmaf(c, xv.w - q.w, g.w);
+        }
+        __stcs(grad_x + i, g);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // embed_code (vqvae.py:77-78): contiguous [N, D] gather
 // ------------------------------------------------------------------------------------------------

@@ -324,6 +324,19 @@ int vqb200_quantize_backward(const float* d_x, const int64_t* d_embed_ind, const
     RowLayout L{n_rows, rows_per_image, image_stride, row_stride, col_stride};
     CodebookImage cb = codebook_view(const_cast<void*>(d_codebook), dim, n_embed);
     int64_t total = n_rows * (int64_t)dim;
+    const bool dense = col_stride == 1 && row_stride == dim && (n_rows <= rows_per_image || image_stride == rows_per_image * (int64_t)dim) &&
+                       dim % 4 == 0 && ((reinterpret_cast<uintptr_t>(d_x) | reinterpret_cast<uintptr_t>(d_grad_x) |
+                                         reinterpret_cast<uintptr_t>(d_grad_quantize)) & 15u) == 0;
+    if (dense) {
+        const int64_t n_vec = total / 4;
+        int blocks = (int)std::min<int64_t>((n_vec + 255) / 256, (int64_t)tc_num_sms() * 32);
+        k_backward_dense<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<const float4*>(d_x), n_vec, dim / 4, d_embed_ind, reinterpret_cast<const float4*>(cb.cbT),
+            reinterpret_cast<const float4*>(d_grad_quantize), d_grad_diff, reinterpret_cast<float4*>(d_grad_x),
+            2.0 / (double)total);
+        VQ_LAUNCH_CHECK();
+        return VQB200_OK;
+    }
     int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
     k_backward<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_x, L, dim, d_embed_ind, cb.cbT, d_grad_quantize,
                                                           d_grad_diff, d_grad_x, 2.0 / (double)total);
