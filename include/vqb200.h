@@ -113,13 +113,16 @@ int vqb200_ema_update_p2p(const void* const* h_stats_ptrs, void* const* h_flag_p
  *   vqb200_codebook_prepare(d_embed) + vqb200_quantize_forward(...) and, when `ema` != 0 and d_stats != NULL,
  *   vqb200_ema_update on the statistics of this call (single-process training).  With several ranks the caller
  *   passes ema = 0, all-reduces d_stats (vqvae.py:58-59) and calls vqb200_ema_update itself.
- * d_cluster_size / d_embed_avg are only touched when the EMA runs.                                    */
+ * d_cluster_size / d_embed_avg are only touched when the EMA runs.
+ * d_x_dense (may be NULL): n_rows*dim floats of scratch.  With it, NCHW-physical rows (unit row stride, the
+ * permute(0,2,3,1) view of vqvae.py:227,235; whole 128-row tiles per image) are consumed IN PLACE by the tensor-core
+ * kernel in training mode too: its converters write the dense copy the code-statistics kernel gathers from.     */
 int vqb200_quantize_step(const float* d_x, int64_t n_rows, int32_t dim, int32_t n_embed,
                          int64_t rows_per_image, int64_t image_stride, int64_t row_stride, int64_t col_stride,
                          float* d_embed, float* d_cluster_size, float* d_embed_avg, void* d_codebook,
                          float* d_quantize, int64_t* d_embed_ind, float* d_diff, float* d_stats,
-                         void* d_scratch, int32_t engine, int32_t ema, float decay, float one_minus_decay,
-                         float eps, void* stream);
+                         void* d_scratch, float* d_x_dense, int32_t engine, int32_t ema, float decay,
+                         float one_minus_decay, float eps, void* stream);
 
 /* Re-pack between a strided row layout (same layout arguments as vqb200_quantize_forward; e.g. the NCHW-physical
  * permute(0,2,3,1) view VQVAE.encode passes, vqvae.py:227,235) and dense [n_rows, dim] rows, coalesced on both sides.

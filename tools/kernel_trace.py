@@ -11,6 +11,7 @@ import vq_vae_2_pytorch_b200 as vq  # noqa: E402
 
 engine = sys.argv[1] if len(sys.argv) > 1 else "auto"
 dist = sys.argv[2] if len(sys.argv) > 2 else "clustered"
+layout = sys.argv[3] if len(sys.argv) > 3 else "dense"
 B, H, W, D, K = 128, 64, 64, 64, 512
 N = B * H * W
 import os
@@ -32,7 +33,10 @@ for i in range(3):
         x = embed0.t()[pick] + 0.1 * torch.randn(N, D, device=dev, generator=g)
     else:
         x = torch.randn(N, D, device=dev, generator=g)
-    xs.append(x.reshape(B, H, W, D).contiguous())
+    x = x.reshape(B, H, W, D).contiguous()
+    if layout == "nchw":
+        x = x.permute(0, 3, 1, 2).contiguous().permute(0, 2, 3, 1)
+    xs.append(x)
 if dist == "clustered":
     q.cluster_size.data.fill_(float(world * N) / K)
     q.embed_avg.data.copy_(embed0 * (float(world * N) / K))

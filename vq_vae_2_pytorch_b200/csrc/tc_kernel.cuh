@@ -21,6 +21,7 @@
 //   WG3: fp32->bf16 converters | WG4: w16 bulk-copy producer, w17 MMA issuer + TMEM owner (w18-19 idle).
 #pragma once
 #include <cuda_bf16.h>
+#include <cudaTypedefs.h>   // CUtensorMap, PFN_cuTensorMapEncodeTiled (resolved at run time: no link-time libcuda dependency)
 
 #include "common.cuh"
 
@@ -37,7 +38,7 @@ constexpr int THREADS = 768;        // 6 warpgroups; register budgets re-balance
 // producer, then the converters (their latency serialises with the MMAs while A is single-buffered), then
 // the output warps; the two epilogue groups have slack and take what is left.
 constexpr int W_EPI0 = 0, W_EPI1 = 4, W_OUT = 8, W_CONV = 16, W_PROD = 20, W_MMA = 21;
-constexpr int NORM_RING = 8;
+constexpr int NORM_RING = 4;        // converters run at most 3 tiles ahead of the certificate (A stages + TMEM buffers bound the lead)
 constexpr int RES_RING = 2;
 #ifndef VQB200_RELAX_NS
 #define VQB200_RELAX_NS 0    /* measured: 200 ns polling costs 3 us per launch (late wake-ups outweigh the freed issue slots) */
@@ -101,6 +102,11 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 __device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
+}
+// 3-D tiled TMA load (tensor map in kernel parameter space): box -> shared memory, completion on an mbarrier
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, int c0, int c1, int c2, uint32_t bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;"
+                 ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar), "l"(policy) : "memory");
 }
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
     uint64_t p;
@@ -472,6 +478,7 @@ struct Plan {
 };
 
 struct Params {
+    alignas(64) CUtensorMap tmap;    // NCHW only: x as a 3-D tensor [image][dim][row-in-image], box = 128 rows x 64 dims
     const float* x;
     int64_t n_rows;
     int K;
@@ -491,6 +498,10 @@ struct Params {
     // codebooks larger than the resident operand image (K > 512): one launch per 512-code slice.  Scores of a row are
     // comparable across slices (same row offset, per-code error terms), so the running (m1, m2, winner, ||e_winner||) is
     // carried in `partial` (one float4 per row); only the last slice certifies and writes outputs.
+    // NCHW-physical input (kernel template flag NCHW): element (n, d) of x / quantize at
+    //   (n / rpi) * img_stride + d * col_stride + (n % rpi), rpi % 128 == 0 (a tile never straddles two images)
+    int64_t rpi, img_stride, col_stride;
+    float* x_dense;                  // NCHW only, may be null: dense [N][64] copy of x for the statistics kernel
     int code_base;                   // global index of this launch's first code
     float4* partial;                 // may be null (single launch)
     int pass_first, pass_last;
@@ -509,8 +520,8 @@ enum BarId { BAR_B = 0, BAR_XF = 1, BAR_XE = 5, BAR_AF = 9, BAR_AE = 13, BAR_TF 
 // holds only half of the codebook operand image (the B rows of its half of every 256-code unit).  That halves the
 // image's shared-memory footprint (144 KB -> 72 KB at K = 512), which is what pays for double-buffered A and x
 // stages, and halves the operand bandwidth each SM's tensor core draws from shared memory.
-template <int NSPLIT, int AS, int XS, bool DBG, bool CTA2>
-__global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
+template <int NSPLIT, int AS, int XS, bool DBG, bool CTA2, bool NCHW = false>
+__global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const __grid_constant__ Params p) {
     using P = Plan<NSPLIT, AS, XS, CTA2>;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -563,7 +574,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
     // ---- one-time setup -----------------------------------------------------------------------------
     if (threadIdx.x == 0) {
         mbar_init(bar(BAR_B), 1);
-        for (int s = 0; s < XS; ++s) { mbar_init(bar(BAR_XF + s), 1); mbar_init(bar(BAR_XE + s), 4); }
+        for (int s = 0; s < XS; ++s) { mbar_init(bar(BAR_XF + s), 1); mbar_init(bar(BAR_XE + s), NCHW ? 12 : 4); }   // converters (+ output warps: NCHW reads x from the stage)
         for (int s = 0; s < AS; ++s) { mbar_init(bar(BAR_AF + s), PAIR_THREADS); mbar_init(bar(BAR_AE + s), 1); }
         for (int s = 0; s < NBUF; ++s) { mbar_init(bar(BAR_TF + s), 1); mbar_init(bar(BAR_TE + s), PAIR_THREADS); }
         mbar_init(bar(BAR_PB), 1);
@@ -619,7 +630,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
                 const uint32_t rows = (uint32_t)max((int64_t)0, min((int64_t)TILE_M, p.n_rows - r0));
                 const uint32_t bytes = rows * TC_D * 4u;
                 mbar_expect_tx(bar(BAR_XF + s), bytes);
-                if (bytes) bulk_g2s_hint(sX + s * P::X_STAGE, p.x + r0 * TC_D, bytes, bar(BAR_XF + s), keep);
+                if (NCHW) {                      // one tiled TMA load: box [64 dims][128 rows] -> the stage holds x^T [d][row]
+                    // (64 separate 512-byte bulk copies cost ~140 cycles each in the TMA unit: 126 us per launch)
+                    if (bytes) tma_load_3d(sX + s * P::X_STAGE, &p.tmap, (int)(r0 % p.rpi), 0, (int)(r0 / p.rpi), bar(BAR_XF + s), keep);
+                } else if (bytes) bulk_g2s_hint(sX + s * P::X_STAGE, p.x + r0 * TC_D, bytes, bar(BAR_XF + s), keep);
             }
             if (DBG && prof) flush(PF_PROD_WAIT_XE, 0);
         }
@@ -681,6 +695,41 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
             unsigned char* am = ah + (P::A_STAGE - 4096u);
             const long long tc0 = (DBG && prof && rec) ? clock64() : 0;
             float my_sq = 1.f;
+            if (NCHW) {
+                // the stage holds x^T [d][row]: thread = row (conflict-free 128-byte reads per dim), all 64 components pass
+                // through this thread, so the row norm needs no shuffles
+                if (!(DBG && (p.dbg_skip & 2))) {
+                    const int r = cw * 32 + lane;
+                    const float* xr = reinterpret_cast<const float*>(xs) + r;
+                    float4* xd = p.x_dense ? reinterpret_cast<float4*>(p.x_dense + (t * TILE_M + r) * TC_D) : nullptr;
+                    float sq = 0.f;
+#pragma unroll 2
+                    for (int c = 0; c < 8; ++c) {         // 8 dims -> one 16-byte chunk of the K-major operand row
+                        float v[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] = xr[(c * 8 + j) * TILE_M];
+                        const uint32_t p01 = pack_bf16(v[0], v[1]), p23 = pack_bf16(v[2], v[3]);
+                        const uint32_t p45 = pack_bf16(v[4], v[5]), p67 = pack_bf16(v[6], v[7]);
+                        const uint32_t off = sw128_off((uint32_t)r, (uint32_t)c * 8);
+                        *reinterpret_cast<uint4*>(ah + off) = make_uint4(p01, p23, p45, p67);
+                        if (NSPLIT == 3) {
+                            const uint32_t pk[4] = {p01, p23, p45, p67};
+                            uint32_t lo[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                lo[j] = pack_bf16(v[2 * j] - __uint_as_float(pk[j] << 16), v[2 * j + 1] - __uint_as_float(pk[j] & 0xFFFF0000u));
+                            *reinterpret_cast<uint4*>(al + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) sq = fmaf(v[j], v[j], sq);
+                        if (xd) {                         // dense copy for the statistics kernel (merged into full sectors in L2)
+                            __stcg(xd + 2 * c, make_float4(v[0], v[1], v[2], v[3]));
+                            __stcg(xd + 2 * c + 1, make_float4(v[4], v[5], v[6], v[7]));
+                        }
+                    }
+                    my_sq = sq;
+                }
+            } else
             if (!(DBG && (p.dbg_skip & 2))) {
 #pragma unroll 1
                 for (int g4 = 0; g4 < 4; ++g4) {          // 4 row pairs per trip
@@ -720,7 +769,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
             }
             const long long tc1 = (DBG && prof && rec) ? clock64() : 0;
             {
-                const int r = cw * 32 + 2 * q4 + half;
+                const int r = NCHW ? cw * 32 + lane : cw * 32 + 2 * q4 + half;
                 const float nx = sqrtf(my_sq);
                 float o1, o2, o3;
                 split3(my_sq * 1.001953125f, o1, o2, o3);            // off_i = ||x||^2 (1 + 2^-9)
@@ -861,6 +910,43 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const Params p) {
             const int64_t t = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
             const uint32_t rs = it % RES_RING, phr = (it / RES_RING) & 1u;
             wait_r(BAR_RF + rs, phr, 0, rec);
+            if (NCHW) {
+                // NCHW-physical quantize: lanes = 32 consecutive rows at a fixed dim (128-byte coalesced stores); warp ow
+                // takes row group ow & 3 and the dims [32 (ow >> 2), +32).  x comes from the shared-memory stage (x^T
+                // [d][row], kept until the output warps release it), the code row is gathered per lane with all 8 loads
+                // in flight: one L2 round trip per tile.
+                const uint32_t sx = it % XS;
+                if (!(DBG && (p.dbg_skip & 1))) {
+                    const int r = (ow & 3) * 32 + lane, d0 = (ow >> 2) * 32;
+                    const int k = codes_s[rs * TILE_M + r];
+                    if (k >= 0) {
+                        const int64_t n0 = t * TILE_M;
+                        const int64_t base = (n0 / p.rpi) * p.img_stride + (n0 % p.rpi) + r + (int64_t)d0 * p.col_stride;
+                        float* og = p.quantize ? p.quantize + base : nullptr;
+                        const float* xsr = reinterpret_cast<const float*>(sm + P::off_x(K) + sx * P::X_STAGE) + d0 * TILE_M + r;
+                        const float4* q4p = reinterpret_cast<const float4*>(p.cbT + (size_t)k * TC_D + d0);
+                        float4 qq[8];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) qq[c] = __ldg(q4p + c);
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const float qv[4] = {qq[c].x, qq[c].y, qq[c].z, qq[c].w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float xv = xsr[(c * 4 + j) * TILE_M];
+                                const float dl = qv[j] - xv;
+                                dacc = fmaf(dl, dl, dacc);
+                                if (og) __stcs(og + (int64_t)(c * 4 + j) * p.col_stride, xv + dl);
+                                if (p.stat_sums) red_add_f32(p.stat_sums + (size_t)k * TC_D + d0 + c * 4 + j, xv);
+                            }
+                        }
+                        if (p.stat_sums && d0 == 0) red_add_f32(p.stat_counts + k, 1.0f);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(bar(BAR_RE + rs)); mbar_arrive(bar(BAR_XE + sx)); }
+                continue;
+            }
             const float4* xt = reinterpret_cast<const float4*>(p.x) + (size_t)t * TILE_M * RQ + my_off;
             float4* qt = p.quantize ? reinterpret_cast<float4*>(p.quantize) + (size_t)t * TILE_M * RQ + my_off : nullptr;
             const int* cs = codes_s + rs * TILE_M + ow * 16 + half;
@@ -955,12 +1041,43 @@ inline bool tc_sliced_ok(int dim, int n_embed) {
 }
 inline bool tc_any_ok(int dim, int n_embed) { return tc_shape_ok(dim, n_embed) || tc_sliced_ok(dim, n_embed); }
 
+// NCHW-physical rows (the permute(0,2,3,1) view of vqvae.py:227,235) the kernel consumes in place: unit row stride, whole
+// 128-row tiles inside one image, 16-byte aligned 512-byte pieces
+inline bool tc_layout_nchw(const RowLayout& L, const float* x, int dim) {
+    if (L.row_stride != 1 || L.col_stride < L.rows_per_image || dim != tc::TC_D) return false;
+    if (L.rows_per_image % tc::TILE_M != 0 || L.n_rows % L.rows_per_image != 0) return false;
+    if ((L.col_stride & 3) != 0 || (L.image_stride & 3) != 0) return false;
+    if (L.n_rows > L.rows_per_image && L.image_stride < (int64_t)dim * L.col_stride) return false;
+    return (reinterpret_cast<uintptr_t>(x) & 15u) == 0;
+}
+inline bool tc_layout_dense(const RowLayout& L, const float* x, int dim) {
+    if (L.col_stride != 1 || L.row_stride != dim) return false;
+    if (L.n_rows > L.rows_per_image && L.image_stride != L.rows_per_image * dim) return false;
+    return (reinterpret_cast<uintptr_t>(x) & 15u) == 0;                          // bulk copies need 16-byte alignment
+}
 inline bool tc_supported(const RowLayout& L, const float* x, int dim, int n_embed) {
     if (!tc_any_ok(dim, n_embed) || L.n_rows < 1) return false;
     if (getenv("VQB200_DISABLE_TC")) return false;
-    if (L.col_stride != 1 || L.row_stride != dim) return false;                 // contiguous rows only (for now)
-    if (L.n_rows > L.rows_per_image && L.image_stride != L.rows_per_image * dim) return false;
-    return (reinterpret_cast<uintptr_t>(x) & 15u) == 0;                          // bulk copies need 16-byte alignment
+    return tc_layout_dense(L, x, dim) || tc_layout_nchw(L, x, dim);
+}
+
+// x (NCHW-physical) as a 3-D tensor map: dims (fastest first) row-in-image, dim, image; box = one 128-row x 64-dim tile
+inline int tc_encode_tmap(CUtensorMap* tm, const float* x, const RowLayout& L, int dim) {
+    static PFN_cuTensorMapEncodeTiled encode = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess) f = nullptr;
+        return reinterpret_cast<PFN_cuTensorMapEncodeTiled>(f);
+    }();
+    if (!encode) return 1;
+    const cuuint64_t n_img = (cuuint64_t)(L.n_rows / L.rows_per_image);
+    const cuuint64_t img_stride = n_img > 1 ? (cuuint64_t)L.image_stride : (cuuint64_t)dim * (cuuint64_t)L.col_stride;
+    cuuint64_t gdim[3] = {(cuuint64_t)L.rows_per_image, (cuuint64_t)dim, n_img};
+    cuuint64_t gstr[2] = {(cuuint64_t)L.col_stride * 4u, img_stride * 4u};
+    cuuint32_t box[3] = {(cuuint32_t)tc::TILE_M, (cuuint32_t)dim, 1u};
+    cuuint32_t estr[3] = {1u, 1u, 1u};
+    return encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS;
 }
 
 // CTAs the tensor-core kernel runs for n_rows rows (= number of private statistics tables it fills)
@@ -973,10 +1090,10 @@ inline int tc_grid(int64_t n_rows, bool pair) {
     return grid;
 }
 
-template <int NSPLIT, int AS, int XS, bool DBG, bool CTA2>
+template <int NSPLIT, int AS, int XS, bool DBG, bool CTA2, bool NCHW = false>
 inline int tc_launch(const tc::Params& prm, cudaStream_t st) {
     using P = tc::Plan<NSPLIT, AS, XS, CTA2>;
-    auto kern = tc::k_vq_tc<NSPLIT, AS, XS, DBG, CTA2>;
+    auto kern = tc::k_vq_tc<NSPLIT, AS, XS, DBG, CTA2, NCHW>;
     const int smem = (int)P::total(prm.K);
     static int configured = 0;
     if (configured < smem) {
@@ -1005,8 +1122,10 @@ inline int tc_launch(const tc::Params& prm, cudaStream_t st) {
 inline int tc_forward(const float* x, const RowLayout& L, int dim, int n_embed, const CodebookImage& cb,
                       float* quantize, int64_t* embed_ind, const ForwardScratch& sc, double* diff_acc,
                       float* sums, float* counts, float* dbg_scores, cudaStream_t st,
-                      unsigned long long* prof = nullptr, int nsplit = 0, int* grid_out = nullptr) {
+                      unsigned long long* prof = nullptr, int nsplit = 0, int* grid_out = nullptr,
+                      float* x_dense = nullptr) {
     if (nsplit != 1 && nsplit != 3) nsplit = tc_nsplit();
+    const bool nchw = !tc_layout_dense(L, x, dim);
     (void)dim;
     static const bool pair = [] { const char* e = getenv("VQB200_TC_CTA2"); return e ? atoi(e) != 0 : true; }();
     static const bool pair1 = [] { const char* e = getenv("VQB200_TC_CTA2_BF16"); return e ? atoi(e) != 0 : false; }();
@@ -1017,8 +1136,13 @@ inline int tc_forward(const float* x, const RowLayout& L, int dim, int n_embed, 
     if (grid_out) *grid_out = tc_grid(L.n_rows, use_pair);
     const bool dbg = dbg_scores || prof;           // diagnostics live in a separate instantiation
     if (sliced && (dbg || !sc.partial)) return 1;
+    if (nchw && dbg) return 1;
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    if (nchw && tc_encode_tmap(&tmap, x, L, dim)) return 1;
     for (int sl = 0; sl < n_slices; ++sl) {
         tc::Params prm;
+        prm.tmap = tmap;
         prm.x = x; prm.n_rows = L.n_rows; prm.K = K_launch;
         prm.image = cb.tc + (size_t)sl * tc::image_bytes(TC_SLICE); prm.cbT = cb.cbT;
         prm.quantize = quantize; prm.embed_ind = embed_ind; prm.diff_acc = diff_acc;
@@ -1027,10 +1151,16 @@ inline int tc_forward(const float* x, const RowLayout& L, int dim, int n_embed, 
         prm.prof = prof;
         { const char* e = getenv("VQB200_DBG_SKIP"); prm.dbg_skip = e ? atoi(e) : 0; }
         prm.cA = tc::bound_cA(nsplit); prm.cB = tc::BOUND_CB;
+        prm.rpi = L.rows_per_image; prm.img_stride = L.image_stride; prm.col_stride = L.col_stride;
+        prm.x_dense = (nchw && sl == 0) ? x_dense : nullptr;
         prm.code_base = sl * TC_SLICE; prm.partial = sliced ? sc.partial : nullptr;
         prm.pass_first = sl == 0; prm.pass_last = sl == n_slices - 1;
         int rc;
-        if (nsplit == 3) {
+        if (nchw) {                                // x stages x3: the output warps read x from the stage too
+            if (nsplit == 3) rc = (pair && K_launch == 512) ? tc_launch<3, 1, 3, false, true, true>(prm, st) : tc_launch<3, 1, 1, false, false, true>(prm, st);
+            else rc = getenv("VQB200_DBG_SKIP") ? tc_launch<1, 2, 3, true, false, true>(prm, st)      // (diagnostics: role skipping)
+                                                : tc_launch<1, 2, 3, false, false, true>(prm, st);
+        } else if (nsplit == 3) {
             if (pair && K_launch == 512)           // CTA pairs: half the operand image per CTA -> double-buffered A and x
                 rc = dbg ? tc_launch<3, 2, 2, true, true>(prm, st) : tc_launch<3, 2, 2, false, true>(prm, st);
             else

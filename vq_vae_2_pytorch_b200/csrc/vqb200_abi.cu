@@ -72,7 +72,8 @@ int prepare_codebook(const float* d_embed, int dim, int n_embed, void* d_codeboo
 int forward_impl(const float* d_x, const RowLayout& L, int dim, int n_embed, const void* d_codebook,
                  float* d_quantize, int64_t* d_ind, float* d_diff, float* d_stats, void* d_scratch,
                  int engine, bool zero_first, bool finalize, int64_t total_rows, cudaStream_t st,
-                 float* dbg_scores = nullptr, int64_t scratch_rows = -1, unsigned long long* prof = nullptr) {
+                 float* dbg_scores = nullptr, int64_t scratch_rows = -1, unsigned long long* prof = nullptr,
+                 float* d_x_dense = nullptr) {
     if (scratch_rows < 0) scratch_rows = total_rows;
     CodebookImage cb = codebook_view(const_cast<void*>(d_codebook), dim, n_embed);
     ForwardScratch sc = scratch_view(d_scratch, scratch_rows, dim, n_embed);
@@ -91,6 +92,13 @@ int forward_impl(const float* d_x, const RowLayout& L, int dim, int n_embed, con
     // d_stats, no memset needed), else the gather kernels fall back to global atomics on a cleared d_stats
     const size_t cs_smem = code_stats_smem_bytes(dim, n_embed);
     const bool stats_kernel = d_stats && cs_smem <= 200 * 1024 && n_embed <= 65535;
+    // NCHW-physical rows consumed in place by the tensor-core kernel: the statistics kernel gathers rows by code, which
+    // only coalesces on dense rows, so training needs the dense copy the kernel's converters can write on the side
+    const bool nchw = use_tc && !tc_layout_dense(L, d_x, dim);
+    if (nchw && stats_kernel && !d_x_dense) {
+        if (engine == VQB200_ENGINE_TCGEN05 || engine == VQB200_ENGINE_TCGEN05_BF16) return VQB200_EUNSUPPORTED;
+        use_tc = false;
+    }
     if (zero_first) {
         VQ_CUDA(cudaMemsetAsync(sc.diff_acc, 0, 256, st));      // loss accumulator, flagged-row counter, ticket
         if (d_stats && (!stats_kernel || L.n_rows == 0)) VQ_CUDA(cudaMemsetAsync(d_stats, 0, vqb200_stats_bytes(dim, n_embed), st));
@@ -112,7 +120,7 @@ int forward_impl(const float* d_x, const RowLayout& L, int dim, int n_embed, con
             // tensor-core filter + fused output for certified rows; flagged rows -> exact SIMT fix-up (one launch:
             // re-score, gather / output / loss of those rows, loss finalisation)
             int rc = tc_forward(d_x, L, dim, n_embed, cb, d_quantize, d_ind, sc, d_diff ? sc.diff_acc : nullptr, sums,
-                                counts, dbg_scores, st, prof, nsplit);
+                                counts, dbg_scores, st, prof, nsplit, nullptr, (nchw && stats_kernel) ? d_x_dense : nullptr);
             g_launches.fetch_add(1);
             if (rc) return cuda_fail(cudaGetLastError());
             k_fixup<<<sms, AS_THREADS, gsmem, st>>>(d_x, L, dim, n_embed, cb.cbT, cb.ee, d_ind, d_quantize,
@@ -143,7 +151,10 @@ int forward_impl(const float* d_x, const RowLayout& L, int dim, int n_embed, con
             chunk = std::min<int64_t>(CS_CHUNK, std::max<int64_t>(256, (chunk + 31) / 32 * 32));
             int64_t n_chunks = (L.n_rows + chunk - 1) / chunk;
             int parts = (int)std::min<int64_t>(n_chunks, sms_cs);
-            k_code_stats<<<parts, CS_THREADS, cs_smem, st>>>(d_x, L, dim, n_embed, d_ind, sc.stat_partials, (int)chunk);
+            const bool from_dense = use_tc && nchw;
+            const RowLayout Ld{L.n_rows, L.n_rows, 0, dim, 1};
+            k_code_stats<<<parts, CS_THREADS, cs_smem, st>>>(from_dense ? d_x_dense : d_x, from_dense ? Ld : L, dim, n_embed,
+                                                             d_ind, sc.stat_partials, (int)chunk);
             VQ_LAUNCH_CHECK();
             // d_stats (+)= sum of the per-CTA tables: overwrite on the first call, accumulate on host-path continuation chunks
             const int nstat = n_embed * (dim + 1);
@@ -277,14 +288,23 @@ int vqb200_ema_update_p2p(const void* const* h_stats_ptrs, void* const* h_flag_p
 int vqb200_quantize_step(const float* d_x, int64_t n_rows, int32_t dim, int32_t n_embed, int64_t rows_per_image,
                          int64_t image_stride, int64_t row_stride, int64_t col_stride, float* d_embed,
                          float* d_cluster_size, float* d_embed_avg, void* d_codebook, float* d_quantize,
-                         int64_t* d_embed_ind, float* d_diff, float* d_stats, void* d_scratch, int32_t engine,
-                         int32_t ema, float decay, float one_minus_decay, float eps, void* stream) {
+                         int64_t* d_embed_ind, float* d_diff, float* d_stats, void* d_scratch, float* d_x_dense,
+                         int32_t engine, int32_t ema, float decay, float one_minus_decay, float eps, void* stream) {
     if (!d_embed) return VQB200_EINVAL;
     if (ema && d_stats && (!d_cluster_size || !d_embed_avg)) return VQB200_EINVAL;
     int rc = vqb200_codebook_prepare(d_embed, dim, n_embed, d_codebook, stream);
     if (rc) return rc;
-    rc = vqb200_quantize_forward(d_x, n_rows, dim, n_embed, rows_per_image, image_stride, row_stride, col_stride,
-                                 d_codebook, d_quantize, d_embed_ind, d_diff, d_stats, d_scratch, engine, stream);
+    if (!d_codebook || !d_scratch || dim <= 0 || n_embed <= 0 || n_rows < 0) return VQB200_EINVAL;
+    if (n_rows > 0 && (!d_x || !d_embed_ind)) return VQB200_EINVAL;
+    if (n_rows > (int64_t)INT32_MAX) return VQB200_EUNSUPPORTED;
+    if (engine < VQB200_ENGINE_AUTO || engine > VQB200_ENGINE_TCGEN05_BF16) return VQB200_EINVAL;
+    if (n_rows > 0 && !layout_ok(n_rows, dim, rows_per_image, image_stride, row_stride, col_stride))
+        return VQB200_EUNSUPPORTED;
+    {
+        RowLayout L{n_rows, rows_per_image > 0 ? rows_per_image : 1, image_stride, row_stride, col_stride};
+        rc = forward_impl(d_x, L, dim, n_embed, d_codebook, d_quantize, d_embed_ind, d_diff, d_stats, d_scratch, engine, true,
+                          true, n_rows, (cudaStream_t)stream, nullptr, -1, nullptr, d_x_dense);
+    }
     if (rc || !ema || !d_stats) return rc;
     return vqb200_ema_update(d_stats, d_cluster_size, d_embed_avg, d_embed, dim, n_embed, decay, one_minus_decay, eps,
                              nullptr, stream);

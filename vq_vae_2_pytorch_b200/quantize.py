@@ -285,17 +285,22 @@ class Quantize(nn.Module):
                 peer["step"] += 1
                 peer["parity"] = peer["step"] & 1
                 stats = peer["stats"][peer["parity"]]
-        # Strided rows (the NCHW-physical permute(0,2,3,1) view of vqvae.py:227,235) on a shape the tcgen05 engine
-        # covers: re-pack to dense rows (coalesced CUDA transpose), run the tensor-core engine, re-pack `quantize` back to
-        # the input's strides (vqvae.py:73).  ~3x the HBM traffic of the dense case, still ~7x faster than the SIMT engine.
-        x_run, q_run, lay_run = x, quantize, lay
-        if (col != 1 or (n > 1 and row != self.dim)) and n > 0 and self.engine != "simt" and \
-                lib.vqb200_tc_supported(ws["stats"].data_ptr(), n, self.dim, self.n_embed, n, 0, self.dim, 1):
-            x_run = torch.empty((n, self.dim), dtype=torch.float32, device=dev)
-            _native.check(lib.vqb200_repack_rows(x.data_ptr(), x_run.data_ptr(), n, self.dim, rpi, img, row, col, 1, stream),
-                          "vqb200_repack_rows")
-            q_run = torch.empty_like(x_run) if want_quantize else None
-            lay_run = (n, n, 0, self.dim, 1)
+        x_run, q_run, lay_run, x_dense = x, quantize, lay, None
+        strided = n > 0 and (col != 1 or (n > 1 and row != self.dim))
+        if strided and self.engine != "simt":
+            if lib.vqb200_tc_supported(x.data_ptr(), n, self.dim, self.n_embed, rpi, img, row, col):
+                # NCHW-physical rows the tensor-core kernel consumes in place; in training mode its converters also write
+                # the dense copy of x the code-statistics kernel gathers from
+                if self.training:
+                    x_dense = torch.empty((n, self.dim), dtype=torch.float32, device=dev)
+            elif lib.vqb200_tc_supported(ws["stats"].data_ptr(), n, self.dim, self.n_embed, n, 0, self.dim, 1):
+                # other strided layouts on a covered shape: re-pack to dense rows (coalesced CUDA transpose), run the
+                # tensor-core engine, re-pack `quantize` back to the input's strides (vqvae.py:73)
+                x_run = torch.empty((n, self.dim), dtype=torch.float32, device=dev)
+                _native.check(lib.vqb200_repack_rows(x.data_ptr(), x_run.data_ptr(), n, self.dim, rpi, img, row, col, 1, stream),
+                              "vqb200_repack_rows")
+                q_run = torch.empty_like(x_run) if want_quantize else None
+                lay_run = (n, n, 0, self.dim, 1)
         eng = self._pick_engine(x_run, lay_run)
         n, rpi, img, row, col = lay_run
         fused_ema = self.training and dist_fn.get_world_size() == 1
@@ -305,8 +310,8 @@ class Quantize(nn.Module):
             x_run.data_ptr(), n, self.dim, self.n_embed, rpi, img, row, col, self.embed.data_ptr(),
             self.cluster_size.data_ptr(), self.embed_avg.data_ptr(), image.data_ptr(),
             q_run.data_ptr() if q_run is not None else None, ind.data_ptr(), diff.data_ptr(),
-            stats.data_ptr() if stats is not None else None, ws["scratch"].data_ptr(), eng,
-            1 if fused_ema else 0, float(self.decay), float(1 - self.decay), float(self.eps), stream),
+            stats.data_ptr() if stats is not None else None, ws["scratch"].data_ptr(),
+            x_dense.data_ptr() if x_dense is not None else None, eng, 1 if fused_ema else 0, float(self.decay), float(1 - self.decay), float(self.eps), stream),
             "vqb200_quantize_step")                                                           # vqvae.py:43-73
         if q_run is not quantize:             # dense result -> the input's strides
             _native.check(lib.vqb200_repack_rows(q_run.data_ptr(), quantize.data_ptr(), lay[0], self.dim, lay[1], lay[2],
