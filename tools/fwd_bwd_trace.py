@@ -5,7 +5,9 @@ dev="cuda:0"; D,K,N=64,512,128*64*64
 torch.manual_seed(0)
 q=vq.Quantize(D,K).to(dev).train()
 pick=torch.randint(0,K,(N,),device=dev)
-x=(q.embed.t()[pick]+0.1*torch.randn(N,D,device=dev)).reshape(128,64,64,D).contiguous().requires_grad_(True)
+x=(q.embed.t()[pick]+0.1*torch.randn(N,D,device=dev)).reshape(128,64,64,D).contiguous()
+if len(sys.argv)>1 and sys.argv[1]=='nchw': x=x.permute(0,3,1,2).contiguous().permute(0,2,3,1)
+x=x.requires_grad_(True)
 def step():
     quant,diff,ind=q(x)
     (quant.sum()+0.25*diff).backward()

@@ -572,6 +572,39 @@ k_backward_dense(const float4* __restrict__ x, int64_t n_vec /* N*D/4 */, int ve
     }
 }
 
+// NCHW-physical rows (unit row stride; rows_per_image, col_stride, image_stride multiples of 4; 16-byte aligned): a
+// thread owns 4 consecutive rows and walks a chunk of dims, so x / grad_q / grad_x move as row-coalesced float4 and
+// the four code rows are read sequentially (L1-resident sectors).  grid = (ceil(N / 1024), dim chunks).
+__global__ void __launch_bounds__(256)
+k_backward_nchw(const float* __restrict__ x, RowLayout L, int D, int dims_per_block, const int64_t* __restrict__ embed_ind,
+                const float* __restrict__ cbT, const float* __restrict__ grad_q, const float* __restrict__ grad_diff,
+                float* __restrict__ grad_x, double two_over_count) {
+    const float c = grad_diff ? (float)(two_over_count * (double)grad_diff[0]) : 0.f;
+    const int64_t n = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
+    if (n >= L.n_rows) return;
+    const int64_t img = n / L.rows_per_image, r = n - img * L.rows_per_image;
+    const int64_t base = img * L.image_stride + r;
+    const int d0 = blockIdx.y * dims_per_block, d1 = min(D, d0 + dims_per_block);
+    int64_t k[4] = {0, 0, 0, 0};
+    if (c != 0.f) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) k[j] = embed_ind[n + j] * D;
+    }
+#pragma unroll 4
+    for (int d = d0; d < d1; ++d) {
+        const int64_t off = base + (int64_t)d * L.col_stride;
+        float4 g = grad_q ? __ldcs(reinterpret_cast<const float4*>(grad_q + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c != 0.f) {
+            const float4 xv = __ldcs(reinterpret_cast<const float4*>(x + off));
+            g.x = fmaf(c, xv.x - __ldg(cbT + k[0] + d), g.x);
+            g.y = fmaf(c, xv.y - __ldg(cbT + k[1] + d), g.y);
+            g.z = fmaf(c, xv.z - __ldg(cbT + k[2] + d), g.z);
+            g.w = fmaf(c, xv.w - __ldg(cbT + k[3] + d), g.w);
+        }
+        __stcs(reinterpret_cast<float4*>(grad_x + off), g);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // embed_code (vqvae.py:77-78): contiguous [N, D] gather
 // ------------------------------------------------------------------------------------------------

@@ -357,6 +357,18 @@ int vqb200_quantize_backward(const float* d_x, const int64_t* d_embed_ind, const
         VQ_LAUNCH_CHECK();
         return VQB200_OK;
     }
+    const bool nchw = row_stride == 1 && col_stride >= rows_per_image && rows_per_image % 4 == 0 && col_stride % 4 == 0 &&
+                      image_stride % 4 == 0 && n_rows % 4 == 0 &&
+                      ((reinterpret_cast<uintptr_t>(d_x) | reinterpret_cast<uintptr_t>(d_grad_x) |
+                        reinterpret_cast<uintptr_t>(d_grad_quantize)) & 15u) == 0;
+    if (nchw) {
+        const int dims_per_block = dim >= 64 ? 16 : dim;
+        dim3 grid((unsigned)((n_rows / 4 + 255) / 256), (unsigned)((dim + dims_per_block - 1) / dims_per_block));
+        k_backward_nchw<<<grid, 256, 0, (cudaStream_t)stream>>>(d_x, L, dim, dims_per_block, d_embed_ind, cb.cbT, d_grad_quantize,
+                                                                 d_grad_diff, d_grad_x, 2.0 / (double)total);
+        VQ_LAUNCH_CHECK();
+        return VQB200_OK;
+    }
     int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
     k_backward<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_x, L, dim, d_embed_ind, cb.cbT, d_grad_quantize,
                                                           d_grad_diff, d_grad_x, 2.0 / (double)total);
