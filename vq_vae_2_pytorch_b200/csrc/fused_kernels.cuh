@@ -20,6 +20,8 @@ __global__ void __launch_bounds__(256) k_prepare64(const float* __restrict__ emb
                                                     float cA, float cA1, float cB) {
     __shared__ float es[PREP_CODES][65];
     __shared__ float e2s[PREP_CODES];
+    pdl_wait();
+    pdl_trigger();
     const int k0 = blockIdx.x * PREP_CODES, tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
     for (int i = tid; i < 64 * PREP_CODES; i += 256) {          // 32-byte segments of 8 consecutive codes per dim
         const int d = i >> 3, j = i & 7;
@@ -97,6 +99,8 @@ __global__ void __launch_bounds__(256) k_ema64(const float* __restrict__ stats, 
     __shared__ float part[8];
     __shared__ float n_s;
     __shared__ unsigned int last_s;
+    pdl_wait();
+    pdl_trigger();
     const int k0 = blockIdx.x * PREP_CODES, tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
     if (P2P) {
         if (blockIdx.x == 0 && tid < peers.world) {             // my statistics (written by the previous kernels) are complete
@@ -193,6 +197,8 @@ k_fixup(const float* __restrict__ x, RowLayout L, int D, int K, const float* __r
     extern __shared__ float gs_tile[];
     __shared__ float warp_part[AS_THREADS / 32];
     __shared__ unsigned int last_s;
+    pdl_wait();
+    pdl_trigger();
     const int64_t total = (int64_t)(*row_count);
     float acc = 0.f;
     for (int64_t n0 = (int64_t)blockIdx.x * AS_BM; n0 < total; n0 += (int64_t)gridDim.x * AS_BM) {

@@ -265,8 +265,10 @@ k_code_stats(const float* __restrict__ x, RowLayout L, int D, int K, const int64
     unsigned short* scode = code + CS_CHUNK;                  // [CS_CHUNK] code at sorted position p
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = CS_THREADS / 32;
 
+    pdl_trigger();
     for (int i = tid; i < K * D; i += CS_THREADS) table[i] = 0.f;
     for (int i = tid; i < K; i += CS_THREADS) cnt_total[i] = 0;
+    pdl_wait();                                               // (the shared-memory table is cleared while the upstream kernel drains)
     const int64_t n_chunks = (L.n_rows + chunk - 1) / chunk;
     const bool fast = (D == 64 && L.col_stride == 1 && (reinterpret_cast<uintptr_t>(x) & 7u) == 0 && (L.row_stride & 1) == 0 &&
                        (L.image_stride & 1) == 0);
@@ -396,6 +398,8 @@ constexpr int FOLD_Y = 16;
 __global__ void __launch_bounds__(32 * FOLD_Y)
 k_stats_fold(const float* __restrict__ partials, int n_parts, int n, float* __restrict__ stats, int accumulate) {
     __shared__ float part[FOLD_Y][4][32];
+    pdl_wait();
+    pdl_trigger();
     const int col = threadIdx.x, y = threadIdx.y;
     const int i0 = blockIdx.x * 128;
     float s[4] = {0.f, 0.f, 0.f, 0.f};

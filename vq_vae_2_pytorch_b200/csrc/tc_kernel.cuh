@@ -540,6 +540,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const __grid_constant__ Pa
     uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(sm + P::off_bars(K) + BAR_COUNT * 8);
     auto bar = [&](int id) { return bars + 8u * (uint32_t)id; };
 
+    pdl_wait();                                   // codebook image / previous step's outputs complete (no-op without PDL)
+    pdl_trigger();
     const int64_t n_tiles = (p.n_rows + TILE_M - 1) / TILE_M;
     const uint32_t crank = CTA2 ? cluster_ctarank() : 0u;
     // both CTAs of a pair run the same number of trips (the pair's second tile may lie past the end on the last one)
@@ -1101,20 +1103,19 @@ inline int tc_launch(const tc::Params& prm, cudaStream_t st) {
         configured = smem;
     }
     const int grid = tc_grid(prm.n_rows, CTA2);
-    if (!CTA2) {
-        kern<<<grid, tc::THREADS, smem, st>>>(prm);
-        return cudaGetLastError() != cudaSuccess;
-    }
+    if (!CTA2) return launch_pdl(kern, dim3((unsigned)grid), dim3(tc::THREADS), (size_t)smem, st, prm) != cudaSuccess;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(tc::THREADS);
     cfg.dynamicSmemBytes = (size_t)smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 2;
     return cudaLaunchKernelEx(&cfg, kern, prm) != cudaSuccess;
 }
 
