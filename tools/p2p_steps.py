@@ -41,5 +41,23 @@ for r in range(world):
         dist.barrier()
     if r == rank:
         print(f"[rank {rank}] us/step: " + " ".join(f"{v:.0f}" for v in d) + f" | mean {sum(d) / len(d):.1f}", flush=True)
+pw = q._ws.get(dev, {}).get("peer")
+if pw is not None and os.environ.get("VQB200_P2P_TRACE"):
+    n_al = (len(pw["stats"][0]) + 63) // 64 * 64
+    fl = pw["buf"][2 * n_al:2 * n_al + 128].view(torch.int32).cpu().tolist()
+    recs = []
+    for par in (0, 1):
+        for i in range(14):
+            t0, w, st = fl[64 * par + 8 + 4 * i: 64 * par + 8 + 4 * i + 3]
+            if st:
+                recs.append((st & 0xffffffff, t0 & 0xffffffff, w))
+    recs.sort()
+    out = []
+    for (s0, a, w0), (s1, b, w1) in zip(recs[:-1], recs[1:]):
+        out.append(f"{s1}:{((b - a) & 0xffffffff) / 1e3:.0f}/{w1 / 1e3:.0f}")
+    for r in range(world):
+        dist.barrier()
+        if r == rank:
+            print(f"[rank {rank}] step:dt_us/wait_us " + " ".join(out[-20:]), flush=True)
 if world > 1:
     dist.destroy_process_group()

@@ -30,7 +30,7 @@ def build(force=False, verbose=False):
     if not force and not is_stale():
         return LIB
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
-           "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v" if verbose else "-O3",
+           "-Xcompiler", "-fPIC", "-shared"] + (["-DVQB200_P2P_TRACE"] if os.environ.get("VQB200_P2P_TRACE") else []) + [ "-Xptxas", "-v" if verbose else "-O3",
            "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lcuda"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:

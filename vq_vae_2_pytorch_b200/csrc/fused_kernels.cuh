@@ -107,11 +107,22 @@ __global__ void __launch_bounds__(256) k_ema64(const float* __restrict__ stats, 
             __threadfence_system();
             st_release_sys(peers.flags[tid] + peers.rank, peers.step);
         }
+#ifdef VQB200_P2P_TRACE
+        unsigned long long t0 = 0, t1 = 0;
+        if (blockIdx.x == 0 && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+#endif
         if (tid < peers.world) {
             const unsigned int* f = peers.flags[peers.rank] + tid;
             while ((int)(ld_acquire_sys(f) - peers.step) < 0) __nanosleep(64);
         }
         __syncthreads();
+#ifdef VQB200_P2P_TRACE
+        if (blockIdx.x == 0 && tid == 0) {       // ring of (kernel start, wait) in the unused tail of my flag array
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            unsigned int* ring = peers.flags[peers.rank] + 8 + ((peers.step >> 1) % 14) * 4;
+            ring[0] = (unsigned int)(t0 & 0xffffffffu); ring[1] = (unsigned int)(t1 - t0); ring[2] = peers.step;
+        }
+#endif
 
     }
     // counts / sums of this step (summed over the ranks in rank order) -> shared memory, all peer loads in one phase
