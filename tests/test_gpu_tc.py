@@ -278,3 +278,40 @@ def test_tc_sliced_codebook_matches_simt(K, engine):
             assert col_rel_err(a.embed_avg.cpu().numpy(), b.embed_avg.cpu().numpy()) <= REL_TOL
             assert torch.allclose(a.cluster_size, b.cluster_size, rtol=1e-5, atol=1e-7)
         b.load_state_dict(a.state_dict())
+
+
+@pytest.mark.parametrize("engine", ["tcgen05", "tcgen05_bf16"])
+@pytest.mark.parametrize("K", [256, 512, 1024])
+@pytest.mark.parametrize("shape,train", [((4, 64, 32, 32), True), ((1, 64, 128, 128), True), ((37, 64, 16, 8), False)])
+def test_tc_nchw_in_place_variants(shape, train, K, engine):
+    """The NCHW-physical kernel variant (3-D TMA tensor-map tile loads, x^T stage, row-per-thread converters, row-coalesced
+    output) over both filters (incl. the CTA-pair split kernel), the sliced codebook, training (dense copy for the
+    statistics) and eval, many trips per CTA and a single image."""
+    torch.manual_seed(61)
+    B, D, H, W = shape
+    a = vq.Quantize(D, K, engine=engine).to(DEV).train(train)
+    b = vq.Quantize(D, K, engine="simt").to(DEV).train(train)
+    b.load_state_dict(a.state_dict())
+    embed0 = a.embed.clone()
+    n = B * H * W
+    pick = torch.randint(0, K, (n,), device=DEV)
+    dense = embed0.t()[pick] + 0.25 * torch.randn(n, D, device=DEV)
+    x = dense.reshape(B, H, W, D).permute(0, 3, 1, 2).contiguous().permute(0, 2, 3, 1)     # NCHW-physical
+    lib = _native.load()
+    from vq_vae_2_pytorch_b200 import row_layout
+    lay = row_layout(x)
+    assert lib.vqb200_tc_supported(_native.ptr(x), lay[0], D, K, lay[1], lay[2], lay[3], lay[4]) == 1   # consumed in place
+    for step in range(2 if train else 1):
+        embed_before = b.embed.cpu().numpy().copy()
+        qa, da, ia = a(x)
+        qb, db, ib = b(x)
+        assert qa.stride() == x.stride()
+        _, nbad, _ = tie_tolerant_index_mismatches(x.cpu().numpy(), embed_before, ia.cpu().numpy(), ib.cpu().numpy())
+        assert nbad == 0
+        if int((ia != ib).sum()) == 0:
+            assert torch.equal(qa, qb)
+            assert abs(float(da) - float(db)) <= 1e-5 * abs(float(db))
+            if train:
+                assert col_rel_err(a.embed_avg.cpu().numpy(), b.embed_avg.cpu().numpy()) <= REL_TOL
+                assert torch.allclose(a.cluster_size, b.cluster_size, rtol=1e-5, atol=1e-7)
+        b.load_state_dict(a.state_dict())
