@@ -47,6 +47,13 @@ def test_argument_validation_without_a_gpu():
     assert lib.vqb200_quantize_forward(None, 10, 64, 512, 10, 0, 64, 1, None, None, None, None, None, None, 0, None) == -1
     assert lib.vqb200_ema_update(None, None, None, None, 64, 512, 0.99, 0.01, 1e-5, None, None) == -1
     assert lib.vqb200_embed_code(None, 5, None, 64, 512, None, None, None) == -1
+    # the single-call step, the re-pack kernels and the fused peer-to-peer EMA reject bad arguments before touching CUDA
+    assert lib.vqb200_quantize_step(None, 10, 64, 512, 10, 0, 64, 1, None, None, None, None, None, None, None, None, None, None,
+                                    0, 1, 0.99, 0.01, 1e-5, None) == -1
+    assert lib.vqb200_repack_rows(None, None, 10, 64, 10, 0, 64, 1, 1, None) == -1
+    assert lib.vqb200_repack_rows(None, None, 0, 64, 1, 0, 64, 1, 1, None) == 0            # nothing to do
+    assert lib.vqb200_ema_update_p2p(None, None, 0, 2, 1, None, None, None, 64, 512, 0.99, 0.01, 1e-5, None, None) == -1
+    assert lib.vqb200_debug_tc_kernel(None, 10, 64, 512, None, None, None, None, 2, None) == -1
 
 
 def test_row_layout_detection():
