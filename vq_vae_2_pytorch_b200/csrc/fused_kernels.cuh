@@ -17,12 +17,14 @@ constexpr int PREP_CODES = 8;      // codes per block of the image / EMA kernels
 __global__ void __launch_bounds__(256) k_prepare64(const float* __restrict__ embed, float* __restrict__ cbT,
                                                     float* __restrict__ ee, unsigned char* __restrict__ img, int K,
                                                     int slice_codes /* 0: one image of K codes; else sub-images of that many */,
-                                                    float cA, float cA1, float cB) {
+                                                    float cA, float cA1, float cB,
+                                                    unsigned int* __restrict__ zero_header /* may be null: 256-byte forward scratch header */) {
     __shared__ float es[PREP_CODES][65];
     __shared__ float e2s[PREP_CODES];
     pdl_wait();
     pdl_trigger();
     const int k0 = blockIdx.x * PREP_CODES, tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    if (zero_header && blockIdx.x == 0 && tid < 64) zero_header[tid] = 0u;   // loss accumulator, flagged-row counter, ticket (saves a memset node)
     for (int i = tid; i < 64 * PREP_CODES; i += 256) {          // 32-byte segments of 8 consecutive codes per dim
         const int d = i >> 3, j = i & 7;
         es[j][d] = embed[(size_t)d * K + k0 + j];

@@ -47,12 +47,15 @@ bool layout_ok(int64_t n_rows, int32_t dim, int64_t rpi, int64_t img_stride, int
     return col_stride == 1 || row_stride == 1;
 }
 
-int prepare_codebook(const float* d_embed, int dim, int n_embed, void* d_codebook, cudaStream_t st) {
+int prepare_codebook(const float* d_embed, int dim, int n_embed, void* d_codebook, cudaStream_t st,
+                     unsigned int* zero_header = nullptr, bool* header_zeroed = nullptr) {
+    if (header_zeroed) *header_zeroed = false;
     CodebookImage cb = codebook_view(d_codebook, dim, n_embed);
     if (tc_any_ok(dim, n_embed)) {                // one launch: transpose + norms + tensor-core operand image(s)
         VQ_CUDA(launch_pdl(k_prepare64, dim3(n_embed / PREP_CODES), dim3(256), 0, st, d_embed, cb.cbT, cb.ee, cb.tc, n_embed,
-                           tc_sliced_ok(dim, n_embed) ? TC_SLICE : 0, tc::bound_cA(3), tc::bound_cA(1), tc::BOUND_CB));
+                           tc_sliced_ok(dim, n_embed) ? TC_SLICE : 0, tc::bound_cA(3), tc::bound_cA(1), tc::BOUND_CB, zero_header));
         g_launches.fetch_add(1);
+        if (header_zeroed) *header_zeroed = zero_header != nullptr;
         return VQB200_OK;
     }
     dim3 grid((n_embed + 31) / 32, (dim + 31) / 32), block(32, 8);
@@ -98,15 +101,17 @@ int forward_impl(const float* d_x, const RowLayout& L, int dim, int n_embed, con
         if (engine == VQB200_ENGINE_TCGEN05 || engine == VQB200_ENGINE_TCGEN05_BF16) return VQB200_EUNSUPPORTED;
         use_tc = false;
     }
+    bool header_zeroed = false;
+    if (zero_first && d_stats && (!stats_kernel || L.n_rows == 0)) VQ_CUDA(cudaMemsetAsync(d_stats, 0, vqb200_stats_bytes(dim, n_embed), st));
+    if (d_embed_prepare) {                        // ahead of the main kernel, adjacent launches (PDL); also clears the scratch header
+        int rc = prepare_codebook(d_embed_prepare, dim, n_embed, const_cast<void*>(d_codebook), st,
+                                  zero_first ? reinterpret_cast<unsigned int*>(sc.diff_acc) : nullptr, &header_zeroed);
+        if (rc) return rc;
+    }
     if (zero_first) {
-        VQ_CUDA(cudaMemsetAsync(sc.diff_acc, 0, 256, st));      // loss accumulator, flagged-row counter, ticket
-        if (d_stats && (!stats_kernel || L.n_rows == 0)) VQ_CUDA(cudaMemsetAsync(d_stats, 0, vqb200_stats_bytes(dim, n_embed), st));
+        if (!header_zeroed) VQ_CUDA(cudaMemsetAsync(sc.diff_acc, 0, 256, st));      // loss accumulator, flagged-row counter, ticket
     } else if (use_tc) {
         VQ_CUDA(cudaMemsetAsync(sc.flagged_count, 0, sizeof(int), st));
-    }
-    if (d_embed_prepare) {                        // after the memsets, so that prepare -> main kernel stay adjacent launches (PDL)
-        int rc = prepare_codebook(d_embed_prepare, dim, n_embed, const_cast<void*>(d_codebook), st);
-        if (rc) return rc;
     }
     if (L.n_rows > 0) {
         const int nsplit = engine == VQB200_ENGINE_TCGEN05_BF16 ? 1 : (engine == VQB200_ENGINE_TCGEN05 ? 3 : 0);
