@@ -34,6 +34,24 @@ def _collapse(sizes, strides):
 
 
 _LAYOUT_CACHE = {}
+_TC_CACHE = {}
+_ENV_PIN_FILTER = bool(os.environ.get("VQB200_TC_SPLIT"))      # read once: the filter precision is pinned by the environment
+
+
+def _tc_supported(lib, ptr, lay, dim, n_embed):
+    """vqb200_tc_supported, memoised on (layout, shape, pointer alignment)."""
+    key = (lay, dim, n_embed, ptr & 15)
+    hit = _TC_CACHE.get(key)
+    if hit is None:
+        n, rpi, img, row, col = lay
+        hit = bool(lib.vqb200_tc_supported(ptr, n, dim, n_embed, rpi, img, row, col))
+        if len(_TC_CACHE) < 4096:
+            _TC_CACHE[key] = hit
+    return hit
+
+
+def _raw_stream(dev):
+    return torch._C._cuda_getCurrentRawStream(dev.index)
 
 
 def row_layout(x: torch.Tensor):
@@ -214,11 +232,9 @@ class Quantize(nn.Module):
     FLAG_SAMPLE_EVERY = 8                     # bf16-mode calls between two read-backs of the counter
 
     def _pick_engine(self, x, lay):
-        if self.engine != "auto" or os.environ.get("VQB200_TC_SPLIT"):
+        if self.engine != "auto" or _ENV_PIN_FILTER:
             return _native.ENGINES[self.engine]
-        lib = _native.load()
-        n, rpi, img, row, col = lay
-        if not lib.vqb200_tc_supported(_native.ptr(x), n, self.dim, self.n_embed, rpi, img, row, col):
+        if lay[0] == 0 or not _tc_supported(_native.load(), x.data_ptr(), lay, self.dim, self.n_embed):
             return _native.ENGINE_AUTO
         f = self._filter
         pend = f["pending"]
@@ -245,7 +261,7 @@ class Quantize(nn.Module):
             host = ws["flag_host"] = torch.zeros(1, dtype=torch.int32).pin_memory()
         host.copy_(ws["scratch"][16:20].view(torch.int32), non_blocking=True)   # vqb200.h: int32 at byte 16 of the scratch
         ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream(dev))
+        ev.record()
         f["pending"] = (ev, host, n, "bf16" if eng == _native.ENGINE_TCGEN05_BF16 else "split")
 
     def _check_input(self, x):
@@ -272,14 +288,15 @@ class Quantize(nn.Module):
         image = ws["image"]
         if keep_image:                        # backward gathers from the codebook this forward used
             image = torch.empty_like(ws["image"])
-        stream = torch.cuda.current_stream(dev).cuda_stream
         if torch.cuda.current_device() != dev.index:
             torch.cuda.set_device(dev)        # kernels launch on the input's device
+        stream = _raw_stream(dev)
         quantize = torch.empty_strided(x.shape, x.stride(), dtype=torch.float32, device=dev) if want_quantize else None
         ind = torch.empty(x.shape[:-1], dtype=torch.int64, device=dev)
         diff = torch.empty((), dtype=torch.float32, device=dev)
         stats = ws["stats"] if self.training else None
-        if self.training and dist_fn.get_world_size() > 1:
+        world = dist_fn.get_world_size() if self.training else 1
+        if world > 1:
             peer = self._peer_workspace(ws, dev)
             if peer is not None:              # this step's statistics go straight into peer-mapped memory
                 peer["step"] += 1
@@ -288,12 +305,12 @@ class Quantize(nn.Module):
         x_run, q_run, lay_run, x_dense = x, quantize, lay, None
         strided = n > 0 and (col != 1 or (n > 1 and row != self.dim))
         if strided and self.engine != "simt":
-            if lib.vqb200_tc_supported(x.data_ptr(), n, self.dim, self.n_embed, rpi, img, row, col):
+            if _tc_supported(lib, x.data_ptr(), lay, self.dim, self.n_embed):
                 # NCHW-physical rows the tensor-core kernel consumes in place; in training mode its converters also write
                 # the dense copy of x the code-statistics kernel gathers from
                 if self.training:
                     x_dense = torch.empty((n, self.dim), dtype=torch.float32, device=dev)
-            elif lib.vqb200_tc_supported(ws["stats"].data_ptr(), n, self.dim, self.n_embed, n, 0, self.dim, 1):
+            elif _tc_supported(lib, 0, (n, n, 0, self.dim, 1), self.dim, self.n_embed):
                 # other strided layouts on a covered shape: re-pack to dense rows (coalesced CUDA transpose), run the
                 # tensor-core engine, re-pack `quantize` back to the input's strides (vqvae.py:73)
                 x_run = torch.empty((n, self.dim), dtype=torch.float32, device=dev)
@@ -303,7 +320,7 @@ class Quantize(nn.Module):
                 lay_run = (n, n, 0, self.dim, 1)
         eng = self._pick_engine(x_run, lay_run)
         n, rpi, img, row, col = lay_run
-        fused_ema = self.training and dist_fn.get_world_size() == 1
+        fused_ema = self.training and world == 1
         # the codebook image is re-derived from `embed` on every call: external writes to the buffer
         # (load_state_dict, .data.copy_, DDP buffer broadcast) can never leave it stale
         _native.check(lib.vqb200_quantize_step(
