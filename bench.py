@@ -75,48 +75,104 @@ def time_cpu_port(steps, warmup):
     return CPU_SAMPLE_ROWS / med, med
 
 
+_NVML_POLL = r"""
+import sys, time
+import pynvml as nv
+nv.nvmlInit()
+key = sys.argv[1]
+try:
+    h = nv.nvmlDeviceGetHandleByUUID(key if key.startswith("GPU-") else "GPU-" + key) if len(key) > 8 else nv.nvmlDeviceGetHandleByIndex(int(key))
+except Exception:
+    h = nv.nvmlDeviceGetHandleByIndex(0)
+smax = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+bits = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+        ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap))
+print("ready", smax, flush=True)
+out = sys.stdout
+while True:
+    t = time.time()
+    sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+    out.write("%.6f %d %s\n" % (t, sm, ",".join(n for n, b in bits if r & b) or "-"))
+    out.flush()
+    time.sleep(0.0005)
+"""
+
+
 class ClockSampler:
+    """SM clock and throttle reasons of one GPU, polled from a SEPARATE process (no GIL contention with the issuing
+    loop) through NVML about once per millisecond, every sample time-stamped; stop(t0, t1) keeps the samples taken
+    inside the timed region [t0, t1] (host clock, both ends after a device synchronize).  Falls back to
+    `nvidia-smi -lms` (the recipe's clocks line) when NVML is not importable."""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index, uuid=None):
+        self.index, self.uuid, self.rows, self.proc, self.mode, self.smax = index, uuid, [], None, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+            self.proc = subprocess.Popen([sys.executable, "-c", _NVML_POLL, str(self.uuid or self.index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
+            head = self.proc.stdout.readline().split()
+            if len(head) != 2 or head[0] != "ready":
+                raise RuntimeError("nvml poller did not start")
+            self.smax, self.mode = float(head[1]), "nvml"
         except Exception:
-            self.proc = None
+            try:
+                if self.proc:
+                    self.proc.kill()
+                self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
+                                              "--format=csv,noheader,nounits", "-lms", "100"],
+                                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                self.mode = "nvidia-smi"
+            except Exception:
+                self.proc = None
+                return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append(line)
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["clock sampler unavailable"]}
+        time.sleep(0.02 if self.mode == "nvml" else 0.15)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, smax, reasons = [], [], set()
-        for r in self.rows:
+        rows = list(self.rows)
+        window = "timed region" if (self.mode == "nvml" and t0 is not None) else "sampler lifetime"
+        if self.mode == "nvml" and t0 is not None:
+            inside = [ln for ln in rows if ln.split() and t0 <= float(ln.split()[0]) <= t1]
+            if len(inside) < 3:                  # very short timed region: take the loaded neighbourhood (warm-up .. roofline runs)
+                t0, t1, window = t0 - 0.05, t1 + 0.05, "timed region +-50 ms"
+        sm, smax, reasons, n_all = [], [], set(), 0
+        for line in rows:
             try:
-                sm.append(float(r[1])); smax.append(float(r[2]))
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
+                if self.mode == "nvml":
+                    ts, mhz, why = line.split()
+                    n_all += 1
+                    if t0 is not None and not (t0 <= float(ts) <= t1):
+                        continue
+                    sm.append(float(mhz)); smax.append(self.smax)
+                    reasons.update(w for w in why.split(",") if w != "-")
+                else:
+                    r = [c.strip() for c in line.split(",")]
+                    sm.append(float(r[1])); smax.append(float(r[2])); n_all += 1
+                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                        if v.lower().startswith("active"):
+                            reasons.add(name)
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": self.mode,
+                "window": window}
 
 
 def run_reference_arm(args, rank):
@@ -204,6 +260,13 @@ def main():
         else:
             q.embed_avg.data.copy_(embed0); q.cluster_size.data.zero_()
 
+    try:
+        gpu_uuid = str(torch.cuda.get_device_properties(dev).uuid)
+    except Exception:
+        gpu_uuid = None
+    sampler = ClockSampler(local_rank, gpu_uuid)
+    if rank == 0:
+        sampler.start()                       # before the warm-up: the poller is running long before the timed region
     reset()
     for i in range(warmup):
         step(i)
@@ -212,9 +275,7 @@ def main():
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    t_wall0 = time.time()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = lib.vqb200_launch_count()
     ev0.record()
@@ -225,10 +286,11 @@ def main():
     ev1.record()
     gpu_launches = int(lib.vqb200_launch_count() - launches0)
     torch.cuda.synchronize()
+    t_wall1 = time.time()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     elapsed_ms = ev0.elapsed_time(ev1)
     if world > 1:
         t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
