@@ -275,6 +275,15 @@ def main():
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    if world > 1:
+        # ranks leave the NCCL barrier hundreds of microseconds apart on the host; the step itself keeps them in lock-step
+        # (peer-memory flags), so the earliest starter would time the others' head start.  All ranks of the node share
+        # the host clock: agree on a start instant a few milliseconds ahead and spin until it.
+        t_go = torch.tensor([time.time() + 0.004], dtype=torch.float64, device=dev)
+        dist.broadcast(t_go, 0)
+        t_go = float(t_go.item())
+        while time.time() < t_go:
+            pass
     t_wall0 = time.time()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = lib.vqb200_launch_count()

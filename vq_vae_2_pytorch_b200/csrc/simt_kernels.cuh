@@ -332,15 +332,19 @@ k_code_stats(const float* __restrict__ x, RowLayout L, int D, int K, const int64
                         smem_add(t + 1, a1);
                     }
                 };
-                for (int p = my_begin; p < my_end; p += 16) {
-                    float2 v[16];
+                // software pipeline: two register batches of 8 rows; the loads of one batch are issued before the other is
+                // consumed, so a warp always has 8 .. 16 rows (2 .. 4 KB) in flight instead of draining to zero per trip
+                const float2* xl = reinterpret_cast<const float2*>(x) + lane;
+                auto load8 = [&](float2 (&v)[8], int p) {
 #pragma unroll
-                    for (int u = 0; u < 16; ++u) {
+                    for (int u = 0; u < 8; ++u) {
                         const int pp = p + u;
-                        v[u] = pp < my_end ? __ldcs(reinterpret_cast<const float2*>(x + order[pp]) + lane) : make_float2(0.f, 0.f);
+                        v[u] = pp < my_end ? __ldcs(reinterpret_cast<const float2*>(reinterpret_cast<const float*>(xl) + order[pp])) : make_float2(0.f, 0.f);
                     }
+                };
+                auto eat8 = [&](const float2 (&v)[8], int p) {
 #pragma unroll
-                    for (int u = 0; u < 16; ++u) {
+                    for (int u = 0; u < 8; ++u) {
                         const int cd = p + u < my_end ? (int)scode[p + u] : cur;      // warp-uniform
                         if (cd != cur) {
                             flush(cur);
@@ -350,6 +354,14 @@ k_code_stats(const float* __restrict__ x, RowLayout L, int D, int K, const int64
                         a0 += v[u].x;
                         a1 += v[u].y;
                     }
+                };
+                float2 va[8], vb[8];
+                load8(va, my_begin);
+                for (int p = my_begin; p < my_end; p += 16) {
+                    load8(vb, p + 8);
+                    eat8(va, p);
+                    load8(va, p + 16);
+                    eat8(vb, p + 8);
                 }
                 flush(cur);
             }
