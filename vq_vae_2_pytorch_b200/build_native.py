@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvqb200.so")
 SOURCES = ["vqb200_abi.cu"]
-HEADERS = ["common.cuh", "simt_kernels.cuh", "tc_kernel.cuh", "fused_kernels.cuh", os.path.join("..", "..", "include", "vqb200.h")]
+HEADERS = ["common.cuh", "simt_kernels.cuh", "tc_kernel.cuh", "tc_wide_kernel.cuh", "fused_kernels.cuh", os.path.join("..", "..", "include", "vqb200.h")]
 
 
 def nvcc_path():

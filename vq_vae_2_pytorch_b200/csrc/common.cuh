@@ -67,7 +67,9 @@ struct ForwardScratch {
     float* stat_partials;  // [STAT_PARTS][K*(D+1)] per-CTA statistics tables
 };
 constexpr int STAT_PARTS = 160;
-__host__ __device__ inline bool scratch_has_partial(int dim, int n_embed) { return dim == 64 && n_embed > 512; }
+__host__ __device__ inline bool scratch_has_partial(int dim, int n_embed) {
+    return (dim == 64 && n_embed > 512) || (dim == 128 && n_embed > 512) || (dim == 256 && n_embed > 256);   // sliced tensor-core launches
+}
 __host__ __device__ inline size_t forward_scratch_bytes(int64_t n_rows, int dim, int n_embed) {
     return 256 + align_up((size_t)n_rows * 4, 256) + (scratch_has_partial(dim, n_embed) ? align_up((size_t)n_rows * 16, 256) : 0) +
            (size_t)STAT_PARTS * n_embed * (dim + 1) * 4;

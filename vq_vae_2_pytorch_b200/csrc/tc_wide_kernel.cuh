@@ -1,0 +1,533 @@
+// tcgen05 assignment kernel for WIDE codes: dim = 64 * DB, DB = 2 or 4 (the D axis of BASELINE.json's cfg-5 sweep and the
+// D = 256 quantizers of vqvae_deep.py:252,257).  Same contract, certificate and epilogue as tc::k_vq_tc (tc_kernel.cuh);
+// what changes is the contraction: it runs over DB blocks of 64 dims, and neither a whole fp32 x tile (128 rows x D) nor
+// all bf16 A blocks of a tile fit in shared memory next to the codebook image.  So the loop order is BLOCK-outer,
+// UNIT-inner: all accumulator units of a tile are live in TMEM at once, every 64-dim block of x is staged (2-D TMA tensor
+// map, box = 128 rows x 64 dims), converted to one 16-KB bf16 A stage and multiplied against the resident operand image
+// of that block for every unit; the "misc" MMA (bias, row offset, error bound -- it needs the full row norm) goes LAST.
+//
+//   resident per CTA : eh blocks [DB][KL][64] bf16 (128 KB) + misc rows, KL = codes per launch (512 at D = 128, 256 at
+//                      D = 256); larger codebooks run one launch per KL-code slice with the running (best, runner-up,
+//                      winner) carried per row, exactly like the sliced mode of tc::k_vq_tc
+//   filter           : plain bf16 (cA = 7.9e-3); rows it cannot certify go to the exact fp32 fix-up (k_fixup)
+//   accumulation term: cB scales with the number of accumulated MMAs (BOUND_CB * DB)
+#pragma once
+#include "tc_kernel.cuh"
+
+namespace vqb200 {
+namespace tcw {
+using namespace tc;
+
+constexpr int AS = 2;                        // bf16 A stages (one 64-dim block of a 128-row tile each)
+constexpr uint32_t A_STAGE = 16384u, AM_STAGE = 4096u, X_STAGE = TILE_M * 64 * 4;
+
+__host__ __device__ inline size_t wimage_off_misc(int KL, int DB) { return (size_t)KL * 128 * DB; }
+__host__ __device__ inline size_t wimage_off_enorm(int KL, int DB) { return (size_t)KL * (128 * DB + 32); }
+__host__ __device__ inline size_t wimage_bytes(int KL, int DB) { return align_up((size_t)KL * (128 * DB + 36), 1024); }
+__host__ __device__ constexpr float bound_cB(int DB) { return BOUND_CB * (float)DB; }
+
+// operand image of the wide engine from cbT [K][D] / ee [K]: one thread per (code, 8-dim chunk)
+__global__ void __launch_bounds__(256) k_prepare_wide(const float* __restrict__ cbT, const float* __restrict__ ee,
+                                                       unsigned char* __restrict__ img, int K, int D, int KL, float cA1, float cB) {
+    pdl_wait();
+    pdl_trigger();
+    const int nch = D / 8, DB = D / 64;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= K * nch) return;
+    const int k = idx / nch, c = idx % nch, sl = k / KL, kl = k % KL;
+    unsigned char* base = img + (size_t)sl * wimage_bytes(KL, DB);
+    const float* e = cbT + (size_t)k * D + c * 8;
+    uint32_t hi[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) hi[j] = pack_bf16(-2.f * e[2 * j], -2.f * e[2 * j + 1]);
+    *reinterpret_cast<uint4*>(base + (size_t)(c >> 3) * KL * 128 + sw128_off((uint32_t)kl, (uint32_t)(c & 7) * 8)) =
+        make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    if (c == 0) {
+        const float e2 = ee[k];
+        float b1, b2, b3;
+        split3(e2, b1, b2, b3);
+        const float ne = sqrtf(e2);
+        const float t6 = -bf16_round(cA1 * ne * 1.0078125f);     // rounded up in magnitude
+        const float t7 = -bf16_round(cB * e2 * 1.0078125f);
+        unsigned char* m = base + wimage_off_misc(KL, DB);
+        *reinterpret_cast<uint4*>(m + sw32_chunk_off((uint32_t)kl, 0)) =
+            make_uint4(pack_bf16(b1, b2), pack_bf16(b3, 1.f), pack_bf16(1.f, 1.f), pack_bf16(t6, t7));
+        *reinterpret_cast<uint4*>(m + sw32_chunk_off((uint32_t)kl, 1)) = make_uint4(0, 0, 0, 0);
+        reinterpret_cast<float*>(base + wimage_off_enorm(KL, DB))[kl] = ne;
+    }
+}
+
+struct Plan {
+    int KL, DB, XS;
+    __host__ __device__ uint32_t off_bmisc() const { return (uint32_t)KL * 128u * (uint32_t)DB; }
+    __host__ __device__ uint32_t off_a() const { return off_bmisc() + (uint32_t)KL * 32u; }
+    __host__ __device__ uint32_t off_am() const { return off_a() + AS * A_STAGE; }
+    __host__ __device__ uint32_t off_x() const { return off_am() + 2u * AM_STAGE; }
+    __host__ __device__ uint32_t off_small() const { return off_x() + (uint32_t)XS * X_STAGE; }
+    __host__ __device__ uint32_t off_rownorm() const { return off_small() + (uint32_t)KL * 4u; }
+    __host__ __device__ uint32_t off_codes() const { return off_rownorm() + NORM_RING * TILE_M * 4u; }
+    __host__ __device__ uint32_t off_parts() const { return off_codes() + RES_RING * TILE_M * 4u; }
+    __host__ __device__ uint32_t off_bars() const { return off_parts() + 2u * TILE_M * 16u; }
+    __host__ __device__ uint32_t total() const { return off_bars() + 384u + 1024u /* base alignment slack */; }
+};
+
+struct WParams {
+    alignas(64) CUtensorMap tmap;    // x as a 2-D tensor [row][dim], box = 128 rows x 64 dims
+    const float* x;
+    int64_t n_rows;
+    int KL;                          // codes in this launch (256 or 512)
+    int K_total;                     // row pitch of dbg_scores
+    const unsigned char* image;      // this slice's operand image
+    const float* cbT;                // [K][D] fp32
+    float* quantize;                 // may be null
+    int64_t* embed_ind;
+    double* diff_acc;                // may be null
+    float* stat_sums;                // may be null (global-atomics statistics)
+    float* stat_counts;
+    int* flagged_count;
+    int* flagged_rows;
+    float* dbg_scores;               // DBG builds: [n_rows][K_total] dump of the tensor-core scores
+    float cA, cB;
+    int code_base;
+    float4* partial;                 // may be null (single launch)
+    int pass_first, pass_last;
+};
+
+enum WBar { WB_B = 0, WB_XF = 1, WB_XE = 5, WB_AF = 9, WB_AE = 11, WB_TF = 13, WB_TE = 17, WB_RF = 21, WB_RE = 23, WB_PF = 25,
+            WB_PE = 27, WB_COUNT = 29 };
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+                 ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar), "l"(policy) : "memory");
+}
+
+// four K = 16 MMAs of one 64-dim block into one accumulator unit (converged warp, one elected lane issues); the first one
+// overwrites the accumulator when acc0 == 0
+__device__ __forceinline__ void issue_block4(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t acc0) {
+#define VQW_KS(KS)                                                                           \
+    "add.u32 ta, %1, " KS ";\n\tadd.u32 tb, %2, " KS ";\n\t"                                   \
+    "mov.b64 da, {ta, %3};\n\tmov.b64 db, {tb, %3};\n\t"                                        \
+    "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, pt;\n\t"
+    asm volatile("{\n\t.reg .pred pa, pt, pe;\n\t.reg .b64 da, db;\n\t.reg .b32 ta, tb;\n\t"
+                 "elect.sync _|pe, 0xffffffff;\n\t"
+                 "setp.ne.b32 pa, %5, 0;\n\tsetp.eq.b32 pt, %4, %4;\n\t"
+                 "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+                 "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, pa;\n\t"
+                 VQW_KS("2") VQW_KS("4") VQW_KS("6") "}"
+                 :: "r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(DESC_HI_SW128), "r"(IDESC), "r"(acc0) : "memory");
+#undef VQW_KS
+}
+// the misc MMA (K = 16, 32-byte swizzle rows): accumulates bias, row offset and error bound onto the finished products
+__device__ __forceinline__ void issue_misc(uint32_t d_tmem, uint32_t am_lo, uint32_t bm_lo) {
+    asm volatile("{\n\t.reg .pred pt, pe;\n\t.reg .b64 da, db;\n\t"
+                 "elect.sync _|pe, 0xffffffff;\n\t"
+                 "setp.eq.b32 pt, %4, %4;\n\t"
+                 "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+                 "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, pt;\n\t}"
+                 :: "r"(d_tmem), "r"(am_lo), "r"(bm_lo), "r"(DESC_HI_SW32), "r"(IDESC) : "memory");
+}
+
+template <int DB, int XS, bool DBG>
+__global__ void __launch_bounds__(THREADS, 1) k_vq_tcw(const __grid_constant__ WParams p) {
+    constexpr int D = 64 * DB;
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    unsigned char* sm = smem_raw + (base - raw);
+    const int KL = p.KL;
+    const int U = KL / UNIT_N;                  // accumulator units per tile: 2 or 4
+    const Plan P{KL, DB, XS};
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    const uint32_t sB = base, sBm = base + P.off_bmisc(), sA = base + P.off_a(), sAm = base + P.off_am(), sX = base + P.off_x();
+    float* enorm_s = reinterpret_cast<float*>(sm + P.off_small());
+    float* rownorm_s = reinterpret_cast<float*>(sm + P.off_rownorm());
+    int* codes_s = reinterpret_cast<int*>(sm + P.off_codes());
+    float4* part_s = reinterpret_cast<float4*>(sm + P.off_parts());
+    const uint32_t bars = base + P.off_bars();
+    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(sm + P.off_bars() + WB_COUNT * 8);
+    auto bar = [&](int id) { return bars + 8u * (uint32_t)id; };
+
+    pdl_wait();
+    pdl_trigger();
+    const int64_t n_tiles = (p.n_rows + TILE_M - 1) / TILE_M;
+    const uint32_t n_iter = (int64_t)blockIdx.x < n_tiles ? (uint32_t)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar(WB_B), 1);
+        for (int s = 0; s < XS; ++s) { mbar_init(bar(WB_XF + s), 1); mbar_init(bar(WB_XE + s), 4); }
+        for (int s = 0; s < AS; ++s) { mbar_init(bar(WB_AF + s), 4); mbar_init(bar(WB_AE + s), 1); }
+        for (int s = 0; s < NBUF; ++s) { mbar_init(bar(WB_TF + s), 1); mbar_init(bar(WB_TE + s), 4); }
+        for (int s = 0; s < RES_RING; ++s) { mbar_init(bar(WB_RF + s), 4); mbar_init(bar(WB_RE + s), 8); }
+        for (int s = 0; s < 2; ++s) { mbar_init(bar(WB_PF + s), 4); mbar_init(bar(WB_PE + s), 4); }
+        fence_barrier_init();
+    }
+    if (warp == W_MMA) tmem_alloc(smem_u32(tmem_ptr_s), 512);
+    for (int i = threadIdx.x; i < 2 * TILE_M; i += THREADS)      // constant zero half of the A misc rows
+        *reinterpret_cast<uint4*>(sm + P.off_am() + (i / TILE_M) * AM_STAGE + sw32_chunk_off((uint32_t)(i % TILE_M), 1)) = make_uint4(0, 0, 0, 0);
+    fence_async_smem();
+    int bad = 0;
+    for (int i = threadIdx.x; i < KL; i += THREADS) {
+        const float ne = reinterpret_cast<const float*>(p.image + wimage_off_enorm(KL, DB))[i];
+        enorm_s[i] = ne;
+        bad |= !(ne < 1.0e18f);                  // NaN / inf / absurd norms: certify nothing, the exact path decides
+    }
+    tc_fence_before();
+    const bool cb_bad = __syncthreads_or(bad) != 0;
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_s;
+
+    if (warp == W_PROD) {
+        // ================= producer: resident operand image once, then one 2-D TMA box per (tile, block) ==========
+        reg_dec<24>();
+        if (lane == 0) {
+            const uint32_t img_bytes = (uint32_t)KL * 128u * DB, misc_bytes = (uint32_t)KL * 32u;
+            mbar_expect_tx(bar(WB_B), img_bytes + misc_bytes);
+            for (uint32_t o = 0; o < img_bytes; o += 16384u) bulk_g2s(sB + o, p.image + o, 16384u, bar(WB_B));
+            bulk_g2s(sBm, p.image + wimage_off_misc(KL, DB), misc_bytes, bar(WB_B));
+            const uint64_t keep = l2_policy_evict_last();       // the output warps read the tile again through L2
+            for (uint32_t it = 0; it < n_iter; ++it) {
+                const int64_t t = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
+                for (int b = 0; b < DB; ++b) {
+                    const uint32_t g = it * DB + b, s = g % XS, ph = (g / XS) & 1u;
+                    mbar_wait(bar(WB_XE + s), ph ^ 1u);
+                    mbar_expect_tx(bar(WB_XF + s), X_STAGE);     // rows past the end are zero-filled and still counted
+                    tma_load_2d(sX + s * X_STAGE, &p.tmap, b * 64, (int)(t * TILE_M), bar(WB_XF + s), keep);
+                }
+            }
+        }
+    } else if (warp == W_MMA) {
+        // ================= MMA issuer (converged warp; tcgen05 instructions predicated on one elected lane) ======
+        reg_dec<24>();
+        mbar_wait(bar(WB_B), 0);
+        const uint32_t b_lo0 = desc_lo(sB), bm_lo0 = desc_lo(sBm);
+        for (uint32_t it = 0; it < n_iter; ++it) {
+            const uint32_t am_lo = desc_lo(sAm + (it & 1u) * AM_STAGE);
+            for (int b = 0; b < DB; ++b) {
+                const uint32_t g = it * DB + b, sa = g % AS, pha = (g / AS) & 1u;
+                mbar_wait(bar(WB_AF + sa), pha);
+                tc_fence_after();
+                const uint32_t a_lo = desc_lo(sA + sa * A_STAGE);
+                for (int u = 0; u < U; ++u) {
+                    const uint32_t uc = it * (uint32_t)U + (uint32_t)u, buf = uc % NBUF, pht = (uc / NBUF) & 1u;
+                    if (b == 0) {
+                        mbar_wait(bar(WB_TE + buf), pht ^ 1u);
+                        tc_fence_after();
+                    }
+                    issue_block4(tmem_base + buf * UNIT_N, a_lo, b_lo0 + ((((uint32_t)b * KL + (uint32_t)u * UNIT_N) * 128u) >> 4),
+                                 b != 0 ? 1u : 0u);
+                    if (b == DB - 1) {           // the misc rows of this tile were written before the last block's AF arrival
+                        issue_misc(tmem_base + buf * UNIT_N, am_lo, bm_lo0 + (((uint32_t)u * UNIT_N * 32u) >> 4));
+                        commit_elected<false>(bar(WB_TF + buf));
+                    }
+                }
+                commit_elected<false>(bar(WB_AE + sa));          // also covers every earlier MMA (the misc rows of older tiles)
+            }
+        }
+    } else if (warp > W_MMA) {
+        reg_dec<24>();
+    } else if (warp >= W_CONV) {
+        // ================= converters: one fp32 [128][64] block -> bf16 K-major A stage ==========================
+        reg_dec<56>();
+        const int cw = warp - W_CONV;            // rows cw*32 .. cw*32+31
+        const int half = lane >> 4, q4 = lane & 15;
+        for (uint32_t it = 0; it < n_iter; ++it) {
+            float row_sq = 0.f;                  // ||x||^2 of row cw*32 + 2*q4 + half, accumulated over the blocks
+            for (int b = 0; b < DB; ++b) {
+                const uint32_t g = it * DB + b, sx = g % XS, phx = (g / XS) & 1u, sa = g % AS, pha = (g / AS) & 1u;
+                mbar_wait(bar(WB_XF + sx), phx);
+                mbar_wait(bar(WB_AE + sa), pha ^ 1u);
+                const unsigned char* xs = sm + P.off_x() + sx * X_STAGE;
+                unsigned char* ah = sm + P.off_a() + sa * A_STAGE;
+                float my_sq = 0.f;
+#pragma unroll 1
+                for (int g4 = 0; g4 < 4; ++g4) {          // 4 row pairs per trip
+                    float4 v[4];
+                    float sq[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        v[u] = *reinterpret_cast<const float4*>(xs + (cw * 32 + 2 * (4 * g4 + u) + half) * 256 + q4 * 16);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int r = cw * 32 + 2 * (4 * g4 + u) + half;
+                        *reinterpret_cast<uint2*>(ah + sw128_off((uint32_t)r, (uint32_t)q4 * 4)) =
+                            make_uint2(pack_bf16(v[u].x, v[u].y), pack_bf16(v[u].z, v[u].w));
+                        sq[u] = fmaf(v[u].x, v[u].x, fmaf(v[u].y, v[u].y, fmaf(v[u].z, v[u].z, v[u].w * v[u].w)));
+                    }
+                    {   // transposing butterfly: lane (half, q4) ends with the sum of row 2*q4 + half
+                        const bool up = (q4 & 2) != 0;
+                        const float s0 = up ? sq[0] : sq[2], k0 = up ? sq[2] : sq[0];
+                        const float s1 = up ? sq[1] : sq[3], k1 = up ? sq[3] : sq[1];
+                        sq[0] = k0 + __shfl_xor_sync(0xffffffffu, s0, 2);
+                        sq[1] = k1 + __shfl_xor_sync(0xffffffffu, s1, 2);
+                        const bool up1 = (q4 & 1) != 0;
+                        const float s2 = up1 ? sq[0] : sq[1], k2 = up1 ? sq[1] : sq[0];
+                        float tot = k2 + __shfl_xor_sync(0xffffffffu, s2, 1);
+                        tot += __shfl_xor_sync(0xffffffffu, tot, 4);
+                        tot += __shfl_xor_sync(0xffffffffu, tot, 8);
+                        if ((q4 >> 2) == g4) my_sq = tot;
+                    }
+                }
+                row_sq += my_sq;
+                if (b == DB - 1) {
+                    const int r = cw * 32 + 2 * q4 + half;
+                    const float nx = sqrtf(row_sq);
+                    float o1, o2, o3;
+                    split3(row_sq * 1.001953125f, o1, o2, o3);            // off_i = ||x||^2 (1 + 2^-9)
+                    const float nxu = bf16_round(nx * 1.0078125f);        // ||x|| rounded up
+                    *reinterpret_cast<uint4*>(sm + P.off_am() + (it & 1u) * AM_STAGE + sw32_chunk_off((uint32_t)r, 0)) =
+                        make_uint4(pack_bf16(1.f, 1.f), pack_bf16(1.f, o1), pack_bf16(o2, o3), pack_bf16(nxu, 1.f));
+                    rownorm_s[(it % NORM_RING) * TILE_M + r] = nx;
+                }
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(bar(WB_AF + sa)); mbar_arrive(bar(WB_XE + sx)); }
+            }
+        }
+    } else if (warp < W_OUT) {
+        // ================= epilogue: TMEM -> two-class min scan -> certified arg-min (as tc::k_vq_tc) =============
+        reg_inc<128>();
+        const int g = warp >> 2;
+        const int wq = warp & 3;
+        const int row_in_tile = wq * 32 + lane;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(wq * 32) << 16);
+        for (uint32_t it = 0; it < n_iter; ++it) {
+            const int64_t t = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
+            const int64_t grow = t * TILE_M + row_in_tile;
+            float rA[16], rB[16];
+#pragma unroll
+            for (int a = 0; a < 16; ++a) { rA[a] = INFINITY; rB[a] = INFINITY; }
+            float* dbg = (DBG && p.dbg_scores && grow < p.n_rows) ? p.dbg_scores + grow * p.K_total + p.code_base : nullptr;
+            {   // first unit of the group
+                const uint32_t uc = it * (uint32_t)U + (uint32_t)g, buf = uc % NBUF, pht = (uc / NBUF) & 1u;
+                mbar_wait(bar(WB_TF + buf), pht);
+                tc_fence_after();
+                scan_buffer<0, DBG>(lane_base + buf * UNIT_N, rA, rB, dbg ? dbg + g * UNIT_N : nullptr);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(WB_TE + buf));
+            }
+            if (U == 4) {   // second unit (codes 128*(g+2) ..)
+                const uint32_t uc = it * 4u + (uint32_t)g + 2u, buf = uc % NBUF, pht = (uc / NBUF) & 1u;
+                mbar_wait(bar(WB_TF + buf), pht);
+                tc_fence_after();
+                scan_buffer<4, DBG>(lane_base + buf * UNIT_N, rA, rB, dbg ? dbg + (g + 2) * UNIT_N - 4 * 32 : nullptr);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(WB_TE + buf));
+            }
+            float m1, m2;
+            int k1;
+            {
+                const int v = scan_finish(rA, rB, m1, m2);        // virtual column 0..255 of this group
+                k1 = (v < UNIT_N ? g : g + 2) * UNIT_N + (v & (UNIT_N - 1));
+            }
+            {
+                const uint32_t ps = it & 1u, php = (it >> 1) & 1u;
+                if (g == 0) {                    // hand this group's result to group 1
+                    mbar_wait(bar(WB_PE + ps), php ^ 1u);
+                    part_s[ps * TILE_M + row_in_tile] = make_float4(m1, m2, __int_as_float(k1), 0.f);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar(WB_PF + ps));
+                    continue;
+                }
+                mbar_wait(bar(WB_PF + ps), php);
+                const float4 o = part_s[ps * TILE_M + row_in_tile];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(WB_PE + ps));
+                const int ko = __float_as_int(o.z);
+                m2 = fminf(fminf(o.y, m2), fmaxf(o.x, m1));
+                const bool take_other = (o.x < m1) || (o.x == m1 && ko < k1);
+                if (take_other) { m1 = o.x; k1 = ko; }
+            }
+            const float xn = rownorm_s[(it % NORM_RING) * TILE_M + row_in_tile];
+            float en = enorm_s[k1 < KL ? k1 : 0];
+            const bool in_range = grow < p.n_rows;
+            k1 += p.code_base;
+            bool badrow = cb_bad;
+            if (p.partial) {                     // sliced codebook: fold in the earlier slices / hand on to the later ones
+                if (!p.pass_first && in_range) {
+                    const float4 o = p.partial[grow];
+                    const int ko = __float_as_int(o.z);
+                    badrow = badrow || ((__float_as_uint(o.w) >> 31) != 0u);
+                    m2 = fminf(fminf(o.y, m2), fmaxf(o.x, m1));
+                    if ((o.x < m1) || (o.x == m1 && ko < k1)) { m1 = o.x; k1 = ko; en = fabsf(o.w); }
+                }
+                if (!p.pass_last && in_range)
+                    p.partial[grow] = make_float4(m1, m2, __int_as_float(k1), badrow ? __uint_as_float(__float_as_uint(en) | 0x80000000u) : en);
+            }
+            const float need = 2.f * (p.cA * BOUND_UP * xn * en + p.cB * (BOUND_UP * en * en + xn * xn));
+            const bool certified = ((m2 - m1) > need) && (xn < 1.0e18f) && !badrow;   // NaN -> false
+            const uint32_t rs = it % RES_RING, phr = (it / RES_RING) & 1u;
+            mbar_wait(bar(WB_RE + rs), phr ^ 1u);
+            int code = -2;
+            if (in_range && p.pass_last) {
+                code = certified ? k1 : -1;
+                if (certified) p.embed_ind[grow] = (int64_t)k1;
+            }
+            codes_s[rs * TILE_M + row_in_tile] = code;
+            const unsigned fl = __ballot_sync(0xffffffffu, code == -1);
+            if (fl) {
+                int basei = 0;
+                const int leader = __ffs(fl) - 1;
+                if (lane == leader) basei = atomicAdd(p.flagged_count, __popc(fl));
+                basei = __shfl_sync(0xffffffffu, basei, leader);
+                if (code == -1) p.flagged_rows[basei + __popc(fl & ((1u << lane) - 1u))] = (int)grow;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(WB_RF + rs));
+        }
+    } else {
+        // ================= output: gather, straight-through value, loss ==========================================
+        // 8 warps x 16 rows; a half-warp covers one 64-dim block of one row per instruction (16 lanes x 16 bytes)
+        reg_dec<72>();
+        const int ow = warp - W_OUT;
+        const int half = lane >> 4, q4 = lane & 15;
+        float dacc = 0.f;
+        constexpr int RQ = D / 4;                // float4 per row
+        const float4* x4 = reinterpret_cast<const float4*>(p.x);
+        float4* o4 = reinterpret_cast<float4*>(p.quantize);
+        const float4* cb4 = reinterpret_cast<const float4*>(p.cbT);
+        for (uint32_t it = 0; it < n_iter; ++it) {
+            const int64_t t = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
+            const uint32_t rs = it % RES_RING, phr = (it / RES_RING) & 1u;
+            mbar_wait(bar(WB_RF + rs), phr);
+            const int* cs = codes_s + rs * TILE_M + ow * 16 + half;
+            const size_t row0 = (size_t)t * TILE_M + ow * 16 + half;
+#pragma unroll
+            for (int b2 = 0; b2 < 2; ++b2) {
+                int kk[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) kk[i] = cs[b2 * 8 + i * 2];
+#pragma unroll
+                for (int blk = 0; blk < DB; ++blk) {
+                    float4 xv[4], qv[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (kk[i] >= 0) {
+                            xv[i] = __ldcg(x4 + (row0 + b2 * 8 + i * 2) * RQ + blk * 16 + q4);
+                            qv[i] = __ldcg(cb4 + (size_t)kk[i] * RQ + blk * 16 + q4);
+                        }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (kk[i] < 0) continue;
+                        float4 d, o;
+                        d.x = qv[i].x - xv[i].x; d.y = qv[i].y - xv[i].y; d.z = qv[i].z - xv[i].z; d.w = qv[i].w - xv[i].w;
+                        o.x = xv[i].x + d.x; o.y = xv[i].y + d.y; o.z = xv[i].z + d.z; o.w = xv[i].w + d.w;
+                        dacc = fmaf(d.x, d.x, fmaf(d.y, d.y, fmaf(d.z, d.z, fmaf(d.w, d.w, dacc))));
+                        if (o4) __stcs(o4 + (row0 + b2 * 8 + i * 2) * RQ + blk * 16 + q4, o);
+                        if (p.stat_sums) {
+                            red_add_v4(p.stat_sums + (size_t)kk[i] * D + blk * 64 + q4 * 4, xv[i]);
+                            if (q4 == 0 && blk == 0) red_add_f32(p.stat_counts + kk[i], 1.0f);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(WB_RE + rs));
+        }
+        if (p.diff_acc) {
+            dacc = warp_sum(dacc);
+            if (lane == 0) atomicAdd(p.diff_acc, (double)dacc);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == W_MMA) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace tcw
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+// codes per launch: the bf16 operand image of a launch is 128 KB of shared memory
+inline int tcw_slice(int dim, int n_embed) { return (dim == 128 && n_embed >= 512) ? 512 : 256; }   // 2 or 4 units of 128 codes
+inline bool tcw_shape_ok(int dim, int n_embed) {
+    if (dim != 128 && dim != 256) return false;
+    if (n_embed < 256 || n_embed > 16384) return false;
+    return n_embed % tcw_slice(dim, n_embed) == 0;
+}
+inline bool tcw_supported(const RowLayout& L, const float* x, int dim, int n_embed) {
+    if (!tcw_shape_ok(dim, n_embed) || L.n_rows < 1) return false;
+    if (getenv("VQB200_DISABLE_TC") || getenv("VQB200_DISABLE_TCW")) return false;
+    return tc_layout_dense(L, x, dim);
+}
+
+inline int tcw_encode_tmap(CUtensorMap* tm, const float* x, int64_t n_rows, int dim) {
+    static PFN_cuTensorMapEncodeTiled encode = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess) f = nullptr;
+        return reinterpret_cast<PFN_cuTensorMapEncodeTiled>(f);
+    }();
+    if (!encode) return 1;
+    cuuint64_t gdim[2] = {(cuuint64_t)dim, (cuuint64_t)n_rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)dim * 4u};
+    cuuint32_t box[2] = {64u, (cuuint32_t)tc::TILE_M};
+    cuuint32_t estr[2] = {1u, 1u};
+    return encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS;
+}
+
+template <int DB, int XS, bool DBG>
+inline int tcw_launch(const tcw::WParams& prm, cudaStream_t st) {
+    auto kern = tcw::k_vq_tcw<DB, XS, DBG>;
+    const tcw::Plan P{prm.KL, DB, XS};
+    const int smem = (int)P.total();
+    static int configured = 0;
+    if (configured < smem) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+            fprintf(stderr, "vqb200: wide tensor-core kernel needs %d bytes of shared memory (DB=%d XS=%d KL=%d)\n", smem, DB, XS, prm.KL);
+            return 1;
+        }
+        configured = smem;
+    }
+    const cudaError_t e = launch_pdl(kern, dim3((unsigned)tc_grid(prm.n_rows, false)), dim3(tc::THREADS), (size_t)smem, st, prm);
+    if (e != cudaSuccess) fprintf(stderr, "vqb200: wide tensor-core kernel launch failed: %s (smem %d)\n", cudaGetErrorString(e), smem);
+    return e != cudaSuccess;
+}
+
+// operand image(s) of the wide engine from the fp32 code-major copy
+inline cudaError_t tcw_prepare(const CodebookImage& cb, int dim, int n_embed, cudaStream_t st) {
+    const int threads = n_embed * (dim / 8);
+    return launch_pdl(tcw::k_prepare_wide, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, st, (const float*)cb.cbT, (const float*)cb.ee,
+                      cb.tc, n_embed, dim, tcw_slice(dim, n_embed), tc::bound_cA(1), tcw::bound_cB(dim / 64));
+}
+
+// main kernel only (one launch per slice); the caller runs the exact fix-up over the flagged rows afterwards
+inline int tcw_forward(const float* x, const RowLayout& L, int dim, int n_embed, const CodebookImage& cb, float* quantize,
+                       int64_t* embed_ind, const ForwardScratch& sc, double* diff_acc, float* sums, float* counts,
+                       float* dbg_scores, cudaStream_t st) {
+    const int DB = dim / 64, KL = tcw_slice(dim, n_embed), n_slices = n_embed / KL;
+    if (n_slices > 1 && !sc.partial) return 1;
+    CUtensorMap tmap;
+    if (tcw_encode_tmap(&tmap, x, L.n_rows, dim)) {
+        fprintf(stderr, "vqb200: cuTensorMapEncodeTiled failed for x [%lld, %d]\n", (long long)L.n_rows, dim);
+        return 1;
+    }
+    for (int sl = 0; sl < n_slices; ++sl) {
+        tcw::WParams prm;
+        prm.tmap = tmap;
+        prm.x = x; prm.n_rows = L.n_rows; prm.KL = KL; prm.K_total = n_embed;
+        prm.image = cb.tc + (size_t)sl * tcw::wimage_bytes(KL, DB); prm.cbT = cb.cbT;
+        prm.quantize = quantize; prm.embed_ind = embed_ind; prm.diff_acc = diff_acc;
+        prm.stat_sums = sums; prm.stat_counts = counts;
+        prm.flagged_count = sc.flagged_count; prm.flagged_rows = sc.flagged_rows; prm.dbg_scores = dbg_scores;
+        prm.cA = tc::bound_cA(1); prm.cB = tcw::bound_cB(DB);
+        prm.code_base = sl * KL; prm.partial = n_slices > 1 ? sc.partial : nullptr;
+        prm.pass_first = sl == 0; prm.pass_last = sl == n_slices - 1;
+        int rc;
+        if (DB == 2) {
+            if (KL == 512) rc = dbg_scores ? tcw_launch<2, 1, true>(prm, st) : tcw_launch<2, 1, false>(prm, st);
+            else rc = dbg_scores ? tcw_launch<2, 3, true>(prm, st) : tcw_launch<2, 3, false>(prm, st);
+        } else {
+            rc = dbg_scores ? tcw_launch<4, 1, true>(prm, st) : tcw_launch<4, 1, false>(prm, st);
+        }
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+}  // namespace vqb200

@@ -16,6 +16,7 @@
 #include "simt_kernels.cuh"
 #include "tc_kernel.cuh"
 #include "fused_kernels.cuh"
+#include "tc_wide_kernel.cuh"
 
 using namespace vqb200;
 
@@ -65,6 +66,10 @@ int prepare_codebook(const float* d_embed, int dim, int n_embed, void* d_codeboo
     k_codebook_norms<<<(n_embed + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(
         cb.cbT, cb.ee, dim, n_embed);
     VQ_LAUNCH_CHECK();
+    if (tcw_shape_ok(dim, n_embed)) {             // bf16 operand image(s) of the wide tensor-core engine (D = 128 / 256)
+        VQ_CUDA(tcw_prepare(cb, dim, n_embed, st));
+        g_launches.fetch_add(1);
+    }
     return VQB200_OK;
 }
 
@@ -87,7 +92,8 @@ int forward_impl(const float* d_x, const RowLayout& L, int dim, int n_embed, con
     bool finalized = false;
     bool use_tc = false;
     if (L.n_rows > 0 && (engine == VQB200_ENGINE_TCGEN05 || engine == VQB200_ENGINE_TCGEN05_BF16 || engine == VQB200_ENGINE_AUTO))
-        use_tc = tc_supported(L, d_x, dim, n_embed);
+        use_tc = tc_supported(L, d_x, dim, n_embed) || tcw_supported(L, d_x, dim, n_embed);
+    const bool wide = use_tc && dim != tc::TC_D;  // tc_wide_kernel.cuh
     if (L.n_rows > 0 && (engine == VQB200_ENGINE_TCGEN05 || engine == VQB200_ENGINE_TCGEN05_BF16) && !use_tc)
         return VQB200_EUNSUPPORTED;
     // statistics: private-table segmented reduction when [K][D] fp32 fits in shared memory (its fold kernel writes
@@ -119,17 +125,18 @@ int forward_impl(const float* d_x, const RowLayout& L, int dim, int n_embed, con
         const bool want_gather = d_quantize || d_diff || sums;
         const size_t gsmem = (size_t)GS_BM * (dim + 1) * sizeof(float);
         if (gsmem > 200 * 1024) return VQB200_EUNSUPPORTED;
-        if (gsmem > 48 * 1024) {
-            VQ_CUDA(cudaFuncSetAttribute(k_gather_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
-            VQ_CUDA(cudaFuncSetAttribute(k_fixup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
-        }
+        if (gsmem > 48 * 1024) VQ_CUDA(cudaFuncSetAttribute(k_gather_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+        // k_fixup also carries ~18 KB of static shared memory (the exact re-score tiles): opt in as soon as the sum passes 48 KB
+        if (gsmem > 24 * 1024) VQ_CUDA(cudaFuncSetAttribute(k_fixup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
         const int sms = tc_num_sms();
         if (use_tc) {
             // tensor-core filter + fused output for certified rows; flagged rows -> exact SIMT fix-up (one launch:
             // re-score, gather / output / loss of those rows, loss finalisation)
-            int rc = tc_forward(d_x, L, dim, n_embed, cb, d_quantize, d_ind, sc, d_diff ? sc.diff_acc : nullptr, sums,
-                                counts, dbg_scores, st, prof, nsplit, nullptr, (nchw && stats_kernel) ? d_x_dense : nullptr);
-            g_launches.fetch_add(1);
+            int rc = wide ? tcw_forward(d_x, L, dim, n_embed, cb, d_quantize, d_ind, sc, d_diff ? sc.diff_acc : nullptr, sums,
+                                        counts, dbg_scores, st)
+                          : tc_forward(d_x, L, dim, n_embed, cb, d_quantize, d_ind, sc, d_diff ? sc.diff_acc : nullptr, sums,
+                                       counts, dbg_scores, st, prof, nsplit, nullptr, (nchw && stats_kernel) ? d_x_dense : nullptr);
+            g_launches.fetch_add(wide ? (unsigned long long)(n_embed / tcw_slice(dim, n_embed)) : 1ull);
             if (rc) return cuda_fail(cudaGetLastError());
             VQ_CUDA(launch_pdl(k_fixup, dim3(sms), dim3(AS_THREADS), gsmem, st, d_x, L, dim, n_embed, cb.cbT, cb.ee, d_ind,
                                d_quantize, d_diff ? sc.diff_acc : nullptr, sums, counts, sc.flagged_rows, sc.flagged_count,
@@ -208,6 +215,10 @@ int ema_impl(const float* d_stats, const PeerStats* peers, float* d_cluster_size
                                                                  d_embed, cb.cbT, cb.ee, dim, n_embed, decay,
                                                                  one_minus_decay, eps);
     VQ_LAUNCH_CHECK();
+    if (d_codebook && tcw_shape_ok(dim, n_embed)) {
+        VQ_CUDA(tcw_prepare(cb, dim, n_embed, st));
+        g_launches.fetch_add(1);
+    }
     return VQB200_OK;
 }
 
@@ -402,7 +413,7 @@ int vqb200_debug_tc_scores(const float* d_x, int64_t n_rows, int32_t dim, int32_
                            void* stream) {
     if (!d_x || !d_codebook || !d_embed_ind || !d_scores || !d_scratch || n_rows <= 0) return VQB200_EINVAL;
     RowLayout L{n_rows, n_rows, 0, dim, 1};
-    if (!tc_supported(L, d_x, dim, n_embed)) return VQB200_EUNSUPPORTED;
+    if (!tc_supported(L, d_x, dim, n_embed) && !tcw_supported(L, d_x, dim, n_embed)) return VQB200_EUNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     int rc = forward_impl(d_x, L, dim, n_embed, d_codebook, nullptr, d_embed_ind, nullptr, nullptr, d_scratch,
                           VQB200_ENGINE_TCGEN05, true, false, n_rows, st, d_scores);
@@ -419,7 +430,7 @@ int vqb200_tc_supported(const float* d_x, int64_t n_rows, int32_t dim, int32_t n
                         int64_t image_stride, int64_t row_stride, int64_t col_stride) {
     if (n_rows <= 0 || rows_per_image <= 0) return 0;
     RowLayout L{n_rows, rows_per_image, image_stride, row_stride, col_stride};
-    return tc_supported(L, d_x, dim, n_embed) ? 1 : 0;
+    return (tc_supported(L, d_x, dim, n_embed) || tcw_supported(L, d_x, dim, n_embed)) ? 1 : 0;
 }
 
 int vqb200_debug_tc_profile(const float* d_x, int64_t n_rows, int32_t dim, int32_t n_embed, const void* d_codebook,
