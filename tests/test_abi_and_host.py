@@ -39,6 +39,12 @@ def test_size_queries():
     assert lib.vqb200_codebook_bytes(64, 512) >= 512 * 64 * 4 + 512 * 4
     assert lib.vqb200_forward_scratch_bytes(1000, 64, 512) >= 4000
     assert lib.vqb200_codebook_bytes(0, 512) == 0 and lib.vqb200_stats_bytes(64, -1) == 0
+    # sliced wide tensor-core shapes (dim 128 / 256) carry the per-call bf16 operand image of x in the scratch:
+    # per 128-row tile dim/64 blocks of 16 KB + 4 KB misc rows + 512 B norms, and the float4 carried from slice to slice
+    tiles = (1000 + 127) // 128
+    extra = lib.vqb200_forward_scratch_bytes(1000, 256, 512) - lib.vqb200_forward_scratch_bytes(1000, 256, 256) \
+        - 160 * 256 * 257 * 4
+    assert extra == tiles * (4 * 16384 + 4096 + 512) + 1000 * 16 + (-1000 * 16) % 256
 
 
 def test_argument_validation_without_a_gpu():

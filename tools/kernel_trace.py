@@ -1,5 +1,6 @@
 """Per-kernel device times of real training steps (CUPTI activity trace via torch.profiler: back-to-back launches,
 warm caches -- unlike the ncu launch list, which serialises and flushes).  Usage: python tools/kernel_trace.py [engine] [dist]"""
+import os
 import sys
 from collections import defaultdict
 
@@ -12,7 +13,7 @@ import vq_vae_2_pytorch_b200 as vq  # noqa: E402
 engine = sys.argv[1] if len(sys.argv) > 1 else "auto"
 dist = sys.argv[2] if len(sys.argv) > 2 else "clustered"
 layout = sys.argv[3] if len(sys.argv) > 3 else "dense"
-B, H, W, D, K = 128, 64, 64, 64, 512
+B, H, W, D, K = 128, 64, 64, int(os.environ.get("VQ_TRACE_D", "64")), int(os.environ.get("VQ_TRACE_K", "512"))
 N = B * H * W
 import os
 world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -24,6 +25,8 @@ if world > 1:
     tdist.init_process_group("nccl", device_id=torch.device(dev))
 torch.manual_seed(0)
 q = vq.Quantize(D, K, engine=engine).to(dev).train()
+if os.environ.get("VQ_TRACE_EVAL"):
+    q.eval()
 embed0 = q.embed.clone()
 xs = []
 for i in range(3):

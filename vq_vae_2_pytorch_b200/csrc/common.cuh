@@ -65,13 +65,23 @@ struct ForwardScratch {
     int* flagged_rows;     // [n_rows] row ids
     float4* partial;       // [n_rows] running (m1, m2, winner, ||e_winner||) of the sliced tensor-core engine (n_embed > 512), else null
     float* stat_partials;  // [STAT_PARTS][K*(D+1)] per-CTA statistics tables
+    // sliced WIDE tensor-core engine (dim 128 / 256, tc_wide_kernel.cuh): x converted once per call, per 128-row tile
+    unsigned char* wide_a; // [tiles][dim/64][16384] bf16 operand blocks (128-byte swizzle image)
+    unsigned char* wide_m; // [tiles][4096] misc rows (32-byte swizzle image)
+    float* wide_norm;      // [tiles][128] ||x_row||
 };
 constexpr int STAT_PARTS = 160;
 __host__ __device__ inline bool scratch_has_partial(int dim, int n_embed) {
     return (dim == 64 && n_embed > 512) || (dim == 128 && n_embed > 512) || (dim == 256 && n_embed > 256);   // sliced tensor-core launches
 }
+__host__ __device__ inline bool scratch_has_wide(int dim, int n_embed) { return dim != 64 && scratch_has_partial(dim, n_embed); }
+__host__ __device__ inline size_t scratch_wide_bytes(int64_t n_rows, int dim) {
+    const size_t tiles = (size_t)((n_rows + 127) / 128);
+    return tiles * ((size_t)(dim / 64) * 16384 + 4096 + 512);
+}
 __host__ __device__ inline size_t forward_scratch_bytes(int64_t n_rows, int dim, int n_embed) {
     return 256 + align_up((size_t)n_rows * 4, 256) + (scratch_has_partial(dim, n_embed) ? align_up((size_t)n_rows * 16, 256) : 0) +
+           (scratch_has_wide(dim, n_embed) ? scratch_wide_bytes(n_rows, dim) : 0) +
            (size_t)STAT_PARTS * n_embed * (dim + 1) * 4;
 }
 __host__ __device__ inline ForwardScratch scratch_view(void* base, int64_t n_rows, int dim, int n_embed) {
@@ -84,6 +94,13 @@ __host__ __device__ inline ForwardScratch scratch_view(void* base, int64_t n_row
     p += 256 + align_up((size_t)n_rows * 4, 256);
     s.partial = nullptr;
     if (scratch_has_partial(dim, n_embed)) { s.partial = (float4*)p; p += align_up((size_t)n_rows * 16, 256); }
+    s.wide_a = nullptr; s.wide_m = nullptr; s.wide_norm = nullptr;
+    if (scratch_has_wide(dim, n_embed)) {
+        const size_t tiles = (size_t)((n_rows + 127) / 128);
+        s.wide_a = p;            p += tiles * (size_t)(dim / 64) * 16384;
+        s.wide_m = p;            p += tiles * 4096;
+        s.wide_norm = (float*)p; p += tiles * 512;
+    }
     s.stat_partials = (float*)p;
     return s;
 }

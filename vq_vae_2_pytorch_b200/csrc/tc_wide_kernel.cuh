@@ -18,7 +18,7 @@ namespace vqb200 {
 namespace tcw {
 using namespace tc;
 
-constexpr int AS = 2;                        // bf16 A stages (one 64-dim block of a 128-row tile each)
+constexpr int AS_CONV = 2, AS_PRE = 4;       // bf16 A stages (one 64-dim block of a 128-row tile each)
 constexpr uint32_t A_STAGE = 16384u, AM_STAGE = 4096u, X_STAGE = TILE_M * 64 * 4;
 
 __host__ __device__ inline size_t wimage_off_misc(int KL, int DB) { return (size_t)KL * 128 * DB; }
@@ -57,11 +57,54 @@ __global__ void __launch_bounds__(256) k_prepare_wide(const float* __restrict__ 
     }
 }
 
+// x [N][64 DB] fp32 -> per 128-row tile: DB bf16 operand blocks, the tile's misc rows and the row norms, all byte-identical
+// to the shared-memory stages of k_vq_tcw<PRE> (one plain bulk copy each).  Sliced codebooks convert x ONCE per call
+// instead of once per slice.  A half-warp owns a row: coalesced 256-byte reads, 128-byte writes.
+template <int DB>
+__global__ void __launch_bounds__(256) k_convert_wide(const float* __restrict__ x, int64_t n_rows, unsigned char* __restrict__ a_img,
+                                                       unsigned char* __restrict__ m_img, float* __restrict__ norms) {
+    pdl_wait();
+    pdl_trigger();
+    constexpr int D = 64 * DB;
+    const int lane = threadIdx.x & 31, q4 = lane & 15;
+    const int64_t padded = (n_rows + TILE_M - 1) / TILE_M * TILE_M;
+    const int64_t n_hw = ((int64_t)gridDim.x * blockDim.x) >> 4;
+    for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4; row < padded; row += n_hw) {
+        const int64_t t = row >> 7;
+        const uint32_t r = (uint32_t)(row & 127);
+        const bool in = row < n_rows;                              // rows past the end: zeros (finite scores, never used)
+        float4 v[DB];
+#pragma unroll
+        for (int b = 0; b < DB; ++b)
+            v[b] = in ? __ldcs(reinterpret_cast<const float4*>(x + row * D + b * 64) + q4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float sq = 0.f;
+#pragma unroll
+        for (int b = 0; b < DB; ++b) {
+            *reinterpret_cast<uint2*>(a_img + ((size_t)t * DB + b) * A_STAGE + sw128_off(r, (uint32_t)q4 * 4)) =
+                make_uint2(pack_bf16(v[b].x, v[b].y), pack_bf16(v[b].z, v[b].w));
+            sq = fmaf(v[b].x, v[b].x, fmaf(v[b].y, v[b].y, fmaf(v[b].z, v[b].z, fmaf(v[b].w, v[b].w, sq))));
+        }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);      // stays inside the half-warp
+        if (q4 == 0) {
+            const float nx = sqrtf(sq);
+            float o1, o2, o3;
+            split3(sq * 1.001953125f, o1, o2, o3);                 // off_i = ||x||^2 (1 + 2^-9)
+            const float nxu = bf16_round(nx * 1.0078125f);         // ||x|| rounded up
+            unsigned char* m = m_img + (size_t)t * AM_STAGE;
+            *reinterpret_cast<uint4*>(m + sw32_chunk_off(r, 0)) =
+                make_uint4(pack_bf16(1.f, 1.f), pack_bf16(1.f, o1), pack_bf16(o2, o3), pack_bf16(nxu, 1.f));
+            *reinterpret_cast<uint4*>(m + sw32_chunk_off(r, 1)) = make_uint4(0, 0, 0, 0);
+            norms[row] = nx;
+        }
+    }
+}
+
 struct Plan {
-    int KL, DB, XS;
+    int KL, DB, XS, AS;
     __host__ __device__ uint32_t off_bmisc() const { return (uint32_t)KL * 128u * (uint32_t)DB; }
     __host__ __device__ uint32_t off_a() const { return off_bmisc() + (uint32_t)KL * 32u; }
-    __host__ __device__ uint32_t off_am() const { return off_a() + AS * A_STAGE; }
+    __host__ __device__ uint32_t off_am() const { return off_a() + (uint32_t)AS * A_STAGE; }
     __host__ __device__ uint32_t off_x() const { return off_am() + 2u * AM_STAGE; }
     __host__ __device__ uint32_t off_small() const { return off_x() + (uint32_t)XS * X_STAGE; }
     __host__ __device__ uint32_t off_rownorm() const { return off_small() + (uint32_t)KL * 4u; }
@@ -91,10 +134,15 @@ struct WParams {
     int code_base;
     float4* partial;                 // may be null (single launch)
     int pass_first, pass_last;
+    // PRE = true (sliced codebooks): x was converted ONCE by k_convert_wide; the producer streams ready-made operand stages
+    const unsigned char* a_img;      // [tile][DB][16384]: bf16 A blocks, byte-identical to their 128B-swizzled shared-memory layout
+    const unsigned char* m_img;      // [tile][4096]: misc rows of the tile (32-byte swizzle)
+    const float* norms;              // [tile][128]: ||x_row||
+    int64_t row_base;                // global id of row 0 of this launch (row-chunked launches; flagged-row list entries are global)
 };
 
-enum WBar { WB_B = 0, WB_XF = 1, WB_XE = 5, WB_AF = 9, WB_AE = 11, WB_TF = 13, WB_TE = 17, WB_RF = 21, WB_RE = 23, WB_PF = 25,
-            WB_PE = 27, WB_COUNT = 29 };
+enum WBar { WB_B = 0, WB_XF = 1, WB_XE = 5, WB_AF = 9, WB_AE = 13, WB_TF = 17, WB_TE = 21, WB_RF = 25, WB_RE = 27, WB_PF = 29,
+            WB_PE = 31, WB_COUNT = 33 };
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar, uint64_t policy) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
@@ -127,16 +175,17 @@ __device__ __forceinline__ void issue_misc(uint32_t d_tmem, uint32_t am_lo, uint
                  :: "r"(d_tmem), "r"(am_lo), "r"(bm_lo), "r"(DESC_HI_SW32), "r"(IDESC) : "memory");
 }
 
-template <int DB, int XS, bool DBG>
+template <int DB, int XS, bool DBG, bool PRE>
 __global__ void __launch_bounds__(THREADS, 1) k_vq_tcw(const __grid_constant__ WParams p) {
     constexpr int D = 64 * DB;
+    constexpr int AS = PRE ? AS_PRE : AS_CONV;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     unsigned char* sm = smem_raw + (base - raw);
     const int KL = p.KL;
     const int U = KL / UNIT_N;                  // accumulator units per tile: 2 or 4
-    const Plan P{KL, DB, XS};
+    const Plan P{KL, DB, PRE ? 0 : XS, AS};
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     const uint32_t sB = base, sBm = base + P.off_bmisc(), sA = base + P.off_a(), sAm = base + P.off_am(), sX = base + P.off_x();
@@ -156,7 +205,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tcw(const __grid_constant__ W
     if (threadIdx.x == 0) {
         mbar_init(bar(WB_B), 1);
         for (int s = 0; s < XS; ++s) { mbar_init(bar(WB_XF + s), 1); mbar_init(bar(WB_XE + s), 4); }
-        for (int s = 0; s < AS; ++s) { mbar_init(bar(WB_AF + s), 4); mbar_init(bar(WB_AE + s), 1); }
+        for (int s = 0; s < AS; ++s) { mbar_init(bar(WB_AF + s), PRE ? 1 : 4); mbar_init(bar(WB_AE + s), 1); }
         for (int s = 0; s < NBUF; ++s) { mbar_init(bar(WB_TF + s), 1); mbar_init(bar(WB_TE + s), 4); }
         for (int s = 0; s < RES_RING; ++s) { mbar_init(bar(WB_RF + s), 4); mbar_init(bar(WB_RE + s), 8); }
         for (int s = 0; s < 2; ++s) { mbar_init(bar(WB_PF + s), 4); mbar_init(bar(WB_PE + s), 4); }
@@ -188,11 +237,25 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tcw(const __grid_constant__ W
             const uint64_t keep = l2_policy_evict_last();       // the output warps read the tile again through L2
             for (uint32_t it = 0; it < n_iter; ++it) {
                 const int64_t t = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
-                for (int b = 0; b < DB; ++b) {
-                    const uint32_t g = it * DB + b, s = g % XS, ph = (g / XS) & 1u;
-                    mbar_wait(bar(WB_XE + s), ph ^ 1u);
-                    mbar_expect_tx(bar(WB_XF + s), X_STAGE);     // rows past the end are zero-filled and still counted
-                    tma_load_2d(sX + s * X_STAGE, &p.tmap, b * 64, (int)(t * TILE_M), bar(WB_XF + s), keep);
+                if constexpr (PRE) {             // ready-made operand stages: 16 KB per block, misc rows and norms with the last block
+                    for (int b = 0; b < DB; ++b) {
+                        const uint32_t g = it * DB + b, s = g % AS, ph = (g / AS) & 1u;
+                        mbar_wait(bar(WB_AE + s), ph ^ 1u);
+                        const bool last = b == DB - 1;
+                        mbar_expect_tx(bar(WB_AF + s), A_STAGE + (last ? AM_STAGE + TILE_M * 4u : 0u));
+                        bulk_g2s(sA + s * A_STAGE, p.a_img + ((size_t)t * DB + b) * A_STAGE, A_STAGE, bar(WB_AF + s));
+                        if (last) {
+                            bulk_g2s(sAm + (it & 1u) * AM_STAGE, p.m_img + (size_t)t * AM_STAGE, AM_STAGE, bar(WB_AF + s));
+                            bulk_g2s(base + P.off_rownorm() + (it % NORM_RING) * TILE_M * 4u, p.norms + (size_t)t * TILE_M, TILE_M * 4u, bar(WB_AF + s));
+                        }
+                    }
+                } else {
+                    for (int b = 0; b < DB; ++b) {
+                        const uint32_t g = it * DB + b, s = g % XS, ph = (g / XS) & 1u;
+                        mbar_wait(bar(WB_XE + s), ph ^ 1u);
+                        mbar_expect_tx(bar(WB_XF + s), X_STAGE);     // rows past the end are zero-filled and still counted
+                        tma_load_2d(sX + s * X_STAGE, &p.tmap, b * 64, (int)(t * TILE_M), bar(WB_XF + s), keep);
+                    }
                 }
             }
         }
@@ -231,7 +294,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tcw(const __grid_constant__ W
         reg_dec<56>();
         const int cw = warp - W_CONV;            // rows cw*32 .. cw*32+31
         const int half = lane >> 4, q4 = lane & 15;
-        for (uint32_t it = 0; it < n_iter; ++it) {
+        const uint32_t conv_iter = PRE ? 0u : n_iter;             // PRE: nothing to convert
+        for (uint32_t it = 0; it != conv_iter; ++it) {
             float row_sq = 0.f;                  // ||x||^2 of row cw*32 + 2*q4 + half, accumulated over the blocks
             for (int b = 0; b < DB; ++b) {
                 const uint32_t g = it * DB + b, sx = g % XS, phx = (g / XS) & 1u, sa = g % AS, pha = (g / AS) & 1u;
@@ -372,7 +436,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tcw(const __grid_constant__ W
                 const int leader = __ffs(fl) - 1;
                 if (lane == leader) basei = atomicAdd(p.flagged_count, __popc(fl));
                 basei = __shfl_sync(0xffffffffu, basei, leader);
-                if (code == -1) p.flagged_rows[basei + __popc(fl & ((1u << lane) - 1u))] = (int)grow;
+                if (code == -1) p.flagged_rows[basei + __popc(fl & ((1u << lane) - 1u))] = (int)(grow + p.row_base);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(WB_RF + rs));
@@ -471,10 +535,10 @@ inline int tcw_encode_tmap(CUtensorMap* tm, const float* x, int64_t n_rows, int 
                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS;
 }
 
-template <int DB, int XS, bool DBG>
+template <int DB, int XS, bool DBG, bool PRE>
 inline int tcw_launch(const tcw::WParams& prm, cudaStream_t st) {
-    auto kern = tcw::k_vq_tcw<DB, XS, DBG>;
-    const tcw::Plan P{prm.KL, DB, XS};
+    auto kern = tcw::k_vq_tcw<DB, XS, DBG, PRE>;
+    const tcw::Plan P{prm.KL, DB, PRE ? 0 : XS, PRE ? tcw::AS_PRE : tcw::AS_CONV};
     const int smem = (int)P.total();
     static int configured = 0;
     if (configured < smem) {
@@ -499,33 +563,71 @@ inline cudaError_t tcw_prepare(const CodebookImage& cb, int dim, int n_embed, cu
 // main kernel only (one launch per slice); the caller runs the exact fix-up over the flagged rows afterwards
 inline int tcw_forward(const float* x, const RowLayout& L, int dim, int n_embed, const CodebookImage& cb, float* quantize,
                        int64_t* embed_ind, const ForwardScratch& sc, double* diff_acc, float* sums, float* counts,
-                       float* dbg_scores, cudaStream_t st) {
+                       float* dbg_scores, cudaStream_t st, unsigned long long* n_launches = nullptr) {
     const int DB = dim / 64, KL = tcw_slice(dim, n_embed), n_slices = n_embed / KL;
-    if (n_slices > 1 && !sc.partial) return 1;
+    // sliced codebook: convert x once (k_convert_wide), then stream ready-made operand stages.  Measured on B200 at
+    // N = 524 288: with two slices the extra pass over x costs more than converting twice (D = 256, K = 512: 0.53 vs 0.49 ms),
+    // from four slices on it wins (D = 256, K = 8192: 6.15 -> 2.68 ms)
+    const bool pre = n_slices > 2;
+    if (pre && (!sc.partial || !sc.wide_a)) return 1;
     CUtensorMap tmap;
-    if (tcw_encode_tmap(&tmap, x, L.n_rows, dim)) {
+    memset(&tmap, 0, sizeof(tmap));
+    if (!pre && tcw_encode_tmap(&tmap, x, L.n_rows, dim)) {
         fprintf(stderr, "vqb200: cuTensorMapEncodeTiled failed for x [%lld, %d]\n", (long long)L.n_rows, dim);
         return 1;
     }
-    for (int sl = 0; sl < n_slices; ++sl) {
-        tcw::WParams prm;
-        prm.tmap = tmap;
-        prm.x = x; prm.n_rows = L.n_rows; prm.KL = KL; prm.K_total = n_embed;
-        prm.image = cb.tc + (size_t)sl * tcw::wimage_bytes(KL, DB); prm.cbT = cb.cbT;
-        prm.quantize = quantize; prm.embed_ind = embed_ind; prm.diff_acc = diff_acc;
-        prm.stat_sums = sums; prm.stat_counts = counts;
-        prm.flagged_count = sc.flagged_count; prm.flagged_rows = sc.flagged_rows; prm.dbg_scores = dbg_scores;
-        prm.cA = tc::bound_cA(1); prm.cB = tcw::bound_cB(DB);
-        prm.code_base = sl * KL; prm.partial = n_slices > 1 ? sc.partial : nullptr;
-        prm.pass_first = sl == 0; prm.pass_last = sl == n_slices - 1;
-        int rc;
-        if (DB == 2) {
-            if (KL == 512) rc = dbg_scores ? tcw_launch<2, 1, true>(prm, st) : tcw_launch<2, 1, false>(prm, st);
-            else rc = dbg_scores ? tcw_launch<2, 3, true>(prm, st) : tcw_launch<2, 3, false>(prm, st);
-        } else {
-            rc = dbg_scores ? tcw_launch<4, 1, true>(prm, st) : tcw_launch<4, 1, false>(prm, st);
+    // Row chunks whose bf16 image fits in L2 (all slices of a chunk back to back, so that only the first slice reads it from
+    // HBM) were measured and are OFF by default: 48 / 64 / 96 MB chunks were 5-20 % slower than whole-batch passes (more
+    // wave tails and launches; the A stream is bound by the 64 KB of stages in flight per SM, not by HBM).
+    static const int64_t chunk_mb = [] { const char* e = getenv("VQB200_TCW_CHUNK_MB"); return (int64_t)(e ? atoi(e) : 0); }();
+    int64_t chunk_rows = L.n_rows;
+    if (pre && chunk_mb > 0) {
+        chunk_rows = std::max<int64_t>(tc::TILE_M, (chunk_mb << 20) / ((int64_t)dim * 2) / tc::TILE_M * tc::TILE_M);
+        const int64_t per_wave = (int64_t)tc_num_sms() * tc::TILE_M;             // whole waves of tiles
+        if (chunk_rows > per_wave) chunk_rows = chunk_rows / per_wave * per_wave;
+    }
+    for (int64_t r0 = 0; r0 < L.n_rows; r0 += chunk_rows) {
+        const int64_t rows = std::min(chunk_rows, L.n_rows - r0);
+        const int64_t t0 = r0 / tc::TILE_M;
+        if (pre) {
+            const int64_t tiles = (rows + tc::TILE_M - 1) / tc::TILE_M;
+            const unsigned grid = (unsigned)std::min<int64_t>(tiles * 8, (int64_t)tc_num_sms() * 16);
+            unsigned char* a = sc.wide_a + (size_t)t0 * DB * tcw::A_STAGE;
+            unsigned char* m = sc.wide_m + (size_t)t0 * tcw::AM_STAGE;
+            float* nr = sc.wide_norm + (size_t)t0 * tc::TILE_M;
+            cudaError_t e = DB == 2 ? launch_pdl(tcw::k_convert_wide<2>, dim3(grid), dim3(256), 0, st, x + r0 * dim, rows, a, m, nr)
+                                    : launch_pdl(tcw::k_convert_wide<4>, dim3(grid), dim3(256), 0, st, x + r0 * dim, rows, a, m, nr);
+            if (e != cudaSuccess) return 1;
+            if (n_launches) ++*n_launches;
         }
-        if (rc) return rc;
+        for (int sl = 0; sl < n_slices; ++sl) {
+            tcw::WParams prm;
+            prm.tmap = tmap;
+            prm.x = x + r0 * dim; prm.n_rows = rows; prm.KL = KL; prm.K_total = n_embed; prm.row_base = r0;
+            prm.image = cb.tc + (size_t)sl * tcw::wimage_bytes(KL, DB); prm.cbT = cb.cbT;
+            prm.quantize = quantize ? quantize + r0 * dim : nullptr; prm.embed_ind = embed_ind + r0; prm.diff_acc = diff_acc;
+            prm.stat_sums = sums; prm.stat_counts = counts;
+            prm.flagged_count = sc.flagged_count; prm.flagged_rows = sc.flagged_rows;
+            prm.dbg_scores = dbg_scores ? dbg_scores + r0 * n_embed : nullptr;
+            prm.cA = tc::bound_cA(1); prm.cB = tcw::bound_cB(DB);
+            prm.code_base = sl * KL; prm.partial = n_slices > 1 ? sc.partial + r0 : nullptr;
+            prm.pass_first = sl == 0; prm.pass_last = sl == n_slices - 1;
+            prm.a_img = pre ? sc.wide_a + (size_t)t0 * DB * tcw::A_STAGE : nullptr;
+            prm.m_img = pre ? sc.wide_m + (size_t)t0 * tcw::AM_STAGE : nullptr;
+            prm.norms = pre ? sc.wide_norm + (size_t)t0 * tc::TILE_M : nullptr;
+            int rc;
+            if (pre) {
+                if (DB == 2) rc = dbg_scores ? tcw_launch<2, 1, true, true>(prm, st) : tcw_launch<2, 1, false, true>(prm, st);
+                else rc = dbg_scores ? tcw_launch<4, 1, true, true>(prm, st) : tcw_launch<4, 1, false, true>(prm, st);
+            } else if (DB == 2) {
+                if (KL == 512) rc = dbg_scores ? tcw_launch<2, 1, true, false>(prm, st) : tcw_launch<2, 1, false, false>(prm, st);
+                else rc = dbg_scores ? tcw_launch<2, 3, true, false>(prm, st) : tcw_launch<2, 3, false, false>(prm, st);
+            } else {
+                rc = dbg_scores ? tcw_launch<4, 1, true, false>(prm, st) : tcw_launch<4, 1, false, false>(prm, st);
+            }
+            if (rc) return rc;
+            if (n_launches) ++*n_launches;
+        }
     }
     return 0;
 }

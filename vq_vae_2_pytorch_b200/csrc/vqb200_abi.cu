@@ -132,11 +132,12 @@ int forward_impl(const float* d_x, const RowLayout& L, int dim, int n_embed, con
         if (use_tc) {
             // tensor-core filter + fused output for certified rows; flagged rows -> exact SIMT fix-up (one launch:
             // re-score, gather / output / loss of those rows, loss finalisation)
+            unsigned long long wide_launches = 0;
             int rc = wide ? tcw_forward(d_x, L, dim, n_embed, cb, d_quantize, d_ind, sc, d_diff ? sc.diff_acc : nullptr, sums,
-                                        counts, dbg_scores, st)
+                                        counts, dbg_scores, st, &wide_launches)
                           : tc_forward(d_x, L, dim, n_embed, cb, d_quantize, d_ind, sc, d_diff ? sc.diff_acc : nullptr, sums,
                                        counts, dbg_scores, st, prof, nsplit, nullptr, (nchw && stats_kernel) ? d_x_dense : nullptr);
-            g_launches.fetch_add(wide ? (unsigned long long)(n_embed / tcw_slice(dim, n_embed)) : 1ull);
+            g_launches.fetch_add(wide ? wide_launches : 1ull);
             if (rc) return cuda_fail(cudaGetLastError());
             VQ_CUDA(launch_pdl(k_fixup, dim3(sms), dim3(AS_THREADS), gsmem, st, d_x, L, dim, n_embed, cb.cbT, cb.ee, d_ind,
                                d_quantize, d_diff ? sc.diff_acc : nullptr, sums, counts, sc.flagged_rows, sc.flagged_count,
