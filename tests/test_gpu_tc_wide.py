@@ -14,7 +14,8 @@ from test_gpu_tc import tc_scores
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
-SHAPES = [(128, 512), (128, 256), (256, 256), (256, 512), (128, 1024)]     # (D, K): resident, small, sliced x2 ...
+# (D, K): one launch (resident image) / two slices (x converted per slice) / four slices (x converted once, operand stages streamed)
+SHAPES = [(128, 512), (128, 256), (256, 256), (256, 512), (128, 1024), (128, 2048), (256, 1024)]
 
 
 def test_wide_shapes_are_reported_as_tensor_core_shapes():

@@ -19,7 +19,9 @@ namespace tcw {
 using namespace tc;
 
 constexpr int AS_CONV = 2, AS_PRE = 4;       // bf16 A stages (one 64-dim block of a 128-row tile each)
-constexpr uint32_t A_STAGE = 16384u, AM_STAGE = 4096u, X_STAGE = TILE_M * 64 * 4;
+constexpr uint32_t A_STAGE = 16384u, AM_STAGE = 4096u;
+constexpr uint32_t X_ROWS = 64, X_STAGE = X_ROWS * 64 * 4;   // x stage = HALF a block (64 rows x 64 dims fp32): the upper half is
+                                                             // reloaded while the converters still work on the lower half
 
 __host__ __device__ inline size_t wimage_off_misc(int KL, int DB) { return (size_t)KL * 128 * DB; }
 __host__ __device__ inline size_t wimage_off_enorm(int KL, int DB) { return (size_t)KL * (128 * DB + 32); }
@@ -115,7 +117,7 @@ struct Plan {
 };
 
 struct WParams {
-    alignas(64) CUtensorMap tmap;    // x as a 2-D tensor [row][dim], box = 128 rows x 64 dims
+    alignas(64) CUtensorMap tmap;    // x as a 2-D tensor [row][dim], box = 64 rows x 64 dims
     const float* x;
     int64_t n_rows;
     int KL;                          // codes in this launch (256 or 512)
@@ -250,11 +252,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tcw(const __grid_constant__ W
                         }
                     }
                 } else {
-                    for (int b = 0; b < DB; ++b) {
-                        const uint32_t g = it * DB + b, s = g % XS, ph = (g / XS) & 1u;
+                    for (int bh = 0; bh < 2 * DB; ++bh) {            // (block, half) in conversion order
+                        const uint32_t g = it * 2u * DB + bh, s = g % XS, ph = (g / XS) & 1u;
                         mbar_wait(bar(WB_XE + s), ph ^ 1u);
                         mbar_expect_tx(bar(WB_XF + s), X_STAGE);     // rows past the end are zero-filled and still counted
-                        tma_load_2d(sX + s * X_STAGE, &p.tmap, b * 64, (int)(t * TILE_M), bar(WB_XF + s), keep);
+                        tma_load_2d(sX + s * X_STAGE, &p.tmap, (bh >> 1) * 64, (int)(t * TILE_M + (bh & 1) * X_ROWS), bar(WB_XF + s), keep);
                     }
                 }
             }
@@ -292,33 +294,35 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tcw(const __grid_constant__ W
     } else if (warp >= W_CONV) {
         // ================= converters: one fp32 [128][64] block -> bf16 K-major A stage ==========================
         reg_dec<56>();
-        const int cw = warp - W_CONV;            // rows cw*32 .. cw*32+31
+        const int cw = warp - W_CONV;            // rows h*64 + cw*16 .. +15 of both halves h of a block
         const int half = lane >> 4, q4 = lane & 15;
         const uint32_t conv_iter = PRE ? 0u : n_iter;             // PRE: nothing to convert
+        // row (within the tile) handled in trip gi (0..3: half gi >> 1), slot u, by this half-warp
+        auto row_of = [&](int gi, int u) { return (gi >> 1) * 64 + cw * 16 + 2 * (4 * (gi & 1) + u) + half; };
         for (uint32_t it = 0; it != conv_iter; ++it) {
-            float row_sq = 0.f;                  // ||x||^2 of row cw*32 + 2*q4 + half, accumulated over the blocks
+            float row_sq = 0.f;                  // ||x||^2 of row row_of(q4 >> 2, q4 & 3), accumulated over the blocks
             for (int b = 0; b < DB; ++b) {
-                const uint32_t g = it * DB + b, sx = g % XS, phx = (g / XS) & 1u, sa = g % AS, pha = (g / AS) & 1u;
-                mbar_wait(bar(WB_XF + sx), phx);
+                const uint32_t g = it * DB + b, sa = g % AS, pha = (g / AS) & 1u;
                 mbar_wait(bar(WB_AE + sa), pha ^ 1u);
-                const unsigned char* xs = sm + P.off_x() + sx * X_STAGE;
                 unsigned char* ah = sm + P.off_a() + sa * A_STAGE;
                 float my_sq = 0.f;
 #pragma unroll 1
-                for (int g4 = 0; g4 < 4; ++g4) {          // 4 row pairs per trip
+                for (int g4 = 0; g4 < 4; ++g4) {          // 4 row pairs per trip; trips 0,1: upper half, 2,3: lower half
+                    const uint32_t gx = 2u * g + (uint32_t)(g4 >> 1), sx = gx % XS, phx = (gx / XS) & 1u;
+                    if ((g4 & 1) == 0) mbar_wait(bar(WB_XF + sx), phx);
+                    const unsigned char* xs = sm + P.off_x() + sx * X_STAGE;
                     float4 v[4];
                     float sq[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
-                        v[u] = *reinterpret_cast<const float4*>(xs + (cw * 32 + 2 * (4 * g4 + u) + half) * 256 + q4 * 16);
+                        v[u] = *reinterpret_cast<const float4*>(xs + (row_of(g4, u) & 63) * 256 + q4 * 16);
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        const int r = cw * 32 + 2 * (4 * g4 + u) + half;
-                        *reinterpret_cast<uint2*>(ah + sw128_off((uint32_t)r, (uint32_t)q4 * 4)) =
+                        *reinterpret_cast<uint2*>(ah + sw128_off((uint32_t)row_of(g4, u), (uint32_t)q4 * 4)) =
                             make_uint2(pack_bf16(v[u].x, v[u].y), pack_bf16(v[u].z, v[u].w));
                         sq[u] = fmaf(v[u].x, v[u].x, fmaf(v[u].y, v[u].y, fmaf(v[u].z, v[u].z, v[u].w * v[u].w)));
                     }
-                    {   // transposing butterfly: lane (half, q4) ends with the sum of row 2*q4 + half
+                    {   // transposing butterfly: lane (half, q4) ends with the sum of the row of trip q4 >> 2, slot q4 & 3
                         const bool up = (q4 & 2) != 0;
                         const float s0 = up ? sq[0] : sq[2], k0 = up ? sq[2] : sq[0];
                         const float s1 = up ? sq[1] : sq[3], k1 = up ? sq[3] : sq[1];
@@ -331,10 +335,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tcw(const __grid_constant__ W
                         tot += __shfl_xor_sync(0xffffffffu, tot, 8);
                         if ((q4 >> 2) == g4) my_sq = tot;
                     }
+                    if (g4 & 1) {                 // this half of the block is in registers / the A stage: free its x stage
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar(WB_XE + sx));
+                    }
                 }
                 row_sq += my_sq;
                 if (b == DB - 1) {
-                    const int r = cw * 32 + 2 * q4 + half;
+                    const int r = row_of(q4 >> 2, q4 & 3);
                     const float nx = sqrtf(row_sq);
                     float o1, o2, o3;
                     split3(row_sq * 1.001953125f, o1, o2, o3);            // off_i = ||x||^2 (1 + 2^-9)
@@ -345,7 +353,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tcw(const __grid_constant__ W
                 }
                 fence_async_smem();
                 __syncwarp();
-                if (lane == 0) { mbar_arrive(bar(WB_AF + sa)); mbar_arrive(bar(WB_XE + sx)); }
+                if (lane == 0) mbar_arrive(bar(WB_AF + sa));
             }
         }
     } else if (warp < W_OUT) {
@@ -529,7 +537,7 @@ inline int tcw_encode_tmap(CUtensorMap* tm, const float* x, int64_t n_rows, int 
     if (!encode) return 1;
     cuuint64_t gdim[2] = {(cuuint64_t)dim, (cuuint64_t)n_rows};
     cuuint64_t gstr[1] = {(cuuint64_t)dim * 4u};
-    cuuint32_t box[2] = {64u, (cuuint32_t)tc::TILE_M};
+    cuuint32_t box[2] = {64u, (cuuint32_t)tcw::X_ROWS};
     cuuint32_t estr[2] = {1u, 1u};
     return encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS;
@@ -620,10 +628,10 @@ inline int tcw_forward(const float* x, const RowLayout& L, int dim, int n_embed,
                 if (DB == 2) rc = dbg_scores ? tcw_launch<2, 1, true, true>(prm, st) : tcw_launch<2, 1, false, true>(prm, st);
                 else rc = dbg_scores ? tcw_launch<4, 1, true, true>(prm, st) : tcw_launch<4, 1, false, true>(prm, st);
             } else if (DB == 2) {
-                if (KL == 512) rc = dbg_scores ? tcw_launch<2, 1, true, false>(prm, st) : tcw_launch<2, 1, false, false>(prm, st);
-                else rc = dbg_scores ? tcw_launch<2, 3, true, false>(prm, st) : tcw_launch<2, 3, false, false>(prm, st);
+                if (KL == 512) rc = dbg_scores ? tcw_launch<2, 2, true, false>(prm, st) : tcw_launch<2, 2, false, false>(prm, st);
+                else rc = dbg_scores ? tcw_launch<2, 4, true, false>(prm, st) : tcw_launch<2, 4, false, false>(prm, st);
             } else {
-                rc = dbg_scores ? tcw_launch<4, 1, true, false>(prm, st) : tcw_launch<4, 1, false, false>(prm, st);
+                rc = dbg_scores ? tcw_launch<4, 2, true, false>(prm, st) : tcw_launch<4, 2, false, false>(prm, st);
             }
             if (rc) return rc;
             if (n_launches) ++*n_launches;
