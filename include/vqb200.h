@@ -146,6 +146,15 @@ int vqb200_quantize_backward(const float* d_x, const int64_t* d_embed_ind, const
 int vqb200_embed_code(const int64_t* d_embed_id, int64_t n_rows, const void* d_codebook,
                       int32_t dim, int32_t n_embed, float* d_out, int32_t* d_status, void* stream);
 
+/* Index egress for code extraction (extract_code.py:23-33 copies the int64 `id_t` / `id_b` of every batch to the host and
+ * pickles them per image; dataset.py:45-51 reads them back).  n_embed <= 65536 fits 16 bits: pack embed_ind [n] int64 into
+ * out_bytes = 2 (uint16) or 4 (int32) per code on the device so that the D2H copy moves 4x / 2x fewer bytes.  d_status
+ * (1 int32, may be NULL) is set non-zero when an index lies outside [0, n_embed).  Both pointers 16-byte aligned.       */
+int vqb200_pack_indices(const int64_t* d_embed_ind, int64_t n, int32_t n_embed, int32_t out_bytes, void* d_out,
+                        int32_t* d_status, void* stream);
+/* the inverse (codes uploaded for `embed_code` / `decode_code`, vqvae.py:251-259, sample.py:92-97): widen to int64 */
+int vqb200_unpack_indices(const void* d_codes, int64_t n, int32_t in_bytes, int64_t* d_embed_id, void* stream);
+
 /* ---- diagnostics ---------------------------------------------------------------------------------- */
 /* Runs the tcgen05 engine on contiguous rows and additionally dumps the tensor-core scores
  * (certified lower bounds of ||x_n - e_k||^2 + row offset) to d_scores [n_rows, n_embed]; the tests use

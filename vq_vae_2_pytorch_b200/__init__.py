@@ -3,5 +3,6 @@ alehdaghi/vq-vae-2-pytorch `vqvae.Quantize`).  See DESIGN.md / INTEGRATION.md.""
 from .quantize import Quantize, row_layout  # noqa: F401
 from . import distributed  # noqa: F401
 from . import _native  # noqa: F401
+from .egress import CodeEgress, unpack_codes  # noqa: F401
 
-__all__ = ["Quantize", "row_layout", "distributed"]
+__all__ = ["Quantize", "row_layout", "distributed", "CodeEgress", "unpack_codes"]

@@ -409,6 +409,34 @@ int vqb200_embed_code(const int64_t* d_embed_id, int64_t n_rows, const void* d_c
     return VQB200_OK;
 }
 
+int vqb200_pack_indices(const int64_t* d_embed_ind, int64_t n, int32_t n_embed, int32_t out_bytes, void* d_out,
+                        int32_t* d_status, void* stream) {
+    if (n < 0 || n_embed <= 0 || (out_bytes != 2 && out_bytes != 4)) return VQB200_EINVAL;
+    if (out_bytes == 2 && n_embed > 65536) return VQB200_EUNSUPPORTED;
+    if (n == 0) return VQB200_OK;
+    if (!d_embed_ind || !d_out) return VQB200_EINVAL;
+    if ((reinterpret_cast<uintptr_t>(d_embed_ind) & 15u) || (reinterpret_cast<uintptr_t>(d_out) & 15u)) return VQB200_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d_status) VQ_CUDA(cudaMemsetAsync(d_status, 0, sizeof(int32_t), st));
+    const unsigned blocks = (unsigned)((n + 1023) / 1024);
+    if (out_bytes == 2) k_pack_indices<unsigned short><<<blocks, 256, 0, st>>>(d_embed_ind, n, n_embed, (unsigned short*)d_out, d_status);
+    else k_pack_indices<int><<<blocks, 256, 0, st>>>(d_embed_ind, n, n_embed, (int*)d_out, d_status);
+    VQ_LAUNCH_CHECK();
+    return VQB200_OK;
+}
+
+int vqb200_unpack_indices(const void* d_codes, int64_t n, int32_t in_bytes, int64_t* d_embed_id, void* stream) {
+    if (n < 0 || (in_bytes != 2 && in_bytes != 4)) return VQB200_EINVAL;
+    if (n == 0) return VQB200_OK;
+    if (!d_codes || !d_embed_id) return VQB200_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    if (in_bytes == 2) k_unpack_indices<unsigned short><<<blocks, 256, 0, st>>>((const unsigned short*)d_codes, n, d_embed_id);
+    else k_unpack_indices<int><<<blocks, 256, 0, st>>>((const int*)d_codes, n, d_embed_id);
+    VQ_LAUNCH_CHECK();
+    return VQB200_OK;
+}
+
 int vqb200_debug_tc_scores(const float* d_x, int64_t n_rows, int32_t dim, int32_t n_embed, const void* d_codebook,
                            int64_t* d_embed_ind, float* d_scores, int32_t* d_flagged_count, void* d_scratch,
                            void* stream) {
