@@ -129,3 +129,20 @@ def test_wide_engine_on_deep_fork_shapes_with_permuted_input():
         if int((ia != ib).sum()) == 0:
             assert torch.equal(qa, qb)
             assert col_rel_err(a.embed_avg.cpu().numpy(), b.embed_avg.cpu().numpy()) <= REL_TOL
+
+
+@pytest.mark.parametrize("D,K", [(128, 512), (256, 512), (256, 1024)])
+@pytest.mark.parametrize("N", [1, 63, 65, 129])
+def test_wide_engine_tiny_inputs(D, K, N):
+    """Fewer rows than one TMA box / one tile (the tensor map's row extent is smaller than its box)."""
+    torch.manual_seed(17)
+    a = vq.Quantize(D, K, engine="tcgen05").to(DEV).eval()
+    b = vq.Quantize(D, K, engine="simt").to(DEV).eval()
+    b.load_state_dict(a.state_dict())
+    pick = torch.randint(0, K, (N,), device=DEV)
+    x = (a.embed.t()[pick] + 0.1 * torch.randn(N, D, device=DEV)).contiguous()
+    qa, da, ia = a(x)
+    qb, db, ib = b(x)
+    assert torch.equal(ia, pick) and torch.equal(ib, pick)
+    assert torch.equal(qa, qb)
+    assert abs(float(da) - float(db)) <= 1e-6 * abs(float(db))
