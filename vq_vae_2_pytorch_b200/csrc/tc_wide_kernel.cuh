@@ -18,7 +18,13 @@ namespace vqb200 {
 namespace tcw {
 using namespace tc;
 
-constexpr int AS_CONV = 2, AS_PRE = 4;       // bf16 A stages (one 64-dim block of a 128-row tile each)
+constexpr int AS_CONV = 2;                   // bf16 A stages (one 64-dim block of a 128-row tile each) filled by the converters
+// streamed-operand kernels (PRE): 4 stages.  At DB = 2 (four scan groups) three groups hand partial results to
+// the merging group through ONE slot of 3 x 2 KB, and the code norms are read from global memory instead of a 2-KB copy.
+__host__ __device__ constexpr int as_pre(int) { return 4; }
+__host__ __device__ constexpr int n_partials(bool pre, int DB) { return (pre && DB == 2) ? 3 : 1; }
+__host__ __device__ constexpr int n_part_slots(bool pre, int DB) { return (pre && DB == 2) ? 1 : 2; }
+__host__ __device__ constexpr bool enorm_in_smem(bool pre, int DB) { return !(pre && DB == 2); }
 constexpr uint32_t A_STAGE = 16384u, AM_STAGE = 4096u;
 constexpr uint32_t X_ROWS = 64, X_STAGE = X_ROWS * 64 * 4;   // x stage = HALF a block (64 rows x 64 dims fp32): the upper half is
                                                              // reloaded while the converters still work on the lower half
@@ -103,16 +109,16 @@ __global__ void __launch_bounds__(256) k_convert_wide(const float* __restrict__ 
 }
 
 struct Plan {
-    int KL, DB, XS, AS;
+    int KL, DB, XS, AS, NP, NSLOT, ENORM;
     __host__ __device__ uint32_t off_bmisc() const { return (uint32_t)KL * 128u * (uint32_t)DB; }
     __host__ __device__ uint32_t off_a() const { return off_bmisc() + (uint32_t)KL * 32u; }
     __host__ __device__ uint32_t off_am() const { return off_a() + (uint32_t)AS * A_STAGE; }
     __host__ __device__ uint32_t off_x() const { return off_am() + 2u * AM_STAGE; }
     __host__ __device__ uint32_t off_small() const { return off_x() + (uint32_t)XS * X_STAGE; }
-    __host__ __device__ uint32_t off_rownorm() const { return off_small() + (uint32_t)KL * 4u; }
+    __host__ __device__ uint32_t off_rownorm() const { return off_small() + (ENORM ? (uint32_t)KL * 4u : 0u); }
     __host__ __device__ uint32_t off_codes() const { return off_rownorm() + NORM_RING * TILE_M * 4u; }
     __host__ __device__ uint32_t off_parts() const { return off_codes() + RES_RING * TILE_M * 4u; }
-    __host__ __device__ uint32_t off_bars() const { return off_parts() + 2u * TILE_M * 16u; }
+    __host__ __device__ uint32_t off_bars() const { return off_parts() + (uint32_t)NSLOT * (uint32_t)NP * TILE_M * 16u; }
     __host__ __device__ uint32_t total() const { return off_bars() + 384u + 1024u /* base alignment slack */; }
 };
 
@@ -180,14 +186,21 @@ __device__ __forceinline__ void issue_misc(uint32_t d_tmem, uint32_t am_lo, uint
 template <int DB, int XS, bool DBG, bool PRE>
 __global__ void __launch_bounds__(THREADS, 1) k_vq_tcw(const __grid_constant__ WParams p) {
     constexpr int D = 64 * DB;
-    constexpr int AS = PRE ? AS_PRE : AS_CONV;
+    constexpr int AS = PRE ? as_pre(DB) : AS_CONV;
+    constexpr int NP = n_partials(PRE, DB), NSLOT = n_part_slots(PRE, DB);
+    constexpr bool ENORM_S = enorm_in_smem(PRE, DB);
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     unsigned char* sm = smem_raw + (base - raw);
     const int KL = p.KL;
     const int U = KL / UNIT_N;                  // accumulator units per tile: 2 or 4
-    const Plan P{KL, DB, PRE ? 0 : XS, AS};
+    // Streamed passes that write no outputs (every slice but the last) have idle output warps: they join as scan groups 2 and
+    // 3, so that each of the four 128-column units of a tile is scanned by its own warpgroup (four scanning warps per
+    // scheduler instead of two: the scan is bound by TMEM-load / dependent-minimum latency).
+    const bool helper = PRE && DB == 2 && !DBG && U == 4 && !p.pass_last;
+    const int NGRP = helper ? 4 : 2;
+    const Plan P{KL, DB, PRE ? 0 : XS, AS, NP, NSLOT, ENORM_S ? 1 : 0};
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     const uint32_t sB = base, sBm = base + P.off_bmisc(), sA = base + P.off_a(), sAm = base + P.off_am(), sX = base + P.off_x();
@@ -210,7 +223,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tcw(const __grid_constant__ W
         for (int s = 0; s < AS; ++s) { mbar_init(bar(WB_AF + s), PRE ? 1 : 4); mbar_init(bar(WB_AE + s), 1); }
         for (int s = 0; s < NBUF; ++s) { mbar_init(bar(WB_TF + s), 1); mbar_init(bar(WB_TE + s), 4); }
         for (int s = 0; s < RES_RING; ++s) { mbar_init(bar(WB_RF + s), 4); mbar_init(bar(WB_RE + s), 8); }
-        for (int s = 0; s < 2; ++s) { mbar_init(bar(WB_PF + s), 4); mbar_init(bar(WB_PE + s), 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(bar(WB_PF + s), helper ? 12 : 4); mbar_init(bar(WB_PE + s), 4); }
         fence_barrier_init();
     }
     if (warp == W_MMA) tmem_alloc(smem_u32(tmem_ptr_s), 512);
@@ -220,7 +233,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tcw(const __grid_constant__ W
     int bad = 0;
     for (int i = threadIdx.x; i < KL; i += THREADS) {
         const float ne = reinterpret_cast<const float*>(p.image + wimage_off_enorm(KL, DB))[i];
-        enorm_s[i] = ne;
+        if (ENORM_S) enorm_s[i] = ne;
         bad |= !(ne < 1.0e18f);                  // NaN / inf / absurd norms: certify nothing, the exact path decides
     }
     tc_fence_before();
@@ -268,6 +281,27 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tcw(const __grid_constant__ W
         const uint32_t b_lo0 = desc_lo(sB), bm_lo0 = desc_lo(sBm);
         for (uint32_t it = 0; it < n_iter; ++it) {
             const uint32_t am_lo = desc_lo(sAm + (it & 1u) * AM_STAGE);
+            if constexpr (PRE && DB * 2 <= AS) {
+                // Streamed operands and two whole tiles fit in the A ring: UNIT-outer order.  The units of a tile finish one
+                // after the other, every TMEM buffer runs its own scan -> MMA -> scan cycle (with four scan groups the period
+                // is one unit scan + one unit of MMAs instead of the scans of a whole tile).
+                for (int b = 0; b < DB; ++b) {
+                    const uint32_t g = it * DB + b;
+                    mbar_wait(bar(WB_AF + g % AS), (g / AS) & 1u);
+                }
+                tc_fence_after();
+                for (int u = 0; u < U; ++u) {
+                    const uint32_t uc = it * (uint32_t)U + (uint32_t)u, buf = uc % NBUF, pht = (uc / NBUF) & 1u;
+                    mbar_wait(bar(WB_TE + buf), pht ^ 1u);
+                    tc_fence_after();
+                    for (int b = 0; b < DB; ++b)
+                        issue_block4(tmem_base + buf * UNIT_N, desc_lo(sA + ((it * DB + b) % AS) * A_STAGE),
+                                     b_lo0 + ((((uint32_t)b * KL + (uint32_t)u * UNIT_N) * 128u) >> 4), b != 0 ? 1u : 0u);
+                    issue_misc(tmem_base + buf * UNIT_N, am_lo, bm_lo0 + (((uint32_t)u * UNIT_N * 32u) >> 4));
+                    commit_elected<false>(bar(WB_TF + buf));
+                }
+                for (int b = 0; b < DB; ++b) commit_elected<false>(bar(WB_AE + (it * DB + b) % AS));
+            } else
             for (int b = 0; b < DB; ++b) {
                 const uint32_t g = it * DB + b, sa = g % AS, pha = (g / AS) & 1u;
                 mbar_wait(bar(WB_AF + sa), pha);
@@ -293,7 +327,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tcw(const __grid_constant__ W
         reg_dec<24>();
     } else if (warp >= W_CONV) {
         // ================= converters: one fp32 [128][64] block -> bf16 K-major A stage ==========================
-        reg_dec<56>();
+        if constexpr (PRE) reg_dec<24>(); else reg_dec<56>();
         const int cw = warp - W_CONV;            // rows h*64 + cw*16 .. +15 of both halves h of a block
         const int half = lane >> 4, q4 = lane & 15;
         const uint32_t conv_iter = PRE ? 0u : n_iter;             // PRE: nothing to convert
@@ -356,10 +390,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tcw(const __grid_constant__ W
                 if (lane == 0) mbar_arrive(bar(WB_AF + sa));
             }
         }
-    } else if (warp < W_OUT) {
+    } else if (warp < W_OUT || helper) {
         // ================= epilogue: TMEM -> two-class min scan -> certified arg-min (as tc::k_vq_tc) =============
-        reg_inc<128>();
-        const int g = warp >> 2;
+        // setmaxnreg draws from the CTA's LAUNCH allocation (768 x 80 registers): four scanning warpgroups get 104 each
+        // (4 x 128 x 104 + 2 x 128 x 24 = 59 392 <= 61 440); one immediate for every path that reaches the scan code
+        if constexpr (PRE && DB == 2) reg_inc<104>(); else reg_inc<128>();
+        const int g = warp >> 2;                 // scan group 0 .. NGRP-1; group 1 merges and certifies
         const int wq = warp & 3;
         const int row_in_tile = wq * 32 + lane;
         const uint32_t lane_base = tmem_base + ((uint32_t)(wq * 32) << 16);
@@ -379,7 +415,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tcw(const __grid_constant__ W
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar(WB_TE + buf));
             }
-            if (U == 4) {   // second unit (codes 128*(g+2) ..)
+            if (U == 4 && !helper) {   // second unit (codes 128*(g+2) ..)
                 const uint32_t uc = it * 4u + (uint32_t)g + 2u, buf = uc % NBUF, pht = (uc / NBUF) & 1u;
                 mbar_wait(bar(WB_TF + buf), pht);
                 tc_fence_after();
@@ -395,25 +431,31 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tcw(const __grid_constant__ W
                 k1 = (v < UNIT_N ? g : g + 2) * UNIT_N + (v & (UNIT_N - 1));
             }
             {
-                const uint32_t ps = it & 1u, php = (it >> 1) & 1u;
-                if (g == 0) {                    // hand this group's result to group 1
+                const uint32_t ps = it % NSLOT, php = (it / NSLOT) & 1u;
+                if (g != 1) {                    // hand this group's result to group 1 (slot 0: group 0, slots 1, 2: helpers)
                     mbar_wait(bar(WB_PE + ps), php ^ 1u);
-                    part_s[ps * TILE_M + row_in_tile] = make_float4(m1, m2, __int_as_float(k1), 0.f);
+                    part_s[(ps * NP + (g == 0 ? 0 : g - 1)) * TILE_M + row_in_tile] = make_float4(m1, m2, __int_as_float(k1), 0.f);
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar(WB_PF + ps));
                     continue;
                 }
                 mbar_wait(bar(WB_PF + ps), php);
-                const float4 o = part_s[ps * TILE_M + row_in_tile];
+                float4 o[NP];
+#pragma unroll
+                for (int q = 0; q < NP; ++q) o[q] = part_s[(ps * NP + q) * TILE_M + row_in_tile];
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar(WB_PE + ps));
-                const int ko = __float_as_int(o.z);
-                m2 = fminf(fminf(o.y, m2), fmaxf(o.x, m1));
-                const bool take_other = (o.x < m1) || (o.x == m1 && ko < k1);
-                if (take_other) { m1 = o.x; k1 = ko; }
+#pragma unroll
+                for (int q = 0; q < NP; ++q) {
+                    if (q >= NGRP - 1) break;
+                    const int ko = __float_as_int(o[q].z);
+                    m2 = fminf(fminf(o[q].y, m2), fmaxf(o[q].x, m1));
+                    const bool take_other = (o[q].x < m1) || (o[q].x == m1 && ko < k1);
+                    if (take_other) { m1 = o[q].x; k1 = ko; }
+                }
             }
             const float xn = rownorm_s[(it % NORM_RING) * TILE_M + row_in_tile];
-            float en = enorm_s[k1 < KL ? k1 : 0];
+            float en = ENORM_S ? enorm_s[k1 < KL ? k1 : 0] : __ldg(reinterpret_cast<const float*>(p.image + wimage_off_enorm(KL, DB)) + (k1 < KL ? k1 : 0));
             const bool in_range = grow < p.n_rows;
             k1 += p.code_base;
             bool badrow = cb_bad;
@@ -430,6 +472,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tcw(const __grid_constant__ W
             }
             const float need = 2.f * (p.cA * BOUND_UP * xn * en + p.cB * (BOUND_UP * en * en + xn * xn));
             const bool certified = ((m2 - m1) > need) && (xn < 1.0e18f) && !badrow;   // NaN -> false
+            if (helper) continue;                // no outputs in this pass: the output warps are scanning
             const uint32_t rs = it % RES_RING, phr = (it / RES_RING) & 1u;
             mbar_wait(bar(WB_RE + rs), phr ^ 1u);
             int code = -2;
@@ -546,7 +589,8 @@ inline int tcw_encode_tmap(CUtensorMap* tm, const float* x, int64_t n_rows, int 
 template <int DB, int XS, bool DBG, bool PRE>
 inline int tcw_launch(const tcw::WParams& prm, cudaStream_t st) {
     auto kern = tcw::k_vq_tcw<DB, XS, DBG, PRE>;
-    const tcw::Plan P{prm.KL, DB, PRE ? 0 : XS, PRE ? tcw::AS_PRE : tcw::AS_CONV};
+    const tcw::Plan P{prm.KL, DB, PRE ? 0 : XS, PRE ? tcw::as_pre(DB) : tcw::AS_CONV, tcw::n_partials(PRE, DB), tcw::n_part_slots(PRE, DB),
+                       tcw::enorm_in_smem(PRE, DB) ? 1 : 0};
     const int smem = (int)P.total();
     static int configured = 0;
     if (configured < smem) {
