@@ -205,6 +205,17 @@ __device__ __forceinline__ void red_add_f32(float* p, float v) {
     asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): a lane that owns 32 contiguous bytes of a row touches ONE full sector per
+// instruction instead of two half sectors -- the per-lane row accesses of the NCHW variant are bound by L1TEX sector throughput
+__device__ __forceinline__ void ldg_nc_v8(const float* p, float (&v)[8]) {     // p 32-byte aligned
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p));
+}
+__device__ __forceinline__ void stg_v8(float* p, const float (&v)[8]) {        // p 32-byte aligned
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+
 // shared-memory matrix descriptors (cute::UMMA::SmemDescriptor bit layout), K-major operands
 __device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr) {   // rows of 128 B, 8-row atoms of 1024 B
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
@@ -724,10 +735,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const __grid_constant__ Pa
                         }
 #pragma unroll
                         for (int j = 0; j < 8; ++j) sq = fmaf(v[j], v[j], sq);
-                        if (xd) {                         // dense copy for the statistics kernel (merged into full sectors in L2)
-                            __stcg(xd + 2 * c, make_float4(v[0], v[1], v[2], v[3]));
-                            __stcg(xd + 2 * c + 1, make_float4(v[4], v[5], v[6], v[7]));
-                        }
+                        if (xd) stg_v8(reinterpret_cast<float*>(xd + 2 * c), v);   // dense copy for the statistics kernel: one full sector per lane
                     }
                     my_sq = sq;
                 }
@@ -927,12 +935,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const __grid_constant__ Pa
                         float* og = p.quantize ? p.quantize + base : nullptr;
                         const float* xsr = reinterpret_cast<const float*>(sm + P::off_x(K) + sx * P::X_STAGE) + d0 * TILE_M + r;
                         const float4* q4p = reinterpret_cast<const float4*>(p.cbT + (size_t)k * TC_D + d0);
-                        float4 qq[8];
+                        float qq[4][8];
 #pragma unroll
-                        for (int c = 0; c < 8; ++c) qq[c] = __ldg(q4p + c);
+                        for (int c = 0; c < 4; ++c) ldg_nc_v8(reinterpret_cast<const float*>(q4p) + 8 * c, qq[c]);   // 32 B per lane and instruction
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {
-                            const float qv[4] = {qq[c].x, qq[c].y, qq[c].z, qq[c].w};
+                            const float qv[4] = {qq[c >> 1][(c & 1) * 4], qq[c >> 1][(c & 1) * 4 + 1], qq[c >> 1][(c & 1) * 4 + 2], qq[c >> 1][(c & 1) * 4 + 3]};
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 const float xv = xsr[(c * 4 + j) * TILE_M];

@@ -103,6 +103,7 @@ int forward_impl(const float* d_x, const RowLayout& L, int dim, int n_embed, con
     // NCHW-physical rows consumed in place by the tensor-core kernel: the statistics kernel gathers rows by code, which
     // only coalesces on dense rows, so training needs the dense copy the kernel's converters can write on the side
     const bool nchw = use_tc && !tc_layout_dense(L, d_x, dim);
+    if (nchw && d_x_dense && (reinterpret_cast<uintptr_t>(d_x_dense) & 31u)) return VQB200_EINVAL;   // written with 256-bit stores
     if (nchw && stats_kernel && !d_x_dense) {
         if (engine == VQB200_ENGINE_TCGEN05 || engine == VQB200_ENGINE_TCGEN05_BF16) return VQB200_EUNSUPPORTED;
         use_tc = false;
