@@ -123,6 +123,17 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
     return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): a lane that owns 32 contiguous bytes of a row touches ONE full sector per
+// instruction instead of two half sectors -- the per-lane row accesses of the NCHW variant are bound by L1TEX sector throughput
+__device__ __forceinline__ void ldg_nc_v8(const float* p, float (&v)[8]) {     // p 32-byte aligned
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p));
+}
+__device__ __forceinline__ void stg_v8(float* p, const float (&v)[8]) {        // p 32-byte aligned
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -205,17 +205,6 @@ __device__ __forceinline__ void red_add_f32(float* p, float v) {
     asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 
-// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): a lane that owns 32 contiguous bytes of a row touches ONE full sector per
-// instruction instead of two half sectors -- the per-lane row accesses of the NCHW variant are bound by L1TEX sector throughput
-__device__ __forceinline__ void ldg_nc_v8(const float* p, float (&v)[8]) {     // p 32-byte aligned
-    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p));
-}
-__device__ __forceinline__ void stg_v8(float* p, const float (&v)[8]) {        // p 32-byte aligned
-    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
-                 :: "l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
-}
-
 // shared-memory matrix descriptors (cute::UMMA::SmemDescriptor bit layout), K-major operands
 __device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr) {   // rows of 128 B, 8-row atoms of 1024 B
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
