@@ -44,6 +44,8 @@ extern "C" {
 #define VQB200_ENODEVICE     -4   /* no sm_100 device                                               */
 
 /* assignment engines for vqb200_quantize_forward / vqb200_assign */
+/* tcgen05 coverage: dim 64 with n_embed 256 / 512 / k*512 <= 16384 (dense or NCHW-physical rows), and the wide engine
+ * for dim 128 (n_embed 256 or k*512) and dim 256 (n_embed k*256), n_embed <= 16384, dense rows (vqvae_deep.py:252,257). */
 #define VQB200_ENGINE_AUTO    0   /* tcgen05 path when the shape is covered, else exact SIMT        */
 #define VQB200_ENGINE_SIMT    1   /* exact fp32 SIMT distance kernel                                */
 #define VQB200_ENGINE_TCGEN05 2   /* TMA + tcgen05 split-bf16 filter with exact fp32 re-score       */
@@ -114,7 +116,7 @@ int vqb200_ema_update_p2p(const void* const* h_stats_ptrs, void* const* h_flag_p
  *   vqb200_ema_update on the statistics of this call (single-process training).  With several ranks the caller
  *   passes ema = 0, all-reduces d_stats (vqvae.py:58-59) and calls vqb200_ema_update itself.
  * d_cluster_size / d_embed_avg are only touched when the EMA runs.
- * d_x_dense (may be NULL): n_rows*dim floats of scratch.  With it, NCHW-physical rows (unit row stride, the
+ * d_x_dense (may be NULL): n_rows*dim floats of scratch, 32-byte aligned (written with 256-bit stores).  With it, NCHW-physical rows (unit row stride, the
  * permute(0,2,3,1) view of vqvae.py:227,235; whole 128-row tiles per image) are consumed IN PLACE by the tensor-core
  * kernel in training mode too: its converters write the dense copy the code-statistics kernel gathers from.     */
 int vqb200_quantize_step(const float* d_x, int64_t n_rows, int32_t dim, int32_t n_embed,
