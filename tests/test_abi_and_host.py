@@ -130,3 +130,24 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("no CPU or PyTorch fallback", ""), f"{f} mentions the oracle"
+
+
+def test_tensor_core_shape_coverage_table():
+    """vqb200_tc_supported is a pure host query (shape, layout, alignment): the coverage documented in include/vqb200.h."""
+    import ctypes as C
+    lib = _native.load()
+    p = C.c_void_p(0x10000)
+
+    def dense(d, k, ptr=p):
+        return lib.vqb200_tc_supported(ptr, 1000, d, k, 1000, 0, d, 1)
+
+    covered = [(64, 256), (64, 512), (64, 1024), (64, 16384), (128, 256), (128, 512), (128, 1024), (128, 16384),
+               (256, 256), (256, 512), (256, 768), (256, 16384)]
+    not_covered = [(64, 384), (64, 32768), (128, 384), (128, 768), (256, 384), (256, 32768), (192, 512), (32, 512), (64, 128)]
+    assert all(dense(d, k) == 1 for d, k in covered)
+    assert all(dense(d, k) == 0 for d, k in not_covered)
+    assert dense(64, 512, C.c_void_p(0x10004)) == 0                       # bulk copies / TMA need 16-byte alignment
+    # NCHW-physical rows (permute(0,2,3,1) of [B, D, 32, 32]): in place at dim 64 only; the wide engine wants dense rows
+    assert lib.vqb200_tc_supported(p, 4 * 1024, 64, 512, 1024, 64 * 1024, 1, 1024) == 1
+    assert lib.vqb200_tc_supported(p, 4 * 1024, 256, 512, 1024, 256 * 1024, 1, 1024) == 0
+    assert lib.vqb200_tc_supported(p, 0, 64, 512, 1, 0, 64, 1) == 0
