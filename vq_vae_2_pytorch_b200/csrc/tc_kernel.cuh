@@ -1094,7 +1094,11 @@ inline int tc_launch(const tc::Params& prm, cudaStream_t st) {
     using P = tc::Plan<NSPLIT, AS, XS, CTA2>;
     auto kern = tc::k_vq_tc<NSPLIT, AS, XS, DBG, CTA2, NCHW>;
     const int smem = (int)P::total(prm.K);
-    static int configured = 0;
+    // opt-in shared-memory size is a per-device function attribute: cache it per device (several GPUs in one process)
+    static int configured_dev[64] = {0};
+    int dev_id = 0;
+    if (cudaGetDevice(&dev_id) != cudaSuccess || dev_id < 0 || dev_id >= 64) dev_id = 0, configured_dev[0] = 0;
+    int& configured = configured_dev[dev_id];
     if (configured < smem) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 1;
         configured = smem;

@@ -592,7 +592,11 @@ inline int tcw_launch(const tcw::WParams& prm, cudaStream_t st) {
     const tcw::Plan P{prm.KL, DB, PRE ? 0 : XS, PRE ? tcw::as_pre(DB) : tcw::AS_CONV, tcw::n_partials(PRE, DB), tcw::n_part_slots(PRE, DB),
                        tcw::enorm_in_smem(PRE, DB) ? 1 : 0};
     const int smem = (int)P.total();
-    static int configured = 0;
+    // opt-in shared-memory size is a per-device function attribute: cache it per device (several GPUs in one process)
+    static int configured_dev[64] = {0};
+    int dev_id = 0;
+    if (cudaGetDevice(&dev_id) != cudaSuccess || dev_id < 0 || dev_id >= 64) dev_id = 0, configured_dev[0] = 0;
+    int& configured = configured_dev[dev_id];
     if (configured < smem) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
             fprintf(stderr, "vqb200: wide tensor-core kernel needs %d bytes of shared memory (DB=%d XS=%d KL=%d)\n", smem, DB, XS, prm.KL);
