@@ -75,11 +75,12 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
 // sum over the ranks, in rank order, of element i of every rank's statistics buffer.  All loads are issued before the
 // first add (one NVLink round trip instead of `world`); volatile: never from a stale local cache line, never hoisted
 // above the flag wait.
-__device__ __forceinline__ float peer_sum(const PeerStats& peers, size_t i) {
-    float v[P2P_MAX_RANKS];
+__device__ __forceinline__ void peer_load(const PeerStats& peers, size_t i, bool on, float (&v)[P2P_MAX_RANKS]) {
 #pragma unroll
     for (int r = 0; r < P2P_MAX_RANKS; ++r)
-        v[r] = r < peers.world ? *reinterpret_cast<const volatile float*>(peers.stats[r] + i) : 0.f;
+        v[r] = (on && r < peers.world) ? *reinterpret_cast<const volatile float*>(peers.stats[r] + i) : 0.f;
+}
+__device__ __forceinline__ float rank_ordered_sum(const float (&v)[P2P_MAX_RANKS]) {
     float s = 0.f;
 #pragma unroll
     for (int r = 0; r < P2P_MAX_RANKS; ++r) s += v[r];          // + 0.f for absent ranks: exact
@@ -129,12 +130,27 @@ __global__ void __launch_bounds__(256) k_ema64(const float* __restrict__ stats, 
     }
     // counts / sums of this step (summed over the ranks in rank order) -> shared memory, all peer loads in one phase
     float cv[2], sv[2];
+    if constexpr (P2P) {
+        // ALL peer loads of the thread are issued before the first add: with the adds of one sum between the load groups
+        // (what the compiler emits for four separate sums of volatile loads) the warp paid four NVLink round trips in a row
+        float vc[2][P2P_MAX_RANKS], vs[2][P2P_MAX_RANKS];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-        const int k = tid + 256 * u;
-        cv[u] = k < K ? (P2P ? peer_sum(peers, (size_t)K * 64 + k) : stats[(size_t)K * 64 + k]) : 0.f;
-        const int i = tid + 256 * u, j = i >> 6, d = i & 63;   // coalesced 256-byte rows of the 8 codes of this block
-        sv[u] = P2P ? peer_sum(peers, (size_t)(k0 + j) * 64 + d) : stats[(size_t)(k0 + j) * 64 + d];
+        for (int u = 0; u < 2; ++u) {
+            const int k = tid + 256 * u, j = k >> 6, d = k & 63;
+            peer_load(peers, (size_t)K * 64 + k, k < K, vc[u]);
+            peer_load(peers, (size_t)(k0 + j) * 64 + d, true, vs[u]);
+        }
+        asm volatile("" ::: "memory");               // keep the adds behind the last load
+#pragma unroll
+        for (int u = 0; u < 2; ++u) { cv[u] = rank_ordered_sum(vc[u]); sv[u] = rank_ordered_sum(vs[u]); }
+    } else {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int k = tid + 256 * u;
+            cv[u] = k < K ? stats[(size_t)K * 64 + k] : 0.f;
+            const int i = tid + 256 * u, j = i >> 6, d = i & 63;   // coalesced 256-byte rows of the 8 codes of this block
+            sv[u] = stats[(size_t)(k0 + j) * 64 + d];
+        }
     }
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
