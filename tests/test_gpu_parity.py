@@ -16,7 +16,7 @@ import torch
 
 import vq_vae_2_pytorch_b200 as vq
 from vq_vae_2_pytorch_b200 import _native
-from helpers import REL_TOL, col_rel_err, golden_names, load_golden, rel_err
+from helpers import REL_TOL, check_outputs_np, col_rel_err, elem_rel_err, golden_names, load_golden, rel_err
 from oracle.quantize_oracle import QuantizeOracle, tie_tolerant_index_mismatches
 
 pytestmark = pytest.mark.gpu
@@ -43,25 +43,44 @@ def as_strided_cuda(arr, strides):
     return out
 
 
-def check_step(name, s, x_np, embed_before, outs, golden, module, check_buffers=True):
+def check_outputs(tag, x_np, state_before, outs, want, module, want_state, train, decay=0.99, eps=1e-5):
+    """torch front of helpers.check_outputs_np (element-wise 1e-5, near-tie rule, touched EMA columns excluded)."""
     quant, diff, ind = outs
     assert ind.dtype == torch.int64 and ind.is_contiguous() and tuple(ind.shape) == x_np.shape[:-1]
     assert quant.dtype == torch.float32 and diff.dim() == 0 and diff.dtype == torch.float32
-    ind_np = ind.cpu().numpy()
-    ndiff, nbad, bad = tie_tolerant_index_mismatches(x_np, embed_before, ind_np, golden[f"ind{s}"])
-    assert nbad == 0, f"{name} step {s}: {nbad} index mismatches beyond fp32 near-ties (rows {bad[:8]})"
-    # quantize must be the gather of the chosen code from the PRE-update codebook (vqvae.py:52)
-    codes = embed_before.T[ind_np]
-    assert rel_err(quant.cpu().numpy(), x_np + (codes - x_np)) <= REL_TOL
-    if ndiff == 0:
-        assert rel_err(quant.cpu().numpy(), golden[f"quantize{s}"]) <= REL_TOL
-        gd = float(golden[f"diff{s}"])
-        assert abs(float(diff) - gd) <= REL_TOL * abs(gd) + 1e-12
-        if check_buffers:
-            assert rel_err(module.cluster_size.cpu().numpy(), golden[f"cluster_size{s + 1}"]) <= REL_TOL
-            assert col_rel_err(module.embed_avg.cpu().numpy(), golden[f"embed_avg{s + 1}"]) <= REL_TOL
-            assert col_rel_err(module.embed.cpu().numpy(), golden[f"embed{s + 1}"]) <= 4 * REL_TOL
-    return ndiff
+    got_state = (module.cluster_size.cpu().numpy(), module.embed_avg.cpu().numpy(), module.embed.cpu().numpy()) if train else None
+    return check_outputs_np(tag, x_np, state_before, (quant.detach().cpu().numpy(), float(diff), ind.cpu().numpy()), want,
+                            got_state, want_state, train, decay, eps)
+
+
+def module_state(q):
+    return {k: v.detach().cpu().numpy().copy() for k, v in q.state_dict().items()}
+
+
+def load_state(q, cluster_size, embed_avg, embed):
+    q.embed.data.copy_(torch.from_numpy(np.ascontiguousarray(embed)))
+    q.cluster_size.data.copy_(torch.from_numpy(np.ascontiguousarray(cluster_size)))
+    q.embed_avg.data.copy_(torch.from_numpy(np.ascontiguousarray(embed_avg)))
+
+
+def check_step(name, s, x_np, state_before, outs, golden, module, check_buffers=True):
+    want_state = (golden[f"cluster_size{s + 1}"], golden[f"embed_avg{s + 1}"], golden[f"embed{s + 1}"]) if check_buffers else None
+    return check_outputs(f"{name} step {s}", x_np, state_before, outs,
+                         (golden[f"quantize{s}"], golden[f"diff{s}"], golden[f"ind{s}"]), module, want_state, check_buffers,
+                         float(golden["decay"]), float(golden["eps"]))
+
+
+def oracle_step(tag, q, o, x_np, x_dev=None):
+    """One forward of module and oracle from the same state, element-wise check, then the module follows the oracle's
+    trajectory (so a tolerated near-tie never forks the sequence: no skips)."""
+    before = {"embed": o.embed.copy(), "embed_avg": o.embed_avg.copy(), "cluster_size": o.cluster_size.copy()}
+    qo, do, io = o.forward(x_np)
+    outs = q(torch.from_numpy(x_np).to(DEV) if x_dev is None else x_dev)
+    nd = check_outputs(tag, x_np, before, outs, (qo, do, io), q, (o.cluster_size, o.embed_avg, o.embed), q.training,
+                       o.decay, o.eps)
+    if q.training:
+        load_state(q, o.cluster_size, o.embed_avg, o.embed)
+    return nd, outs
 
 
 @pytest.mark.parametrize("engine", ENGINES)
@@ -76,11 +95,11 @@ def test_golden_fixture(name, engine):
         x = as_strided_cuda(x_np, g[f"x{s}_strides"])
         want_grad = f"xgrad{s}" in g
         x.requires_grad_(want_grad)
-        embed_before = q.embed.cpu().numpy().copy()
+        state_np = module_state(q)
         state_before = {k: v.clone() for k, v in q.state_dict().items()}
         quant, diff, ind = q(x)
         assert tuple(quant.stride()) == tuple(int(v) for v in g[f"quantize{s}_strides"])   # strides follow the input
-        ndiff = check_step(name, s, np.ascontiguousarray(x_np), embed_before, (quant.detach(), diff.detach(), ind), g, q,
+        ndiff = check_step(name, s, np.ascontiguousarray(x_np), state_np, (quant.detach(), diff.detach(), ind), g, q,
                            check_buffers=bool(g["train"]))
         if not g["train"]:
             for k, v in q.state_dict().items():
@@ -88,8 +107,9 @@ def test_golden_fixture(name, engine):
         if want_grad:
             gq = torch.from_numpy(g[f"gq{s}"]).to(DEV)
             (quant * gq).sum().add(diff * float(g[f"gd{s}"])).backward()
-            if ndiff == 0:
-                assert rel_err(x.grad.cpu().numpy(), g[f"xgrad{s}"]) <= REL_TOL
+            keep_rows = (ind.cpu().numpy() == g[f"ind{s}"]).reshape(-1)
+            got, want = x.grad.cpu().numpy().reshape(-1, dims[0])[keep_rows], g[f"xgrad{s}"].reshape(-1, dims[0])[keep_rows]
+            assert elem_rel_err(got, want, floor=1e-6 * float(np.abs(want).max())) <= REL_TOL
         # follow the reference trajectory so later steps stay comparable even after a tolerated near-tie
         q.embed.data.copy_(torch.from_numpy(g[f"embed{s + 1}"]))
         q.cluster_size.data.copy_(torch.from_numpy(g[f"cluster_size{s + 1}"]))
@@ -105,18 +125,7 @@ def test_free_running_ema_sequence_matches_oracle(engine):
     o = QuantizeOracle(D, K, embed=q.embed.cpu().numpy())
     for s in range(5):
         x = torch.randn(4, 32, 32, D, generator=torch.Generator().manual_seed(1234 + 1000 * s))
-        embed_before = o.embed.copy()
-        qo, do, io = o.forward(x.numpy())
-        quant, diff, ind = q(x.to(DEV))
-        ndiff, nbad, _ = tie_tolerant_index_mismatches(x.numpy(), embed_before, ind.cpu().numpy(), io)
-        assert nbad == 0
-        if ndiff:
-            pytest.skip("tolerated near-tie changed the trajectory; covered step-wise by the fixtures")
-        assert rel_err(quant.cpu().numpy(), qo) <= REL_TOL
-        assert abs(float(diff) - float(do)) <= REL_TOL * abs(float(do))
-        assert rel_err(q.cluster_size.cpu().numpy(), o.cluster_size) <= REL_TOL
-        assert col_rel_err(q.embed_avg.cpu().numpy(), o.embed_avg) <= 2 * REL_TOL
-        assert col_rel_err(q.embed.cpu().numpy(), o.embed) <= 4 * REL_TOL
+        oracle_step(f"free-running step {s}", q, o, x.numpy())
     assert float(q.embed.abs().max()) > 1e4          # the dead-code blow-up really happened
 
 
@@ -131,35 +140,20 @@ def test_clustered_and_scaled_inputs_vs_oracle(engine):
         x = (e[:, pick].T + noise * rng.standard_normal((3000, D))).astype(np.float32)
         q = make_module((D, K), engine, e).train()
         o = QuantizeOracle(D, K, embed=e)
-        qo, do, io = o.forward(x)
-        quant, diff, ind = q(torch.from_numpy(x).to(DEV))
-        ndiff, nbad, _ = tie_tolerant_index_mismatches(x, e, ind.cpu().numpy(), io)
-        assert nbad == 0
-        if ndiff == 0:
-            assert rel_err(quant.cpu().numpy(), qo) <= REL_TOL
-            assert abs(float(diff) - float(do)) <= REL_TOL * abs(float(do))
-            assert col_rel_err(q.embed_avg.cpu().numpy(), o.embed_avg) <= 2 * REL_TOL
+        oracle_step(f"clustered scale {scale}", q, o, x)
 
 
 @pytest.mark.parametrize("engine", ENGINES)
 @pytest.mark.parametrize("shape,D,K", [((1, 64), 64, 512), ((127, 64), 64, 512), ((129, 64), 64, 512),
                                        ((3, 5, 32), 32, 40), ((1000, 256), 256, 1024), ((77, 128), 128, 2048),
-                                       ((300, 48), 48, 100), ((64, 8), 8, 3)])
+                                       ((300, 48), 48, 100), ((64, 8), 8, 3), ((50, 3), 3, 5), ((33, 7), 7, 9)])
 def test_ragged_shapes_vs_oracle(shape, D, K, engine):
     rng = np.random.default_rng(hash((shape, D, K)) % (2 ** 31))
     embed = rng.standard_normal((D, K)).astype(np.float32)
     x = rng.standard_normal(shape).astype(np.float32)
     q = make_module((D, K), engine, embed).train()
     o = QuantizeOracle(D, K, embed=embed)
-    qo, do, io = o.forward(x)
-    quant, diff, ind = q(torch.from_numpy(x).to(DEV))
-    ndiff, nbad, _ = tie_tolerant_index_mismatches(x, embed, ind.cpu().numpy(), io)
-    assert nbad == 0
-    if ndiff == 0:
-        assert rel_err(quant.cpu().numpy(), qo) <= REL_TOL
-        assert abs(float(diff) - float(do)) <= REL_TOL * abs(float(do))
-        assert rel_err(q.cluster_size.cpu().numpy(), o.cluster_size) <= REL_TOL
-        assert col_rel_err(q.embed_avg.cpu().numpy(), o.embed_avg) <= 2 * REL_TOL
+    oracle_step(f"ragged {shape} D={D} K={K}", q, o, x)
 
 
 @pytest.mark.parametrize("engine", ENGINES)
@@ -231,11 +225,7 @@ def test_multiple_forwards_per_step_see_previous_update():
     o = QuantizeOracle(64, 512, embed=q.embed.cpu().numpy())
     for s in range(3):
         x = torch.randn(512, 64, generator=torch.Generator().manual_seed(50 + s))
-        qo, _, io = o.forward(x.numpy())
-        quant, _, ind = q(x.to(DEV))
-        if not np.array_equal(ind.cpu().numpy(), io):
-            pytest.skip("near-tie")
-        assert rel_err(quant.cpu().numpy(), qo) <= REL_TOL
+        oracle_step(f"multi-forward call {s}", q, o, x.numpy())
 
 
 # ---------------------------------------------------------------------------------------------
@@ -330,4 +320,4 @@ def test_host_buffer_path_matches_device_path():
     assert abs(float(d_h) - float(diff_d)) <= 1e-6 * float(diff_d)
     assert rel_err(q2.cluster_size.cpu().numpy(), q.cluster_size.cpu().numpy()) <= 1e-6
     assert col_rel_err(q2.embed_avg.cpu().numpy(), q.embed_avg.cpu().numpy()) <= REL_TOL
-    assert col_rel_err(q2.embed.cpu().numpy(), q.embed.cpu().numpy()) <= 4 * REL_TOL
+    assert col_rel_err(q2.embed.cpu().numpy(), q.embed.cpu().numpy()) <= REL_TOL

@@ -6,7 +6,7 @@ The fixtures were produced by tests/golden/make_golden.py, which executes the re
 import numpy as np
 import pytest
 
-from helpers import REL_TOL, col_rel_err, golden_names, load_golden, rel_err
+from helpers import REL_TOL, check_outputs_np, elem_rel_err, golden_names, load_golden, rel_err
 from oracle.quantize_oracle import QuantizeOracle, tie_tolerant_index_mismatches
 
 
@@ -19,22 +19,20 @@ def test_oracle_matches_reference_outputs(name):
     for s in range(int(g["steps"])):
         x = np.ascontiguousarray(g[f"x{s}"])
         embed_before = o.embed.copy()
+        before = o.state()
         q, diff, ind = o.forward(x)
         assert ind.dtype == np.int64 and ind.shape == x.shape[:-1]
-        ndiff, nbad, _ = tie_tolerant_index_mismatches(x, embed_before, ind, g[f"ind{s}"])
-        assert nbad == 0, f"{name} step {s}: {nbad} index mismatches beyond fp32 near-ties"
-        if ndiff == 0:
-            assert rel_err(q, g[f"quantize{s}"]) <= REL_TOL
-            assert abs(float(diff) - float(g[f"diff{s}"])) <= REL_TOL * abs(float(g[f"diff{s}"])) + 1e-12
-            assert rel_err(o.cluster_size, g[f"cluster_size{s + 1}"]) <= REL_TOL
-            assert col_rel_err(o.embed_avg, g[f"embed_avg{s + 1}"]) <= REL_TOL
-            assert col_rel_err(o.embed, g[f"embed{s + 1}"]) <= 4 * REL_TOL
+        train = bool(g["train"])
+        check_outputs_np(f"{name} step {s}", x, before, (q, diff, ind), (g[f"quantize{s}"], g[f"diff{s}"], g[f"ind{s}"]),
+                         (o.cluster_size, o.embed_avg, o.embed) if train else None,
+                         (g[f"cluster_size{s + 1}"], g[f"embed_avg{s + 1}"], g[f"embed{s + 1}"]) if train else None,
+                         train, float(g["decay"]), float(g["eps"]))
         # keep both trajectories on the reference's state so later steps stay comparable
         o.load(g[f"embed{s + 1}"], g[f"cluster_size{s + 1}"], g[f"embed_avg{s + 1}"])
         if f"xgrad{s}" in g:
             codes = embed_before.T[g[f"ind{s}"]]
             gx = o.backward(x, codes, g[f"gq{s}"], float(g[f"gd{s}"]))
-            assert rel_err(gx, g[f"xgrad{s}"]) <= REL_TOL
+            assert elem_rel_err(gx, g[f"xgrad{s}"], floor=1e-6 * float(np.abs(g[f"xgrad{s}"]).max())) <= REL_TOL
 
 
 def test_oracle_chunked_equals_unchunked():
