@@ -1,0 +1,67 @@
+"""Collective row (vqvae.py:58-59 -> distributed.py:64-72) on ONE GPU: the all-reduce that is fused
+into the EMA kernel over peer memory (`vqb200_ema_update_p2p`) driven with world = 1 -- its own statistics buffer and
+flag array stand for the peer-mapped ones -- must reproduce `vqb200_ema_update` bit for bit over several steps (flag
+publication, wait, rank-ordered sum of one rank, step/parity bookkeeping).  The multi-rank run of the same kernel is
+checked by bench.py at N > 1 ("parity_multi") and by tools/p2p_check.py; the packing / reduction algebra by the gloo test.
+"""
+import ctypes as C
+
+import pytest
+import torch
+
+import vq_vae_2_pytorch_b200 as vq
+from vq_vae_2_pytorch_b200 import _native
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.mark.parametrize("K", [512, 256])
+def test_p2p_ema_with_world_1_equals_local_ema(K):
+    lib = _native.load()
+    D = 64
+    torch.manual_seed(0)
+    a = vq.Quantize(D, K).to(DEV).train()
+    b = vq.Quantize(D, K).to(DEV).train()
+    b.load_state_dict(a.state_dict())
+    n = lib.vqb200_stats_bytes(D, K) // 4
+    n_al = (n + 63) // 64 * 64
+    buf = torch.zeros(2 * n_al + 128, device=DEV)                # [stats parity 0 | stats parity 1 | flags 0 | flags 1]
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for step in range(1, 5):
+        x = torch.randn(128 * 37 + 5, D, device=DEV, generator=torch.Generator(device=DEV).manual_seed(step))
+        par = step & 1
+        stats = buf[par * n_al: par * n_al + n]
+        ws = b._workspace(x.device, x.shape[0])
+        quant = torch.empty_like(x); ind = torch.empty(x.shape[0], dtype=torch.int64, device=DEV); diff = torch.empty((), device=DEV)
+        # ONE forward (no EMA) writes this step's packed statistics; both EMA variants then consume the same bits (the
+        # statistics kernel's summation order is not reproducible between two runs, like the reference's GEMM)
+        _native.check(lib.vqb200_quantize_step(x.data_ptr(), x.shape[0], D, K, x.shape[0], 0, D, 1, b.embed.data_ptr(),
+                                               b.cluster_size.data_ptr(), b.embed_avg.data_ptr(), ws["image"].data_ptr(),
+                                               quant.data_ptr(), ind.data_ptr(), diff.data_ptr(), stats.data_ptr(),
+                                               ws["scratch"].data_ptr(), None, 0, 0, 0.99, float(1 - 0.99), 1e-5, st), "step")
+        local_stats = stats.clone()
+        _native.check(lib.vqb200_ema_update(local_stats.data_ptr(), a.cluster_size.data_ptr(), a.embed_avg.data_ptr(),
+                                            a.embed.data_ptr(), D, K, 0.99, float(1 - 0.99), 1e-5, None, st), "ema_local")
+        stats_ptrs = (C.c_void_p * 1)(stats.data_ptr())
+        flag_ptrs = (C.c_void_p * 1)(buf.data_ptr() + 4 * (2 * n_al + 64 * par))
+        _native.check(lib.vqb200_ema_update_p2p(stats_ptrs, flag_ptrs, 0, 1, step, b.cluster_size.data_ptr(),
+                                                b.embed_avg.data_ptr(), b.embed.data_ptr(), D, K, 0.99, float(1 - 0.99), 1e-5,
+                                                None, st), "ema_p2p")
+        torch.cuda.synchronize()
+        for name in ("cluster_size", "embed_avg", "embed"):
+            assert torch.equal(getattr(a, name), getattr(b, name)), f"step {step}: {name} differs between the fused P2P and the local EMA"
+        assert int(buf[2 * n_al + 64 * par: 2 * n_al + 64 * par + 1].view(torch.int32)) == step      # the flag this rank published
+    # four EMA steps of 4741 rows each from cluster_size = 0:  sum = N (1-d) (d^3 + d^2 + d + 1)
+    want = (128 * 37 + 5) * 0.01 * (0.99 ** 3 + 0.99 ** 2 + 0.99 + 1)
+    assert abs(float(a.cluster_size.double().sum()) - want) <= 1e-5 * want
+
+
+def test_p2p_ema_rejects_bad_arguments():
+    lib = _native.load()
+    z = torch.zeros(64 * 513 + 4 + 128, device=DEV)
+    ptrs = (C.c_void_p * 1)(z.data_ptr())
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    assert lib.vqb200_ema_update_p2p(ptrs, ptrs, 0, 1, 0, z.data_ptr(), z.data_ptr(), z.data_ptr(), 64, 512, 0.99, 0.01, 1e-5, None, st) == -1   # step 0
+    assert lib.vqb200_ema_update_p2p(ptrs, ptrs, 1, 1, 1, z.data_ptr(), z.data_ptr(), z.data_ptr(), 64, 512, 0.99, 0.01, 1e-5, None, st) == -1   # rank >= world
+    assert lib.vqb200_ema_update_p2p(ptrs, ptrs, 0, 1, 1, z.data_ptr(), z.data_ptr(), z.data_ptr(), 48, 100, 0.99, 0.01, 1e-5, None, st) == -2   # shape

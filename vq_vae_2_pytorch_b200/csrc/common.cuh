@@ -33,10 +33,11 @@ struct CodebookImage {
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-// tensor-core operand image (tc_kernel.cuh): per code 2 x dim bf16 (hi, lo) + 32 B misc row + fp32 norm
+// tensor-core operand image (tc_kernel.cuh): per code 2 x dim bf16 (hi, lo) + 32 B misc row + fp32 norm + 32 B misc row of
+// the plain-bf16 bound, then the tf32 operand (dim fp32 words, low 13 bits clear) + its 32 B misc row
 __host__ __device__ inline size_t tc_image_bytes(int dim, int n_embed) {
     size_t dpad = (size_t)(dim + 63) / 64 * 64;
-    return (size_t)n_embed * (dpad * 4 + 32 + 4 + 32) + 1024;
+    return (size_t)n_embed * (dpad * 4 + 32 + 4 + 32 + dpad * 4 + 32) + 1024;
 }
 
 __host__ __device__ inline size_t codebook_bytes(int dim, int n_embed) {

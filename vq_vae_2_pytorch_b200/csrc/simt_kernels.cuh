@@ -253,15 +253,17 @@ __device__ __forceinline__ void smem_add(float* p, float v) { atomicAdd(p, v); }
 __global__ void __launch_bounds__(CS_THREADS, 1)
 k_code_stats(const float* __restrict__ x, RowLayout L, int D, int K, const int64_t* __restrict__ embed_ind,
              float* __restrict__ partials /* [gridDim.x][K*(D+1)] */, int chunk /* rows per trip, <= CS_CHUNK */) {
-    extern __shared__ float cs_smem[];
-    float* table = cs_smem;                                   // [K][D]
-    int* cnt_total = reinterpret_cast<int*>(table + (size_t)K * D);   // [K]
+    // layout: the int64 array first (dynamic shared memory is 16-byte aligned; behind [K][D] floats it would only be
+    // 4-byte aligned when K*D is odd, e.g. Quantize(3, 5): misaligned 8-byte shared stores), then the 4-byte arrays,
+    // then the 2-byte arrays
+    extern __shared__ __align__(16) unsigned char cs_smem_raw[];
+    int64_t* order = reinterpret_cast<int64_t*>(cs_smem_raw);                     // [CS_CHUNK] element offsets of the rows, bucketed by code
+    float* table = reinterpret_cast<float*>(order + CS_CHUNK);                   // [K][D]
+    int* cnt_total = reinterpret_cast<int*>(table + (size_t)K * D);              // [K]
     int* hist = cnt_total + K;                                // [K]   bucket sizes of this chunk
     int* start = hist + K;                                    // [K+1] bucket offsets
     int* cursor = start + K + 1;                              // [K]
-    int* pad = cursor + K;                                    // keeps the int64 array 8-byte aligned
-    int64_t* order = reinterpret_cast<int64_t*>(pad + ((4 * K + 1) & 1));        // [CS_CHUNK] element offsets of the rows, bucketed by code
-    unsigned short* code = reinterpret_cast<unsigned short*>(order + CS_CHUNK);   // [CS_CHUNK] code of row i
+    unsigned short* code = reinterpret_cast<unsigned short*>(cursor + K);         // [CS_CHUNK] code of row i
     unsigned short* scode = code + CS_CHUNK;                  // [CS_CHUNK] code at sorted position p
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = CS_THREADS / 32;
 

@@ -48,7 +48,10 @@ constexpr int RELAX_NS = VQB200_RELAX_NS;   // poll interval of the relaxed wait
 // error-bound constants (see DESIGN.md "certificate"): dot-product error <= c1 ||x|| ||e||
 //   split-bf16 (3 products): 3.1 * 2^-18 rounding + fp32 accumulation  -> c1 = 2^-16, cA = 2 c1
 //   plain bf16             : (1+2^-9)^2 - 1                            -> c1 = 2^-8 * 1.01
-__host__ __device__ constexpr float bound_cA(int nsplit) { return nsplit == 3 ? 3.0517578125e-5f : 7.9e-3f; }
+//   tf32 (nsplit == 0)     : x is read as tf32 by the tensor core straight from its fp32 TMA stage (the low 13 mantissa bits
+//                            are dropped: relative error < 2^-10 whether the hardware truncates or rounds), -2e is rounded to
+//                            nearest tf32 when the image is built (2^-11)  -> c1 = (2^-10 + 2^-11 + 2^-21) * 1.01, cA = 2 c1
+__host__ __device__ constexpr float bound_cA(int nsplit) { return nsplit == 3 ? 3.0517578125e-5f : (nsplit == 0 ? 2.96e-3f : 7.9e-3f); }
 constexpr float BOUND_CB = 4.0e-6f;        // fp32 accumulation of <= 14 MMAs, relative to ||x||^2 + ||e||^2
 constexpr float BOUND_UP = 1.03125f;       // covers the upward bf16 roundings of ||x||, ||e||, ||e||^2
 
@@ -107,6 +110,10 @@ __device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void* src, uin
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, int c0, int c1, int c2, uint32_t bar, uint64_t policy) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;"
                  ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+                 ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar), "l"(policy) : "memory");
 }
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
     uint64_t p;
@@ -215,6 +222,9 @@ __device__ __forceinline__ uint64_t desc_sw32(uint32_t saddr) {    // rows of 32
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, K-major both, N=256, M=128
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(UNIT_N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
 // same with M = 256 for cta_group::2 (each CTA of the pair owns 128 of the 256 rows and 128 of the 256 B rows)
+// kind::tf32: A = B = tf32 (format 2), K-major both (NCHW-physical x: A is MN-major, bit 15)
+constexpr uint32_t IDESC_TF = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(UNIT_N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+constexpr uint32_t IDESC_TF_AMN = IDESC_TF | (1u << 15);
 constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(UNIT_N >> 3) << 17) | ((uint32_t)((2 * TILE_M) >> 4) << 24);
 
 // byte offset of bf16 element (row, col) inside a 128B-swizzled K-major block (Swizzle<3,4,3>)
@@ -240,20 +250,45 @@ __device__ __forceinline__ void split3(float f, float& a, float& b, float& c) {
     c = bf16_round(r - b);
 }
 
+// tf32 helpers: round to nearest tf32 (10 explicit mantissa bits; the result is an fp32 with the low 13 bits clear, which the
+// kind::tf32 MMA reads exactly) and the exact 3-term tf32 split of an fp32 value
+__device__ __forceinline__ float tf32_rn(float f) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(f));
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ void split3_tf32(float f, float& a, float& b, float& c) {
+    a = tf32_rn(f);
+    float r = f - a;
+    b = tf32_rn(r);
+    c = tf32_rn(r - b);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // tensor-core operand image of the codebook (global memory, byte-identical to its smem layout)
 //   [ eh : K*128 | el : K*128 | misc : K*32 ]   + enorm[K] (fp32 ||e_k||) kept next to it
+//   [ e32 : 2 x K*128 | misc32 : K*32 ]  tf32 operand of -2e: two 32-dim k-blocks of 128-byte swizzled rows, and its misc rows
 // ---------------------------------------------------------------------------------------------------
 __host__ __device__ inline size_t image_off_lo(int K) { return (size_t)K * 128; }
 __host__ __device__ inline size_t image_off_misc(int K) { return (size_t)K * 256; }
 __host__ __device__ inline size_t image_off_enorm(int K) { return (size_t)K * 288; }
 __host__ __device__ inline size_t image_off_misc1(int K) { return (size_t)K * 292; }     // misc block carrying the plain-bf16 bound
-__host__ __device__ inline size_t image_bytes(int K) { return (size_t)K * 292 + (size_t)K * 32; }
+__host__ __device__ inline size_t image_off_tf(int K) { return (size_t)K * 324; }         // tf32 operand [2][K][128 B]
+__host__ __device__ inline size_t image_off_tfmisc(int K) { return (size_t)K * 580; }     // tf32 misc rows [K][32 B]
+__host__ __device__ inline size_t image_bytes(int K) { return (size_t)K * 612; }
 
 // operand-image rows of code k, 8-dim chunk c (0..7): e = the code's 64 fp32 components, e2 = ||e_k||^2; requires D == 64
 __device__ __forceinline__ void tc_image_rows(const float* e_row, float e2, unsigned char* __restrict__ img, int K, int k, int c,
                                               float cA, float cA1, float cB) {
     const float* e = e_row + c * 8;
+    {   // tf32 operand: dims 8c .. 8c+7 = two 16-byte chunks of the 128-byte row of k-block c / 4
+        unsigned char* t = img + image_off_tf(K) + (size_t)(c >> 2) * K * 128 + (size_t)k * 128;
+        const uint32_t ch = 2u * (uint32_t)(c & 3), sw = (uint32_t)k & 7u;
+        *reinterpret_cast<float4*>(t + (((ch) ^ sw) << 4)) =
+            make_float4(tf32_rn(-2.f * e[0]), tf32_rn(-2.f * e[1]), tf32_rn(-2.f * e[2]), tf32_rn(-2.f * e[3]));
+        *reinterpret_cast<float4*>(t + (((ch + 1u) ^ sw) << 4)) =
+            make_float4(tf32_rn(-2.f * e[4]), tf32_rn(-2.f * e[5]), tf32_rn(-2.f * e[6]), tf32_rn(-2.f * e[7]));
+    }
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -282,6 +317,14 @@ __device__ __forceinline__ void tc_image_rows(const float* e_row, float e2, unsi
         *reinterpret_cast<uint4*>(m1 + sw32_chunk_off((uint32_t)k, 0)) =
             make_uint4(pack_bf16(b1, b2), pack_bf16(b3, 1.f), pack_bf16(1.f, 1.f), pack_bf16(t6b, t7));
         *reinterpret_cast<uint4*>(m1 + sw32_chunk_off((uint32_t)k, 1)) = make_uint4(0, 0, 0, 0);
+        // tf32 misc row [b1 b2 b3 1 | 1 1 -cA||e|| -cB||e||^2] (8 tf32 = one 32-byte swizzle row = one K = 8 MMA)
+        float c1, c2, c3;
+        split3_tf32(e2, c1, c2, c3);
+        const float u6 = -tf32_rn(bound_cA(0) * ne * 1.001953125f);      // rounded up in magnitude
+        const float u7 = -tf32_rn(cB * e2 * 1.001953125f);
+        unsigned char* mt = img + image_off_tfmisc(K);
+        *reinterpret_cast<float4*>(mt + sw32_chunk_off((uint32_t)k, 0)) = make_float4(c1, c2, c3, 1.f);
+        *reinterpret_cast<float4*>(mt + sw32_chunk_off((uint32_t)k, 1)) = make_float4(1.f, 1.f, u6, u7);
     }
 }
 
@@ -455,17 +498,56 @@ __device__ __forceinline__ void issue_unit(uint32_t d_tmem, uint32_t am_lo, uint
     }
 }
 
+// ---- kind::tf32 issue (NSPLIT == 0): x is multiplied straight from its fp32 TMA stage ---------------------------------
+// One accumulator unit = 8 MMAs (M128 x N128 x K8, 32 bytes of K per step) over the two 32-dim k-blocks of x and of the
+// -2e image, the first overwriting the accumulator, and LAST the misc MMA (bias, row offset, error bound: it needs the row
+// norms, which the norm warps compute from the same stage while the products are already running) + the commit.
+//   a_lo / b_lo: descriptor low words of k-block 0; a_kb / b_kb: descriptor-unit (16-byte) offset of k-block 1;
+//   a_ks: descriptor-unit step per K = 8 (2 for a K-major stage, 64 for the MN-major x^T stage: 8 dims x 128 bytes)
+__device__ __forceinline__ void issue_unit_tf_products(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t a_kb, uint32_t b_kb,
+                                                       uint32_t a_ks, uint32_t a_hi, uint32_t idesc) {
+#define VQ_TF_OP "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %7, "
+#define VQ_TF_NEXT "add.u32 ta, ta, %6;\n\tadd.u32 tb, tb, 2;\n\tmov.b64 da, {ta, %8};\n\tmov.b64 db, {tb, %3};\n\t" VQ_TF_OP "pt;\n\t"
+    asm volatile(
+        "{\n\t.reg .pred pf, pt, pe;\n\t.reg .b64 da, db;\n\t.reg .b32 ta, tb;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "setp.ne.b32 pf, %7, %7;\n\tsetp.eq.b32 pt, %7, %7;\n\t"
+        "mov.u32 ta, %1;\n\tmov.u32 tb, %2;\n\t"
+        "mov.b64 da, {ta, %8};\n\tmov.b64 db, {tb, %3};\n\t" VQ_TF_OP "pf;\n\t"
+        VQ_TF_NEXT VQ_TF_NEXT VQ_TF_NEXT
+        "add.u32 ta, %1, %4;\n\tadd.u32 tb, %2, %5;\n\t"
+        "mov.b64 da, {ta, %8};\n\tmov.b64 db, {tb, %3};\n\t" VQ_TF_OP "pt;\n\t"
+        VQ_TF_NEXT VQ_TF_NEXT VQ_TF_NEXT
+        "}"
+        :: "r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(DESC_HI_SW128), "r"(a_kb), "r"(b_kb), "r"(a_ks), "r"(idesc), "r"(a_hi) : "memory");
+#undef VQ_TF_NEXT
+#undef VQ_TF_OP
+}
+__device__ __forceinline__ void issue_unit_tf_misc(uint32_t d_tmem, uint32_t am_lo, uint32_t bm_lo, uint32_t bar_tf) {
+    asm volatile(
+        "{\n\t.reg .pred pt, pe;\n\t.reg .b64 da, db;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "setp.eq.b32 pt, %4, %4;\n\t"
+        "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, pt;\n\t"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n\t}"
+        :: "r"(d_tmem), "r"(am_lo), "r"(bm_lo), "r"(DESC_HI_SW32), "r"(IDESC_TF), "r"(bar_tf) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------------
 // shared-memory plan
 // ---------------------------------------------------------------------------------------------------
 template <int NSPLIT, int AS, int XS, bool CTA2 = false>
 struct Plan {
-    static constexpr uint32_t A_STAGE = (NSPLIT == 3 ? 2u : 1u) * 16384u + 4096u;
+    // NSPLIT == 0: tf32 filter -- no converted A operand (the MMAs read the fp32 x stage), an A stage is the misc rows only
+    static constexpr bool TF = NSPLIT == 0;
+    static_assert(!(TF && CTA2), "the tf32 filter has no CTA-pair variant");
+    static constexpr uint32_t A_STAGE = TF ? 4096u : (NSPLIT == 3 ? 2u : 1u) * 16384u + 4096u;
     static constexpr uint32_t X_STAGE = TILE_M * TC_D * 4;
     static constexpr uint32_t BDIV = CTA2 ? 2u : 1u;          // a CTA of a pair holds half of the codes of every unit
-    __host__ __device__ static uint32_t b_bytes(int K) { return ((uint32_t)K * (NSPLIT == 3 ? 256u : 128u) + (uint32_t)K * 32u) / BDIV; }
-    __host__ __device__ static uint32_t off_b_lo(int K) { return (uint32_t)K * 128u / BDIV; }
-    __host__ __device__ static uint32_t off_b_misc(int K) { return (uint32_t)K * (NSPLIT == 3 ? 256u : 128u) / BDIV; }
+    __host__ __device__ static uint32_t b_bytes(int K) { return ((uint32_t)K * ((NSPLIT == 3 || TF) ? 256u : 128u) + (uint32_t)K * 32u) / BDIV; }
+    __host__ __device__ static uint32_t off_b_lo(int K) { return (uint32_t)K * 128u / BDIV; }      // split: el block; tf32: k-block 1
+    __host__ __device__ static uint32_t off_b_misc(int K) { return (uint32_t)K * ((NSPLIT == 3 || TF) ? 256u : 128u) / BDIV; }
     __host__ __device__ static uint32_t off_a(int K) { return b_bytes(K); }
     __host__ __device__ static uint32_t off_x(int K) { return off_a(K) + AS * A_STAGE; }
     __host__ __device__ static uint32_t off_small(int K) { return off_x(K) + XS * X_STAGE; }
