@@ -50,6 +50,7 @@ extern "C" {
 #define VQB200_ENGINE_SIMT    1   /* exact fp32 SIMT distance kernel                                */
 #define VQB200_ENGINE_TCGEN05 2   /* TMA + tcgen05 split-bf16 filter with exact fp32 re-score       */
 #define VQB200_ENGINE_TCGEN05_BF16 3 /* same kernel, plain-bf16 filter: 1/3 of the MMAs, wider bound (more exact re-scores) */
+#define VQB200_ENGINE_TCGEN05_TF32 4 /* kind::tf32 MMAs straight from the fp32 x tile (no conversion pass), dense rows, dim 64 */
 
 int         vqb200_abi_version(void);
 const char* vqb200_error_string(int code);
@@ -165,6 +166,10 @@ int vqb200_unpack_indices(const void* d_codes, int64_t n, int32_t in_bytes, int6
 int vqb200_debug_tc_scores(const float* d_x, int64_t n_rows, int32_t dim, int32_t n_embed,
                            const void* d_codebook, int64_t* d_embed_ind, float* d_scores,
                            int32_t* d_flagged_count, void* d_scratch, void* stream);
+/* same, with the filter chosen by `engine` (VQB200_ENGINE_TCGEN05 / _BF16 / _TF32) */
+int vqb200_debug_tc_scores_ex(const float* d_x, int64_t n_rows, int32_t dim, int32_t n_embed,
+                              const void* d_codebook, int64_t* d_embed_ind, float* d_scores,
+                              int32_t* d_flagged_count, void* d_scratch, int32_t engine, void* stream);
 /* Same run with per-role cycle counters: d_prof [n_CTAs(<=160)][vqb200_tc_profile_slots()] uint64, zeroed by
  * the caller; slot meaning = enum ProfSlot in csrc/tc_kernel.cuh (pipeline bubble analysis for profiles/). */
 int vqb200_debug_tc_profile(const float* d_x, int64_t n_rows, int32_t dim, int32_t n_embed,

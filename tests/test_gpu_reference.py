@@ -68,7 +68,7 @@ def test_cfg2_full_size_multistep_vs_reference(ref, permuted):
 def test_cfg2_filter_engines_vs_reference(ref):
     """Both tensor-core filters pinned explicitly (the precision policy of engine='auto' may pick either) + the SIMT engine."""
     D, K = 64, 512
-    for engine in ("tcgen05", "tcgen05_bf16", "simt"):
+    for engine in ("tcgen05", "tcgen05_bf16", "tcgen05_tf32", "simt"):
         r, o = pair(ref, D, K, seed=3, engine=engine)
         for step, kind in enumerate(["randn", "clustered"]):
             x = H.make_inputs(kind, (32, 64, 64, D), r.embed.detach(), 99 + step, DEV)

@@ -16,8 +16,11 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-def tc_scores(x, embed):
-    """Run vqb200_debug_tc_scores; returns (scores [N,K], embed_ind [N], flagged_count)."""
+FILTERS = {"tcgen05": (3.0517578125e-5, 4.0e-6), "tcgen05_bf16": (7.9e-3, 4.0e-6), "tcgen05_tf32": (2.96e-3, 4.0e-6)}   # engine -> (cA, cB)
+
+
+def tc_scores(x, embed, engine="tcgen05"):
+    """Run vqb200_debug_tc_scores_ex; returns (scores [N,K], embed_ind [N], flagged_count)."""
     lib = _native.load()
     n, d = x.shape
     k = embed.shape[1]
@@ -30,16 +33,11 @@ def tc_scores(x, embed):
     flagged = torch.zeros(1, dtype=torch.int32, device=DEV)
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     _native.check(lib.vqb200_codebook_prepare(_native.ptr(ed), d, k, _native.ptr(image), st), "prepare")
-    _native.check(lib.vqb200_debug_tc_scores(_native.ptr(xd), n, d, k, _native.ptr(image), _native.ptr(ind),
-                                             _native.ptr(scores), _native.ptr(flagged), _native.ptr(scratch), st), "scores")
+    _native.check(lib.vqb200_debug_tc_scores_ex(_native.ptr(xd), n, d, k, _native.ptr(image), _native.ptr(ind),
+                                                _native.ptr(scores), _native.ptr(flagged), _native.ptr(scratch),
+                                                _native.ENGINES[engine], st), "scores")
     torch.cuda.synchronize()
     return scores.cpu().numpy(), ind.cpu().numpy(), int(flagged.item())
-
-
-def bound_constants():
-    split = _native.load().vqb200_tc_split()
-    cA = 3.0517578125e-5 if split == 3 else 7.9e-3
-    return split, cA, 4.0e-6
 
 
 def codebooks():
@@ -51,8 +49,9 @@ def codebooks():
     return {"randn": e0, "dead": dead, "small": small, "k256": e0[:, :256].copy()}
 
 
+@pytest.mark.parametrize("engine", ["tcgen05", "tcgen05_bf16", "tcgen05_tf32"])
 @pytest.mark.parametrize("cb", ["randn", "dead", "small", "k256"])
-def test_tc_scores_are_certified_lower_bounds(cb):
+def test_tc_scores_are_certified_lower_bounds(cb, engine):
     embed = codebooks()[cb]
     K = embed.shape[1]
     rng = np.random.default_rng(1)
@@ -60,9 +59,10 @@ def test_tc_scores_are_certified_lower_bounds(cb):
     scale = 1e-2 if cb == "small" else 1.0
     x = (scale * rng.standard_normal((n, 64))).astype(np.float32)
     x[:64] = embed[:, rng.integers(0, min(K, 60), 64)].T          # rows equal to live codes
-    scores, ind, flagged = tc_scores(x, embed)
+    scores, ind, flagged = tc_scores(x, embed, engine)
     assert not np.isnan(scores).any(), "tensor-core scores were not written for every (row, code)"
-    split, cA, cB = bound_constants()
+    cA, cB = FILTERS[engine]
+    split = engine
     d64 = distances_f64(x, embed)
     xx = (x.astype(np.float64) ** 2).sum(1, keepdims=True)
     ee = (embed.astype(np.float64) ** 2).sum(0, keepdims=True)
@@ -85,13 +85,14 @@ def test_tc_scores_are_certified_lower_bounds(cb):
     _, nbad, _ = tie_tolerant_index_mismatches(x, embed, ind, io)
     assert nbad == 0
     assert (ind >= 0).all() and (ind < K).all()
-    assert flagged < n // 2 or split == 1
+    assert flagged < n // 2 or engine != "tcgen05"
 
 
-def test_tc_and_simt_engines_agree_on_outputs():
+@pytest.mark.parametrize("engine", ["tcgen05", "tcgen05_tf32"])
+def test_tc_and_simt_engines_agree_on_outputs(engine):
     torch.manual_seed(0)
     D, K, N = 64, 512, 128 * 37 + 5
-    a = vq.Quantize(D, K, engine="tcgen05").to(DEV).train()
+    a = vq.Quantize(D, K, engine=engine).to(DEV).train()
     b = vq.Quantize(D, K, engine="simt").to(DEV).train()
     b.load_state_dict(a.state_dict())
     for s in range(3):
@@ -150,12 +151,13 @@ def test_tc_nonfinite_rows_do_not_poison_neighbours():
     assert int(ind.min()) >= 0 and int(ind.max()) < 512
 
 
-def test_tc_plain_bf16_filter_is_exact_after_rescore():
-    """engine='tcgen05_bf16': the cheap filter certifies few rows on N(0,1) inputs; the exact re-score must make the
-    result identical to the SIMT engine anyway (heavy use of the flagged-row path)."""
+@pytest.mark.parametrize("engine", ["tcgen05_bf16", "tcgen05_tf32"])
+def test_tc_plain_bf16_filter_is_exact_after_rescore(engine):
+    """The cheap filters (plain bf16, tf32) certify fewer rows on N(0,1) inputs; the exact re-score must make the result
+    identical to the SIMT engine anyway (heavy use of the flagged-row path)."""
     torch.manual_seed(21)
     D, K, N = 64, 512, 128 * 150 + 9
-    a = vq.Quantize(D, K, engine="tcgen05_bf16").to(DEV).train()
+    a = vq.Quantize(D, K, engine=engine).to(DEV).train()
     b = vq.Quantize(D, K, engine="simt").to(DEV).train()
     b.load_state_dict(a.state_dict())
     x = torch.randn(N, D, device=DEV, generator=torch.Generator(device=DEV).manual_seed(6))
@@ -186,13 +188,14 @@ def test_auto_engine_adapts_filter_precision_without_changing_results():
     assert torch.equal(q2(x)[2], ref(x)[2])
 
 
+@pytest.mark.parametrize("engine", ["tcgen05", "tcgen05_tf32"])
 @pytest.mark.parametrize("K", [512, 256])
-def test_tc_many_trips_per_cta(K):
+def test_tc_many_trips_per_cta(K, engine):
     """More tiles than 3x the SM count: every persistent CTA makes several trips, so the stage / TMEM-buffer
     phase logic (and the CTA-pair tail, where the second tile of the last pair lies past the end) is exercised."""
     torch.manual_seed(11)
     D, N = 64, 128 * 148 * 3 + 128 + 77
-    a = vq.Quantize(D, K, engine="tcgen05").to(DEV).eval()
+    a = vq.Quantize(D, K, engine=engine).to(DEV).eval()
     b = vq.Quantize(D, K, engine="simt").to(DEV).eval()
     b.load_state_dict(a.state_dict())
     x = torch.randn(N, D, device=DEV, generator=torch.Generator(device=DEV).manual_seed(5))
@@ -205,7 +208,7 @@ def test_tc_many_trips_per_cta(K):
         assert abs(float(da) - float(db)) <= 1e-6 * float(db)
 
 
-@pytest.mark.parametrize("engine", ["tcgen05", "tcgen05_bf16"])
+@pytest.mark.parametrize("engine", ["tcgen05", "tcgen05_bf16", "tcgen05_tf32"])
 @pytest.mark.parametrize("live_codes", [1, 3, 40])
 def test_tc_fused_statistics_with_skewed_codes(engine, live_codes):
     """Heavily skewed assignments (collapsed codebook: a handful of live codes): the per-code sums and
@@ -252,7 +255,7 @@ def test_tc_engine_on_nchw_physical_input(shape):
     assert _native.load().vqb200_launch_count() > 0
 
 
-@pytest.mark.parametrize("engine", ["tcgen05", "tcgen05_bf16"])
+@pytest.mark.parametrize("engine", ["tcgen05", "tcgen05_bf16", "tcgen05_tf32"])
 @pytest.mark.parametrize("K", [1024, 2048])
 def test_tc_sliced_codebook_matches_simt(K, engine):
     """Codebooks larger than the resident operand image (BASELINE cfg-5 sweep, D = 64): one tensor-core launch per
@@ -315,3 +318,52 @@ def test_tc_nchw_in_place_variants(shape, train, K, engine):
                 assert col_rel_err(a.embed_avg.cpu().numpy(), b.embed_avg.cpu().numpy()) <= REL_TOL
                 assert torch.allclose(a.cluster_size, b.cluster_size, rtol=1e-5, atol=1e-7)
         b.load_state_dict(a.state_dict())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The certificate's accumulation constant cB is measured, not proven: the tensor core's internal
+# accumulation is not IEEE fp32.  This sweep isolates it: operands that every filter represents EXACTLY (integers / 4 with
+# |v| <= 2, times a power-of-two scale: 4 significant bits, so bf16, tf32 and the bias / offset splits are all exact) leave
+# the accumulation as the only error source.  Magnitudes 1e-6 .. 1e6 of both x and e (and mixed), N = 1e5 rows per point,
+# dims 64 / 128 / 256; the worst |score error| / (||x||^2 + ||e||^2) is printed, written to gpurun_out/, and must stay below
+# cB / 2 (the certificate budgets cB for it; a 2x margin is asserted on every GPU run).
+# ---------------------------------------------------------------------------------------------------------------------
+SWEEP = [("tcgen05", 64, 512), ("tcgen05_bf16", 64, 512), ("tcgen05_tf32", 64, 512), ("tcgen05_tf32", 64, 256),
+         ("tcgen05", 128, 512), ("tcgen05", 256, 256)]
+
+
+@pytest.mark.parametrize("engine,D,K", SWEEP)
+def test_certificate_accumulation_constant_sweep(engine, D, K):
+    import json
+    import os
+    rng = np.random.default_rng(11)
+    cB = 4.0e-6 * (D // 64)
+    worst = {}
+    for sx, se in [(0, 0), (-20, -20), (20, 20), (-20, 0), (0, -20), (0, 17), (10, -10), (-10, 10), (17, 17)]:
+        n = (100000 if (sx, se) == (0, 0) else 16384) // 128 * 128 + 96      # >= 1e5 rows at unit scale, 16 k at the others
+        x = (rng.integers(-8, 9, size=(n, D)) / 4.0 * 2.0 ** sx).astype(np.float32)
+        e = (rng.integers(-8, 9, size=(D, K)) / 4.0 * 2.0 ** se).astype(np.float32)
+        e[:, K // 2:] *= np.float32(2.0 ** 3)             # two magnitude classes inside one accumulator unit
+        scores, ind, flagged = tc_scores(x, e, engine)
+        xx = (x.astype(np.float64) ** 2).sum(1, keepdims=True)
+        ee = (e.astype(np.float64) ** 2).sum(0, keepdims=True)
+        cA = FILTERS[engine][0] if D == 64 else 7.9e-3
+        # what the contraction computes when nothing but the accumulation rounds: bias + offset - 2 x.e - bound terms
+        exact = ee - 2.0 * (x.astype(np.float64) @ e.astype(np.float64)) + xx * (1.0 + 2.0 ** -9)
+        resid = scores.astype(np.float64) - exact          # = -(bound terms, rounded up) + accumulation error
+        bound_lo = -(cA * 1.03125 * np.sqrt(xx) * np.sqrt(ee) + cB * 1.02 * ee)      # BOUND_UP covers the upward roundings
+        acc_err_up = resid                                  # the score may exceed `exact` only through accumulation error
+        acc_err_dn = bound_lo - resid                       # or fall below the nominal bound terms only through it
+        ratio = np.maximum(acc_err_up, acc_err_dn) / (xx + ee)
+        worst[f"x2^{sx} e2^{se}"] = float(ratio.max())
+        assert ratio.max() <= cB / 2, f"{engine} D={D} K={K} scale (2^{sx}, 2^{se}): accumulation error {ratio.max():.3e} (xx+ee) > cB/2"
+        assert (ind >= 0).all() and (ind < K).all()
+    print(f"[cB sweep {engine} D={D} K={K}] worst accumulation error / (xx+ee) = {max(worst.values()):.3e} (cB = {cB:.1e})")
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, f"cb_sweep_{engine}_D{D}_K{K}.json"), "w") as f:
+            json.dump({"engine": engine, "dim": D, "n_embed": K, "rows_unit_scale": 100000 // 128 * 128 + 96, "cB": cB,
+                       "worst_ratio_by_scale": worst}, f, indent=1)
+    except OSError:
+        pass

@@ -9,10 +9,11 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvqb200.so")
+LIB_PATH = os.environ.get("VQB200_LIB") or os.path.join(_HERE, "libvqb200.so")   # VQB200_LIB: an experiment build of the same ABI
 
-ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05, ENGINE_TCGEN05_BF16 = 0, 1, 2, 3
-ENGINES = {"auto": ENGINE_AUTO, "simt": ENGINE_SIMT, "tcgen05": ENGINE_TCGEN05, "tcgen05_bf16": ENGINE_TCGEN05_BF16}
+ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05, ENGINE_TCGEN05_BF16, ENGINE_TCGEN05_TF32 = 0, 1, 2, 3, 4
+ENGINES = {"auto": ENGINE_AUTO, "simt": ENGINE_SIMT, "tcgen05": ENGINE_TCGEN05, "tcgen05_bf16": ENGINE_TCGEN05_BF16,
+           "tcgen05_tf32": ENGINE_TCGEN05_TF32}
 
 _p = C.c_void_p
 _i32, _i64, _f32, _sz = C.c_int32, C.c_int64, C.c_float, C.c_size_t
@@ -38,6 +39,7 @@ SIGNATURES = {
     "vqb200_pack_indices": (C.c_int, [_p, _i64, _i32, _i32, _p, _p, _p]),
     "vqb200_unpack_indices": (C.c_int, [_p, _i64, _i32, _p, _p]),
     "vqb200_debug_tc_scores": (C.c_int, [_p, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p]),
+    "vqb200_debug_tc_scores_ex": (C.c_int, [_p, _i64, _i32, _i32, _p, _p, _p, _p, _p, _i32, _p]),
     "vqb200_tc_split": (C.c_int, []),
     "vqb200_tc_supported": (C.c_int, [_p, _i64, _i32, _i32, _i64, _i64, _i64, _i64]),
     "vqb200_debug_tc_profile": (C.c_int, [_p, _i64, _i32, _i32, _p, _p, _p, _p, _p, _i32, _p]),

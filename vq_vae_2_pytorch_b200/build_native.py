@@ -7,6 +7,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvqb200.so")
+# experiments: VQB200_NVCC_DEFS="-DVQB200_ROLEMAP=1" VQB200_LIB_OUT=/path/libvqb200_exp.so python build_native.py --force
+EXTRA_DEFS = os.environ.get("VQB200_NVCC_DEFS", "").split()
+LIB_OUT = os.environ.get("VQB200_LIB_OUT", LIB)
 SOURCES = ["vqb200_abi.cu"]
 HEADERS = ["common.cuh", "simt_kernels.cuh", "tc_kernel.cuh", "tc_wide_kernel.cuh", "fused_kernels.cuh", os.path.join("..", "..", "include", "vqb200.h")]
 
@@ -27,18 +30,18 @@ def is_stale():
 
 
 def build(force=False, verbose=False):
-    if not force and not is_stale():
+    if not force and not is_stale() and LIB_OUT == LIB:
         return LIB
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
            "-Xcompiler", "-fPIC", "-shared"] + (["-DVQB200_P2P_TRACE"] if os.environ.get("VQB200_P2P_TRACE") else []) + [ "-Xptxas", "-v" if verbose else "-O3",
-           "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lcuda"]
+           "-o", LIB_OUT] + EXTRA_DEFS + [os.path.join(CSRC, s) for s in SOURCES] + ["-lcuda"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
         raise RuntimeError("nvcc failed building libvqb200.so")
     if verbose:
         sys.stderr.write(res.stdout + res.stderr)
-    return LIB
+    return LIB_OUT
 
 
 if __name__ == "__main__":

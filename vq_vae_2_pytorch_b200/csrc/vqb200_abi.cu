@@ -91,10 +91,11 @@ int forward_impl(const float* d_x, const RowLayout& L, int dim, int n_embed, con
     float* fin_diff = (finalize && d_diff) ? d_diff : nullptr;
     bool finalized = false;
     bool use_tc = false;
-    if (L.n_rows > 0 && (engine == VQB200_ENGINE_TCGEN05 || engine == VQB200_ENGINE_TCGEN05_BF16 || engine == VQB200_ENGINE_AUTO))
+    const bool tc_engine = engine == VQB200_ENGINE_TCGEN05 || engine == VQB200_ENGINE_TCGEN05_BF16 || engine == VQB200_ENGINE_TCGEN05_TF32;
+    if (L.n_rows > 0 && (tc_engine || engine == VQB200_ENGINE_AUTO))
         use_tc = tc_supported(L, d_x, dim, n_embed) || tcw_supported(L, d_x, dim, n_embed);
     const bool wide = use_tc && dim != tc::TC_D;  // tc_wide_kernel.cuh
-    if (L.n_rows > 0 && (engine == VQB200_ENGINE_TCGEN05 || engine == VQB200_ENGINE_TCGEN05_BF16) && !use_tc)
+    if (L.n_rows > 0 && tc_engine && !use_tc)
         return VQB200_EUNSUPPORTED;
     // statistics: private-table segmented reduction when [K][D] fp32 fits in shared memory (its fold kernel writes
     // d_stats, no memset needed), else the gather kernels fall back to global atomics on a cleared d_stats
@@ -105,7 +106,7 @@ int forward_impl(const float* d_x, const RowLayout& L, int dim, int n_embed, con
     const bool nchw = use_tc && !tc_layout_dense(L, d_x, dim);
     if (nchw && d_x_dense && (reinterpret_cast<uintptr_t>(d_x_dense) & 31u)) return VQB200_EINVAL;   // written with 256-bit stores
     if (nchw && stats_kernel && !d_x_dense) {
-        if (engine == VQB200_ENGINE_TCGEN05 || engine == VQB200_ENGINE_TCGEN05_BF16) return VQB200_EUNSUPPORTED;
+        if (tc_engine) return VQB200_EUNSUPPORTED;
         use_tc = false;
     }
     bool header_zeroed = false;
@@ -121,7 +122,7 @@ int forward_impl(const float* d_x, const RowLayout& L, int dim, int n_embed, con
         VQ_CUDA(cudaMemsetAsync(sc.flagged_count, 0, sizeof(int), st));
     }
     if (L.n_rows > 0) {
-        const int nsplit = engine == VQB200_ENGINE_TCGEN05_BF16 ? 1 : (engine == VQB200_ENGINE_TCGEN05 ? 3 : 0);
+        const int nsplit = engine == VQB200_ENGINE_TCGEN05_BF16 ? 1 : (engine == VQB200_ENGINE_TCGEN05 ? 3 : (engine == VQB200_ENGINE_TCGEN05_TF32 ? 0 : -1));
         if (stats_kernel) { sums = nullptr; counts = nullptr; }
         const bool want_gather = d_quantize || d_diff || sums;
         const size_t gsmem = (size_t)GS_BM * (dim + 1) * sizeof(float);
@@ -271,7 +272,7 @@ int vqb200_quantize_forward(const float* d_x, int64_t n_rows, int32_t dim, int32
     if (!d_codebook || !d_scratch || dim <= 0 || n_embed <= 0 || n_rows < 0) return VQB200_EINVAL;
     if (n_rows > 0 && (!d_x || !d_embed_ind)) return VQB200_EINVAL;
     if (n_rows > (int64_t)INT32_MAX) return VQB200_EUNSUPPORTED;
-    if (engine < VQB200_ENGINE_AUTO || engine > VQB200_ENGINE_TCGEN05_BF16) return VQB200_EINVAL;
+    if (engine < VQB200_ENGINE_AUTO || engine > VQB200_ENGINE_TCGEN05_TF32) return VQB200_EINVAL;
     if (n_rows > 0 && !layout_ok(n_rows, dim, rows_per_image, image_stride, row_stride, col_stride))
         return VQB200_EUNSUPPORTED;
     RowLayout L{n_rows, rows_per_image > 0 ? rows_per_image : 1, image_stride, row_stride, col_stride};
@@ -317,7 +318,7 @@ int vqb200_quantize_step(const float* d_x, int64_t n_rows, int32_t dim, int32_t 
     if (!d_codebook || !d_scratch || dim <= 0 || n_embed <= 0 || n_rows < 0) return VQB200_EINVAL;
     if (n_rows > 0 && (!d_x || !d_embed_ind)) return VQB200_EINVAL;
     if (n_rows > (int64_t)INT32_MAX) return VQB200_EUNSUPPORTED;
-    if (engine < VQB200_ENGINE_AUTO || engine > VQB200_ENGINE_TCGEN05_BF16) return VQB200_EINVAL;
+    if (engine < VQB200_ENGINE_AUTO || engine > VQB200_ENGINE_TCGEN05_TF32) return VQB200_EINVAL;
     if (n_rows > 0 && !layout_ok(n_rows, dim, rows_per_image, image_stride, row_stride, col_stride))
         return VQB200_EUNSUPPORTED;
     {
@@ -441,12 +442,20 @@ int vqb200_unpack_indices(const void* d_codes, int64_t n, int32_t in_bytes, int6
 int vqb200_debug_tc_scores(const float* d_x, int64_t n_rows, int32_t dim, int32_t n_embed, const void* d_codebook,
                            int64_t* d_embed_ind, float* d_scores, int32_t* d_flagged_count, void* d_scratch,
                            void* stream) {
+    return vqb200_debug_tc_scores_ex(d_x, n_rows, dim, n_embed, d_codebook, d_embed_ind, d_scores, d_flagged_count, d_scratch,
+                                     VQB200_ENGINE_TCGEN05, stream);
+}
+
+int vqb200_debug_tc_scores_ex(const float* d_x, int64_t n_rows, int32_t dim, int32_t n_embed, const void* d_codebook,
+                              int64_t* d_embed_ind, float* d_scores, int32_t* d_flagged_count, void* d_scratch,
+                              int32_t engine, void* stream) {
     if (!d_x || !d_codebook || !d_embed_ind || !d_scores || !d_scratch || n_rows <= 0) return VQB200_EINVAL;
+    if (engine != VQB200_ENGINE_TCGEN05 && engine != VQB200_ENGINE_TCGEN05_BF16 && engine != VQB200_ENGINE_TCGEN05_TF32) return VQB200_EINVAL;
     RowLayout L{n_rows, n_rows, 0, dim, 1};
     if (!tc_supported(L, d_x, dim, n_embed) && !tcw_supported(L, d_x, dim, n_embed)) return VQB200_EUNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     int rc = forward_impl(d_x, L, dim, n_embed, d_codebook, nullptr, d_embed_ind, nullptr, nullptr, d_scratch,
-                          VQB200_ENGINE_TCGEN05, true, false, n_rows, st, d_scores);
+                          engine, true, false, n_rows, st, d_scores);
     if (rc) return rc;
     if (d_flagged_count)
         VQ_CUDA(cudaMemcpyAsync(d_flagged_count, scratch_view(d_scratch, n_rows, dim, n_embed).flagged_count, sizeof(int),
@@ -467,7 +476,7 @@ int vqb200_debug_tc_profile(const float* d_x, int64_t n_rows, int32_t dim, int32
                             float* d_quantize, int64_t* d_embed_ind, void* d_scratch, uint64_t* d_prof, int32_t engine,
                             void* stream) {
     if (!d_x || !d_codebook || !d_embed_ind || !d_scratch || !d_prof || n_rows <= 0) return VQB200_EINVAL;
-    if (engine != VQB200_ENGINE_TCGEN05 && engine != VQB200_ENGINE_TCGEN05_BF16) return VQB200_EINVAL;
+    if (engine != VQB200_ENGINE_TCGEN05 && engine != VQB200_ENGINE_TCGEN05_BF16 && engine != VQB200_ENGINE_TCGEN05_TF32) return VQB200_EINVAL;
     RowLayout L{n_rows, n_rows, 0, dim, 1};
     if (!tc_supported(L, d_x, dim, n_embed)) return VQB200_EUNSUPPORTED;
     return forward_impl(d_x, L, dim, n_embed, d_codebook, d_quantize, d_embed_ind, nullptr, nullptr, d_scratch,
@@ -477,13 +486,13 @@ int vqb200_debug_tc_profile(const float* d_x, int64_t n_rows, int32_t dim, int32
 int vqb200_debug_tc_kernel(const float* d_x, int64_t n_rows, int32_t dim, int32_t n_embed, const void* d_codebook,
                            float* d_quantize, int64_t* d_embed_ind, void* d_scratch, int32_t engine, void* stream) {
     if (!d_x || !d_codebook || !d_embed_ind || !d_scratch || n_rows <= 0) return VQB200_EINVAL;
-    if (engine != VQB200_ENGINE_TCGEN05 && engine != VQB200_ENGINE_TCGEN05_BF16) return VQB200_EINVAL;
+    if (engine != VQB200_ENGINE_TCGEN05 && engine != VQB200_ENGINE_TCGEN05_BF16 && engine != VQB200_ENGINE_TCGEN05_TF32) return VQB200_EINVAL;
     RowLayout L{n_rows, n_rows, 0, dim, 1};
     if (!tc_supported(L, d_x, dim, n_embed)) return VQB200_EUNSUPPORTED;
     CodebookImage cb = codebook_view(const_cast<void*>(d_codebook), dim, n_embed);
     ForwardScratch sc = scratch_view(d_scratch, n_rows, dim, n_embed);
     int rc = tc_forward(d_x, L, dim, n_embed, cb, d_quantize, d_embed_ind, sc, sc.diff_acc, nullptr, nullptr, nullptr,
-                        (cudaStream_t)stream, nullptr, engine == VQB200_ENGINE_TCGEN05_BF16 ? 1 : 3);
+                        (cudaStream_t)stream, nullptr, engine == VQB200_ENGINE_TCGEN05_BF16 ? 1 : (engine == VQB200_ENGINE_TCGEN05_TF32 ? 0 : 3));
     g_launches.fetch_add(1);
     return rc ? cuda_fail(cudaGetLastError()) : VQB200_OK;
 }
