@@ -605,6 +605,7 @@ enum BarId { BAR_B = 0, BAR_XF = 1, BAR_XE = 5, BAR_AF = 9, BAR_AE = 13, BAR_TF 
 template <int NSPLIT, int AS, int XS, bool DBG, bool CTA2, bool NCHW = false>
 __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const __grid_constant__ Params p) {
     using P = Plan<NSPLIT, AS, XS, CTA2>;
+    constexpr bool TF = NSPLIT == 0;              // tf32 filter: MMAs read the fp32 x stage, "converters" only compute row norms
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -658,7 +659,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const __grid_constant__ Pa
     // ---- one-time setup -----------------------------------------------------------------------------
     if (threadIdx.x == 0) {
         mbar_init(bar(BAR_B), 1);
-        for (int s = 0; s < XS; ++s) { mbar_init(bar(BAR_XF + s), 1); mbar_init(bar(BAR_XE + s), NCHW ? 12 : 4); }   // converters (+ output warps: NCHW reads x from the stage)
+        // x stage released by: the converters (+ the output warps, NCHW: they read x from the stage); tf32: the commit behind the tile's last MMA
+        for (int s = 0; s < XS; ++s) { mbar_init(bar(BAR_XF + s), 1); mbar_init(bar(BAR_XE + s), TF ? 1 : (NCHW ? 12 : 4)); }
         for (int s = 0; s < AS; ++s) { mbar_init(bar(BAR_AF + s), PAIR_THREADS); mbar_init(bar(BAR_AE + s), 1); }
         for (int s = 0; s < NBUF; ++s) { mbar_init(bar(BAR_TF + s), 1); mbar_init(bar(BAR_TE + s), PAIR_THREADS); }
         mbar_init(bar(BAR_PB), 1);
@@ -700,6 +702,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const __grid_constant__ Pa
             constexpr uint32_t UROWS = UNIT_N / P::BDIV;
             for (int u = 0; u < U; ++u) {
                 const size_t krow = (size_t)u * UNIT_N + (size_t)crank * UROWS;
+                if (TF) {                        // two 32-dim k-blocks of tf32 rows + the tf32 misc rows
+                    bulk_g2s(sB + (uint32_t)u * UROWS * 128u, p.image + image_off_tf(K) + krow * 128, UROWS * 128u, bar(BAR_B));
+                    bulk_g2s(sB + P::off_b_lo(K) + (uint32_t)u * UROWS * 128u, p.image + image_off_tf(K) + (size_t)K * 128 + krow * 128, UROWS * 128u, bar(BAR_B));
+                    bulk_g2s(sB + P::off_b_misc(K) + (uint32_t)u * UROWS * 32u, p.image + image_off_tfmisc(K) + krow * 32, UROWS * 32u, bar(BAR_B));
+                    continue;
+                }
                 bulk_g2s(sB + (uint32_t)u * UROWS * 128u, p.image + krow * 128, UROWS * 128u, bar(BAR_B));
                 if (NSPLIT == 3)
                     bulk_g2s(sB + P::off_b_lo(K) + (uint32_t)u * UROWS * 128u, p.image + image_off_lo(K) + krow * 128, UROWS * 128u, bar(BAR_B));
@@ -712,8 +720,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const __grid_constant__ Pa
                 wait_r(BAR_XE + s, ph ^ 1u, 0, true);
                 const int64_t r0 = t * TILE_M;
                 const uint32_t rows = (uint32_t)max((int64_t)0, min((int64_t)TILE_M, p.n_rows - r0));
-                const uint32_t bytes = rows * TC_D * 4u;
+                const uint32_t bytes = TF ? (rows ? P::X_STAGE : 0u) : rows * TC_D * 4u;     // tensor-map boxes: rows past the end are zero-filled and counted
                 mbar_expect_tx(bar(BAR_XF + s), bytes);
+                if (TF && !NCHW) {               // two boxes of [128 rows][32 dims], 128-byte swizzle: the K-major tf32 A operand as it is
+                    if (bytes) {
+                        tma_load_2d_hint(sX + s * P::X_STAGE, &p.tmap, 0, (int)r0, bar(BAR_XF + s), keep);
+                        tma_load_2d_hint(sX + s * P::X_STAGE + 16384u, &p.tmap, 32, (int)r0, bar(BAR_XF + s), keep);
+                    }
+                } else
                 if (NCHW) {                      // one tiled TMA load: box [64 dims][128 rows] -> the stage holds x^T [d][row]
                     // (64 separate 512-byte bulk copies cost ~140 cycles each in the TMA unit: 126 us per launch)
                     if (bytes) tma_load_3d(sX + s * P::X_STAGE, &p.tmap, (int)(r0 % p.rpi), 0, (int)(r0 / p.rpi), bar(BAR_XF + s), keep);
@@ -736,6 +750,26 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const __grid_constant__ Pa
         const uint32_t b_lo0 = desc_lo(sB), bl_lo0 = desc_lo(sB + P::off_b_lo(K)), bm_lo0 = desc_lo(sB + P::off_b_misc(K));
         for (uint32_t it = 0; it < (crank == 0 ? n_iter : 0u); ++it) {     // the leader issues for the pair
             const uint32_t sa = it % AS, pha = (it / AS) & 1u;
+            if constexpr (TF) {
+                // products straight from the x stage as soon as it lands; the misc MMA of the first unit waits for the row norms
+                const uint32_t sx = it % XS, phx = (it / XS) & 1u;
+                wait_t(BAR_XF + sx, phx, 0, mrec);
+                tc_fence_after();
+                const uint32_t x_lo = desc_lo(sX + sx * P::X_STAGE), am_lo = desc_lo(sA + sa * P::A_STAGE);
+                for (int u = 0; u < U; ++u) {
+                    const uint32_t uc = it * (uint32_t)U + (uint32_t)u;
+                    const uint32_t buf = uc % NBUF, pht = (uc / NBUF) & 1u;
+                    wait_t(BAR_TE + buf, pht ^ 1u, 1, mrec);
+                    tc_fence_after();
+                    issue_unit_tf_products(tmem_base + buf * UNIT_N, x_lo, b_lo0 + (uint32_t)u * B_STEP, 16384u >> 4,
+                                           P::off_b_lo(K) >> 4, 2u, DESC_HI_SW128, IDESC_TF);
+                    if (u == 0) { wait_t(BAR_AF + sa, pha, 0, mrec); tc_fence_after(); }
+                    issue_unit_tf_misc(tmem_base + buf * UNIT_N, am_lo, bm_lo0 + (uint32_t)u * BM_STEP, bar(BAR_TF + buf));
+                }
+                commit_elected<false>(bar(BAR_XE + sx));      // all MMAs that read this x stage / these misc rows are done
+                commit_elected<false>(bar(BAR_AE + sa));
+                continue;
+            }
             if (CTA2) mbar_wait_cluster(bar(BAR_AF + sa), pha); else wait_t(BAR_AF + sa, pha, 0, mrec);
             tc_fence_after();
             const uint32_t a0 = sA + sa * P::A_STAGE;
@@ -750,6 +784,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const __grid_constant__ Pa
                     __syncwarp();
                 } else {
                     // misc block first (bias, offset, error bound: overwrites the accumulator), then the products
+                    if constexpr (!TF)
                     issue_unit<NSPLIT, CTA2>(tmem_base + buf * UNIT_N, am_lo, bm_lo0 + (uint32_t)u * BM_STEP, a_lo,
                                              b_lo0 + (uint32_t)u * B_STEP, al_lo, bl_lo0 + (uint32_t)u * B_STEP, bar(BAR_TF + buf));
                 }
@@ -779,6 +814,22 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const __grid_constant__ Pa
             unsigned char* am = ah + (P::A_STAGE - 4096u);
             const long long tc0 = (DBG && prof && rec) ? clock64() : 0;
             float my_sq = 1.f;
+            if constexpr (TF && !NCHW) {
+                // tf32: nothing to convert -- thread = row reads its 256 bytes from the two swizzled k-blocks (a quarter warp
+                // covers 8 rows x 16 bytes at 8 distinct chunk positions: conflict-free) for the row norm only
+                const int r = cw * 32 + lane;
+                const unsigned char* xr = xs + r * 128;
+                const uint32_t sw = (uint32_t)r & 7u;
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+                for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const float4 v = *reinterpret_cast<const float4*>(xr + kb * 16384 + (((uint32_t)c ^ sw) << 4));
+                        s0 = fmaf(v.x, v.x, s0); s1 = fmaf(v.y, v.y, s1); s2 = fmaf(v.z, v.z, s2); s3 = fmaf(v.w, v.w, s3);
+                    }
+                my_sq = (s0 + s1) + (s2 + s3);
+            } else
             if (NCHW) {
                 // the stage holds x^T [d][row]: thread = row (conflict-free 128-byte reads per dim), all 64 components pass
                 // through this thread, so the row norm needs no shuffles
@@ -849,7 +900,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const __grid_constant__ Pa
                 }
             }
             const long long tc1 = (DBG && prof && rec) ? clock64() : 0;
-            {
+            if constexpr (TF) {
+                const int r = cw * 32 + lane;
+                const float nx = sqrtf(my_sq);
+                float o1, o2, o3;
+                split3_tf32(my_sq * 1.001953125f, o1, o2, o3);          // off_i = ||x||^2 (1 + 2^-9)
+                const float nxu = tf32_rn(nx * 1.001953125f);           // ||x|| rounded up
+                *reinterpret_cast<float4*>(am + sw32_chunk_off((uint32_t)r, 0)) = make_float4(1.f, 1.f, 1.f, o1);
+                *reinterpret_cast<float4*>(am + sw32_chunk_off((uint32_t)r, 1)) = make_float4(o2, o3, nxu, 1.f);
+                rownorm_s[(it % NORM_RING) * TILE_M + r] = nx;
+            } else {
                 const int r = NCHW ? cw * 32 + lane : cw * 32 + 2 * q4 + half;
                 const float nx = sqrtf(my_sq);
                 float o1, o2, o3;
@@ -862,7 +922,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tc(const __grid_constant__ Pa
             const long long tc2 = (DBG && prof && rec) ? clock64() : 0;
             fence_async_smem();
             __syncwarp();
-            if (lane == 0) { arrive_mma_side(BAR_AF + sa); mbar_arrive(bar(BAR_XE + sx)); }
+            if (lane == 0) { arrive_mma_side(BAR_AF + sa); if (!TF) mbar_arrive(bar(BAR_XE + sx)); }
             if (DBG && prof && rec) {
                 const long long tc3 = clock64();
                 pacc[2] += tc1 - tc0; pacc[3] += tc2 - tc1; pacc[4] += tc3 - tc2;
@@ -1161,6 +1221,24 @@ inline int tc_encode_tmap(CUtensorMap* tm, const float* x, const RowLayout& L, i
                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS;
 }
 
+// dense x [N][64] for the tf32 filter: 2-D tensor map, box = 128 rows x 32 dims (one 128-byte swizzle row per x row and k-block);
+// two boxes per tile land as the K-major SWIZZLE_128B operand the tf32 MMAs read directly
+inline int tc_encode_tmap_dense_tf(CUtensorMap* tm, const float* x, int64_t n_rows) {
+    static PFN_cuTensorMapEncodeTiled encode = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess) f = nullptr;
+        return reinterpret_cast<PFN_cuTensorMapEncodeTiled>(f);
+    }();
+    if (!encode) return 1;
+    cuuint64_t gdim[2] = {(cuuint64_t)tc::TC_D, (cuuint64_t)n_rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)tc::TC_D * 4u};
+    cuuint32_t box[2] = {32u, (cuuint32_t)tc::TILE_M};
+    cuuint32_t estr[2] = {1u, 1u};
+    return encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS;
+}
+
 // CTAs the tensor-core kernel runs for n_rows rows (= number of private statistics tables it fills)
 inline int tc_grid(int64_t n_rows, bool pair) {
     int64_t n_tiles = (n_rows + tc::TILE_M - 1) / tc::TILE_M;
@@ -1206,10 +1284,12 @@ inline int tc_launch(const tc::Params& prm, cudaStream_t st) {
 inline int tc_forward(const float* x, const RowLayout& L, int dim, int n_embed, const CodebookImage& cb,
                       float* quantize, int64_t* embed_ind, const ForwardScratch& sc, double* diff_acc,
                       float* sums, float* counts, float* dbg_scores, cudaStream_t st,
-                      unsigned long long* prof = nullptr, int nsplit = 0, int* grid_out = nullptr,
+                      unsigned long long* prof = nullptr, int nsplit = -1, int* grid_out = nullptr,
                       float* x_dense = nullptr) {
-    if (nsplit != 1 && nsplit != 3) nsplit = tc_nsplit();
+    // nsplit: 3 = split-bf16 filter, 1 = plain bf16, 0 = tf32 (MMAs read the fp32 x stage), -1 = the build's default
+    if (nsplit != 0 && nsplit != 1 && nsplit != 3) nsplit = tc_nsplit();
     const bool nchw = !tc_layout_dense(L, x, dim);
+    if (nsplit == 0 && nchw) nsplit = 1;           // (the tf32 filter covers dense rows; NCHW-physical rows keep the bf16 kernels)
     (void)dim;
     static const bool pair = [] { const char* e = getenv("VQB200_TC_CTA2"); return e ? atoi(e) != 0 : true; }();
     static const bool pair1 = [] { const char* e = getenv("VQB200_TC_CTA2_BF16"); return e ? atoi(e) != 0 : false; }();
@@ -1224,6 +1304,7 @@ inline int tc_forward(const float* x, const RowLayout& L, int dim, int n_embed, 
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
     if (nchw && tc_encode_tmap(&tmap, x, L, dim)) return 1;
+    if (nsplit == 0 && tc_encode_tmap_dense_tf(&tmap, x, L.n_rows)) return 1;
     for (int sl = 0; sl < n_slices; ++sl) {
         tc::Params prm;
         prm.tmap = tmap;
@@ -1244,6 +1325,8 @@ inline int tc_forward(const float* x, const RowLayout& L, int dim, int n_embed, 
             if (nsplit == 3) rc = (pair && K_launch == 512) ? tc_launch<3, 1, 3, false, true, true>(prm, st) : tc_launch<3, 1, 1, false, false, true>(prm, st);
             else rc = getenv("VQB200_DBG_SKIP") ? tc_launch<1, 2, 3, true, false, true>(prm, st)      // (diagnostics: role skipping)
                                                 : tc_launch<1, 2, 3, false, false, true>(prm, st);
+        } else if (nsplit == 0) {
+            rc = dbg ? tc_launch<0, 2, 2, true, false>(prm, st) : tc_launch<0, 2, 2, false, false>(prm, st);
         } else if (nsplit == 3) {
             if (pair && K_launch == 512)           // CTA pairs: half the operand image per CTA -> double-buffered A and x
                 rc = dbg ? tc_launch<3, 2, 2, true, true>(prm, st) : tc_launch<3, 2, 2, false, true>(prm, st);
