@@ -238,6 +238,8 @@ class Quantize(nn.Module):
             return _native.ENGINE_AUTO
         f = self._filter
         pend = f["pending"]
+        if torch.cuda.is_current_stream_capturing():      # CUDA-graph capture: no event queries, keep the filter as it is
+            return _native.ENGINE_TCGEN05_BF16 if f["mode"] == "bf16" else _native.ENGINE_TCGEN05
         if pend is not None and pend[0].query():
             _, host_count, rows, mode_used = pend
             f["pending"] = None
@@ -252,6 +254,8 @@ class Quantize(nn.Module):
     def _note_flagged(self, ws, n, eng, dev):
         f = self._filter
         if eng != _native.ENGINE_TCGEN05_BF16 or self.engine != "auto" or f["pending"] is not None or n == 0:
+            return
+        if torch.cuda.is_current_stream_capturing():      # no pinned read-back / event inside a captured forward
             return
         f["calls"] = f.get("calls", 0) + 1
         if f["calls"] % self.FLAG_SAMPLE_EVERY != 1:
