@@ -332,7 +332,11 @@ def parity_multi(vq, dev, rank, world, dist):
             worst["multi_vs_single_rank"] = max(worst["multi_vs_single_rank"], scaled_max_err(m.embed_avg, ref.embed_avg, scale),
                                                 scaled_max_err(m.cluster_size, ref.cluster_size, ref.cluster_size.double().abs().clamp_min(1e-30)))
         worst["default_vs_nccl"] = max(worst["default_vs_nccl"], scaled_max_err(mods["default"].embed_avg, mods["nccl"].embed_avg, scale))
-        for m in mods.values():                                     # continue from one common state
+        # continue from ONE common state: the single-rank twin's summation order is not reproducible between processes
+        # (shared-memory adds of buckets that straddle two warps), so rank 0's twin is broadcast before it is loaded
+        for buf in (ref.embed, ref.cluster_size, ref.embed_avg):
+            dist.broadcast(buf, 0)
+        for m in mods.values():
             m.load_state_dict(ref.state_dict())
     res.update(worst)
     res["replicas_bit_identical"] = bool(identical)

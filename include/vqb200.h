@@ -111,6 +111,21 @@ int vqb200_ema_update_p2p(const void* const* h_stats_ptrs, void* const* h_flag_p
                           uint32_t step, float* d_cluster_size, float* d_embed_avg, float* d_embed,
                           int32_t dim, int32_t n_embed, float decay, float one_minus_decay, float eps,
                           void* d_codebook, void* stream);
+/* Multi-rank training forward in ONE call, PUSH form of the exchange that replaces dist_fn.all_reduce (vqvae.py:58-59 ->
+ * distributed/distributed.py:64-72), dim 64 / n_embed 256 or 512: forward as vqb200_quantize_step, then ONE kernel folds the
+ * per-CTA statistics tables, stores this rank's packed statistics [K*64 sums | K counts] into h_push_dst[r] = rank r's
+ * receive slot for THIS rank (peer-mapped pointers; r == rank: the local slot) block by block, publishes `step` to
+ * h_push_flags[r][block] (system-scope release), waits on the LOCAL flag array d_flags [world][K/4] (+ 2 time-out words at
+ * word 1024) for every block of every rank, sums the LOCAL receive slots h_recv[0..world) in rank order (bit-identical
+ * replicas) and applies vqvae.py:61-70.  No NCCL call, no remote load.  Slots and flags are double-buffered by the caller
+ * on the parity of `step` (1, 2, ...).  A peer that does not publish within 2 s: d_flags[1024] = step, [1025] = rank.      */
+int vqb200_quantize_step_peers(const float* d_x, int64_t n_rows, int32_t dim, int32_t n_embed, int64_t rows_per_image,
+                               int64_t image_stride, int64_t row_stride, int64_t col_stride, float* d_embed,
+                               float* d_cluster_size, float* d_embed_avg, void* d_codebook, float* d_quantize,
+                               int64_t* d_embed_ind, float* d_diff, void* d_scratch, float* d_x_dense, int32_t engine,
+                               float decay, float one_minus_decay, float eps, void* const* h_push_dst,
+                               void* const* h_push_flags, const void* const* h_recv, void* d_flags, int32_t rank,
+                               int32_t world, uint32_t step, void* stream);
 
 /* The module's whole forward in one call (fewer host round trips per step):
  *   vqb200_codebook_prepare(d_embed) + vqb200_quantize_forward(...) and, when `ema` != 0 and d_stats != NULL,

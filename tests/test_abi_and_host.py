@@ -43,8 +43,13 @@ def test_size_queries():
     # per 128-row tile dim/64 blocks of 16 KB + 4 KB misc rows + 512 B norms, and the float4 carried from slice to slice
     tiles = (1000 + 127) // 128
     extra = lib.vqb200_forward_scratch_bytes(1000, 256, 512) - lib.vqb200_forward_scratch_bytes(1000, 256, 256) \
-        - 160 * 256 * 257 * 4
+        - (512 - 256) * 4                      # rows-per-code counters [n_embed] (int32, 256-byte aligned)
     assert extra == tiles * (4 * 16384 + 4096 + 512) + 1000 * 16 + (-1000 * 16) % 256
+    # per-CTA statistics tables are reserved only where the statistics kernel can use them (table fits shared memory):
+    # 160 x K x (D+1) floats at D = 64, K = 512; nothing at D = 256, K = 8192 (was 1.35 GB)
+    assert lib.vqb200_forward_scratch_bytes(1000, 64, 512) >= 160 * 512 * 65 * 4
+    assert lib.vqb200_forward_scratch_bytes(1000, 256, 8192) < 64 * 1024 * 1024
+    assert lib.vqb200_forward_scratch_bytes(1000, 64, 16384) < 16 * 1024 * 1024
 
 
 def test_argument_validation_without_a_gpu():
@@ -59,6 +64,8 @@ def test_argument_validation_without_a_gpu():
     assert lib.vqb200_repack_rows(None, None, 10, 64, 10, 0, 64, 1, 1, None) == -1
     assert lib.vqb200_repack_rows(None, None, 0, 64, 1, 0, 64, 1, 1, None) == 0            # nothing to do
     assert lib.vqb200_ema_update_p2p(None, None, 0, 2, 1, None, None, None, 64, 512, 0.99, 0.01, 1e-5, None, None) == -1
+    assert lib.vqb200_quantize_step_peers(None, 10, 64, 512, 10, 0, 64, 1, None, None, None, None, None, None, None, None, None, 0,
+                                          0.99, 0.01, 1e-5, None, None, None, None, 0, 2, 1, None) == -1
     assert lib.vqb200_debug_tc_kernel(None, 10, 64, 512, None, None, None, None, 2, None) == -1
 
 

@@ -63,6 +63,9 @@ struct ForwardScratch {
     double* diff_acc;      // 1 double: sum (q-x)^2
     int* flagged_count;    // 1 int: rows sent to the exact re-score
     unsigned int* ticket;  // 1 word: last-block-done ticket of the fix-up / gather kernels (kept zero between launches)
+    unsigned int* ema_ticket;  // 1 word: last-block-done ticket of the fold + EMA kernel
+    unsigned int* n_parts;     // 1 word: number of per-CTA statistics tables the statistics kernel of this call wrote
+    int* code_counts;      // [n_embed] rows per code of this call (integer atomics of the statistics kernel; cleared with the header)
     int* flagged_rows;     // [n_rows] row ids
     float4* partial;       // [n_rows] running (m1, m2, winner, ||e_winner||) of the sliced tensor-core engine (n_embed > 512), else null
     float* stat_partials;  // [STAT_PARTS][K*(D+1)] per-CTA statistics tables
@@ -80,10 +83,16 @@ __host__ __device__ inline size_t scratch_wide_bytes(int64_t n_rows, int dim) {
     const size_t tiles = (size_t)((n_rows + 127) / 128);
     return tiles * ((size_t)(dim / 64) * 16384 + 4096 + 512);
 }
+// per-CTA statistics tables exist only for shapes whose [K][D] table fits the statistics kernel's shared memory (other shapes
+// use global atomics): 21 MB at D = 64, K = 512 -- and nothing (instead of 1.35 GB) at D = 256, K = 8192
+__host__ __device__ inline bool scratch_has_stat_tables(int dim, int n_embed) {
+    return (size_t)n_embed * dim * 4 + (size_t)(4 * n_embed + 2) * 4 + 4096 * 12 + 16 <= 200 * 1024 && n_embed <= 65535;   // = code_stats_smem_bytes <= 200 KB
+}
 __host__ __device__ inline size_t forward_scratch_bytes(int64_t n_rows, int dim, int n_embed) {
-    return 256 + align_up((size_t)n_rows * 4, 256) + (scratch_has_partial(dim, n_embed) ? align_up((size_t)n_rows * 16, 256) : 0) +
+    return 256 + align_up((size_t)n_embed * 4, 256) + align_up((size_t)n_rows * 4, 256) +
+           (scratch_has_partial(dim, n_embed) ? align_up((size_t)n_rows * 16, 256) : 0) +
            (scratch_has_wide(dim, n_embed) ? scratch_wide_bytes(n_rows, dim) : 0) +
-           (size_t)STAT_PARTS * n_embed * (dim + 1) * 4;
+           (scratch_has_stat_tables(dim, n_embed) ? (size_t)STAT_PARTS * n_embed * (dim + 1) * 4 : 0);
 }
 __host__ __device__ inline ForwardScratch scratch_view(void* base, int64_t n_rows, int dim, int n_embed) {
     unsigned char* p = (unsigned char*)base;
@@ -91,8 +100,12 @@ __host__ __device__ inline ForwardScratch scratch_view(void* base, int64_t n_row
     s.diff_acc = (double*)p;
     s.flagged_count = (int*)(p + 16);
     s.ticket = (unsigned int*)(p + 32);
-    s.flagged_rows = (int*)(p + 256);
-    p += 256 + align_up((size_t)n_rows * 4, 256);
+    s.ema_ticket = (unsigned int*)(p + 48);
+    s.n_parts = (unsigned int*)(p + 52);
+    s.code_counts = (int*)(p + 256);
+    p += 256 + align_up((size_t)n_embed * 4, 256);
+    s.flagged_rows = (int*)p;
+    p += align_up((size_t)n_rows * 4, 256);
     s.partial = nullptr;
     if (scratch_has_partial(dim, n_embed)) { s.partial = (float4*)p; p += align_up((size_t)n_rows * 16, 256); }
     s.wide_a = nullptr; s.wide_m = nullptr; s.wide_norm = nullptr;

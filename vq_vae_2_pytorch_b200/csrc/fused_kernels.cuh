@@ -24,7 +24,10 @@ __global__ void __launch_bounds__(256) k_prepare64(const float* __restrict__ emb
     pdl_wait();
     pdl_trigger();
     const int k0 = blockIdx.x * PREP_CODES, tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
-    if (zero_header && blockIdx.x == 0 && tid < 64) zero_header[tid] = 0u;   // loss accumulator, flagged-row counter, ticket (saves a memset node)
+    if (zero_header) {                        // (saves a memset node in the chain)
+        if (blockIdx.x == 0 && tid < 64) zero_header[tid] = 0u;              // loss accumulator, flagged-row counter, tickets
+        if (tid < PREP_CODES) zero_header[64 + k0 + tid] = 0u;               // rows-per-code counters of this call (ForwardScratch::code_counts)
+    }
     for (int i = tid; i < 64 * PREP_CODES; i += 256) {          // 32-byte segments of 8 consecutive codes per dim
         const int d = i >> 3, j = i & 7;
         es[j][d] = embed[(size_t)d * K + k0 + j];
@@ -57,6 +60,7 @@ __global__ void __launch_bounds__(256) k_prepare64(const float* __restrict__ emb
 // per-rank statistics over NVLink in RANK ORDER (identical result on every rank, so the replicas stay bit-identical).
 // ------------------------------------------------------------------------------------------------
 constexpr int P2P_MAX_RANKS = 8;
+constexpr unsigned long long P2P_TIMEOUT_NS = 2000000000ull;   // 2 s: far beyond any step, short enough to fail loudly
 struct PeerStats {
     const float* stats[P2P_MAX_RANKS];     // rank r's packed statistics of this step (this process' mapping)
     unsigned int* flags[P2P_MAX_RANKS];    // rank r's flag array [world]: flags[r][w] = last step rank w has published
@@ -115,8 +119,26 @@ __global__ void __launch_bounds__(256) k_ema64(const float* __restrict__ stats, 
         if (blockIdx.x == 0 && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
 #endif
         if (tid < peers.world) {
+            // bounded wait (a crashed or desynchronised peer must not hang this GPU for ever): after P2P_TIMEOUT_NS the
+            // block gives up, records (step, missing rank) in word 32 / 33 of its flag array -- the host reads it back
+            // (Quantize raises) -- and carries on with whatever the slots hold
             const unsigned int* f = peers.flags[peers.rank] + tid;
-            while ((int)(ld_acquire_sys(f) - peers.step) < 0) __nanosleep(64);
+            unsigned long long t0 = 0;
+            unsigned int spins = 0;
+            while ((int)(ld_acquire_sys(f) - peers.step) < 0) {
+                __nanosleep(64);
+                if ((++spins & 1023u) == 0) {
+                    unsigned long long now;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                    if (t0 == 0) t0 = now;
+                    else if (now - t0 > P2P_TIMEOUT_NS) {
+                        unsigned int* err = peers.flags[peers.rank] + 32;
+                        err[1] = (unsigned int)tid;
+                        atomicExch(err, peers.step);
+                        break;
+                    }
+                }
+            }
         }
         __syncthreads();
 #ifdef VQB200_P2P_TRACE
@@ -255,6 +277,170 @@ k_fixup(const float* __restrict__ x, RowLayout L, int D, int K, const float* __r
     if (last_s && tid == 0) {
         *ticket = 0u;
         if (diff) diff[0] = (float)(*reinterpret_cast<volatile double*>(diff_acc) * inv_count);
+    }
+}
+
+}  // namespace vqb200
+
+namespace vqb200 {
+
+// ------------------------------------------------------------------------------------------------
+// Fold + [exchange] + EMA in ONE launch (vqvae.py:55-70): replaces k_stats_fold / k_stats_fold_push + k_ema64.
+// grid = K / 4 blocks of 1024 threads; block b owns codes 4b .. 4b+3.
+//   fold      the block sums ITS 256 statistics elements over the per-CTA tables of the statistics kernel (4 thread groups,
+//             each over every 4th table, combined in a fixed order -> deterministic); the rows-per-code counts come from the
+//             integer atomics of the statistics kernel (ForwardScratch::code_counts), so nothing else has to be folded;
+//   exchange  (P2P) PUSH form: the block stores its 256 sums + 4 counts into slot `rank` of EVERY rank's receive buffer
+//             (posted NVLink stores), one system-scope fence, then a flag per (rank, block) on every peer; it then waits on
+//             its LOCAL flags for all blocks of all ranks (every block needs all K counts for n = sum cluster_size) and
+//             sums the local slots in RANK ORDER -> identical bits on every rank, no remote load, no NCCL call;
+//   EMA       as k_ema64: decay, Laplace-smoothed renormalisation, embed / embed_avg in place, next codebook image,
+//             cluster_size stored by the last block (every block derives n from the OLD values).
+// A peer that does not publish within P2P_TIMEOUT_NS: (step, rank) recorded behind the flags, host raises.
+// ------------------------------------------------------------------------------------------------
+constexpr int EF_CODES = 4, EF_THREADS = 1024;
+struct PeerFold {
+    float* push_dst[P2P_MAX_RANKS];            // rank r's receive slot for MY statistics ([K*64 sums | K counts])
+    unsigned int* push_flag[P2P_MAX_RANKS];    // rank r's flag row for me: one word per EMA block
+    const float* recv[P2P_MAX_RANKS];          // my local receive slots, one per rank
+    unsigned int* flags;                       // my local flags [world][gridDim.x], then 2 time-out words
+    int rank, world;
+    unsigned int step;
+};
+
+template <bool P2P>
+__global__ void __launch_bounds__(EF_THREADS) k_ema64f(const float* __restrict__ partials, const unsigned int* __restrict__ n_parts_ptr,
+                                                        const int* __restrict__ code_counts, PeerFold peers,
+                                                        float* __restrict__ cluster_size, float* __restrict__ embed_avg,
+                                                        float* __restrict__ embed, float* __restrict__ cbT, float* __restrict__ ee,
+                                                        unsigned char* __restrict__ img, int K, float decay, float one_minus_decay,
+                                                        float eps, float cA, float cA1, float cB, unsigned int* __restrict__ ticket) {
+    __shared__ float red[4][EF_CODES * 64];
+    __shared__ float es[EF_CODES][65];
+    __shared__ float ssum[EF_CODES][65];
+    __shared__ float cnt_s[512];                                // K <= 512 (tc_shape_ok)
+    __shared__ float e2s[EF_CODES];
+    __shared__ float part[32];
+    __shared__ float n_s;
+    __shared__ unsigned int last_s;
+    pdl_wait();
+    pdl_trigger();
+    const int k0 = blockIdx.x * EF_CODES, tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    const int n_parts = (int)*n_parts_ptr, nstat = K * 65;
+    // ---- fold: element e of my 256 (code e / 64, dim e % 64), thread group g over the tables g, g + 4, ...
+    {
+        const int e = tid & 255, g = tid >> 8;
+        const float* src = partials + (size_t)k0 * 64 + e;
+        float s = 0.f;
+#pragma unroll 8
+        for (int c = g; c < n_parts; c += 4) s += __ldcs(src + (size_t)c * nstat);
+        red[g][e] = s;
+    }
+    __syncthreads();
+    float tot = 0.f;
+    if (tid < 256) tot = ((red[0][tid] + red[1][tid]) + red[2][tid]) + red[3][tid];
+    if constexpr (P2P) {
+        // ---- push my block of statistics to every rank (mine included), then one flag per rank
+        if (tid < 256) {
+#pragma unroll
+            for (int r = 0; r < P2P_MAX_RANKS; ++r)
+                if (r < peers.world) peers.push_dst[r][(size_t)k0 * 64 + tid] = tot;
+        } else if (tid < 256 + EF_CODES) {
+            const float c = (float)code_counts[k0 + tid - 256];
+#pragma unroll
+            for (int r = 0; r < P2P_MAX_RANKS; ++r)
+                if (r < peers.world) peers.push_dst[r][(size_t)K * 64 + k0 + tid - 256] = c;
+        }
+        __syncthreads();                          // the block's stores happen-before the flag stores below (cumulative release)
+        if (tid < peers.world) st_release_sys(peers.push_flag[tid] + blockIdx.x, peers.step);
+        // ---- wait for every block of every rank (bounded), on local memory
+        const int n_flags = peers.world * (int)gridDim.x;
+        if (tid < n_flags) {
+            const unsigned int* f = peers.flags + tid;
+            unsigned long long t0 = 0;
+            unsigned int spins = 0;
+            while ((int)(ld_acquire_sys(f) - peers.step) < 0) {
+                __nanosleep(32);
+                if ((++spins & 1023u) == 0) {
+                    unsigned long long now;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                    if (t0 == 0) t0 = now;
+                    else if (now - t0 > P2P_TIMEOUT_NS) {
+                        unsigned int* err = peers.flags + P2P_MAX_RANKS * 128;
+                        err[1] = (unsigned int)(tid / (int)gridDim.x);
+                        atomicExch(err, peers.step);
+                        break;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // ---- rank-ordered sums of the local slots
+        if (tid < 256) {
+            float v[P2P_MAX_RANKS];
+#pragma unroll
+            for (int r = 0; r < P2P_MAX_RANKS; ++r) v[r] = r < peers.world ? __ldcg(peers.recv[r] + (size_t)k0 * 64 + tid) : 0.f;
+            tot = rank_ordered_sum(v);
+        }
+        if (tid >= 512 && tid - 512 < K) {
+            const int k = tid - 512;
+            float v[P2P_MAX_RANKS];
+#pragma unroll
+            for (int r = 0; r < P2P_MAX_RANKS; ++r) v[r] = r < peers.world ? __ldcg(peers.recv[r] + (size_t)K * 64 + k) : 0.f;
+            cnt_s[k] = rank_ordered_sum(v);
+        }
+    } else {
+        if (tid >= 512 && tid - 512 < K) cnt_s[tid - 512] = (float)code_counts[tid - 512];
+    }
+    if (tid < 256) ssum[tid >> 6][tid & 63] = tot;
+    __syncthreads();
+    // ---- n = sum_k cluster_size_new[k] from the OLD cluster sizes (vqvae.py:61-65)
+    float s = 0.f;
+    if (tid < K) s = __fmaf_rn(cnt_s[tid], one_minus_decay, __fmul_rn(cluster_size[tid], decay));
+    s = warp_sum(s);
+    if (lane == 0) part[w] = s;
+    __syncthreads();
+    if (tid == 0) {
+        float n = 0.f;
+        for (int i = 0; i < (K + 31) / 32; ++i) n += part[i];
+        n_s = n;
+    }
+    __syncthreads();
+    const float n = n_s;
+    const float denom = n + (float)((double)K * (double)eps);
+    if (tid < 64 * EF_CODES) {                                   // 16-byte segments of 4 consecutive codes per dim
+        const int d = tid >> 2, j = tid & 3, k = k0 + j;
+        const float c = __fmaf_rn(cnt_s[k], one_minus_decay, __fmul_rn(cluster_size[k], decay));
+        const float cs = (c + eps) / denom * n;                 // vqvae.py:66-68
+        const size_t o = (size_t)d * K + k;
+        const float a = __fmaf_rn(ssum[j][d], one_minus_decay, __fmul_rn(embed_avg[o], decay));       // vqvae.py:64
+        embed_avg[o] = a;
+        const float e = a / cs;                                 // vqvae.py:69-70
+        embed[o] = e;
+        es[j][d] = e;
+    }
+    __syncthreads();
+    if (w < EF_CODES) {
+        const float v0 = es[w][lane], v1 = es[w][lane + 32];
+        if (cbT) {
+            cbT[(size_t)(k0 + w) * 64 + lane] = v0;
+            cbT[(size_t)(k0 + w) * 64 + lane + 32] = v1;
+        }
+        float s2 = fmaf(v0, v0, 0.f);
+        s2 = fmaf(v1, v1, s2);
+        s2 = warp_sum(s2);
+        if (lane == 0) { if (ee) ee[k0 + w] = s2; e2s[w] = s2; }
+    }
+    __syncthreads();
+    if (img && tid < 8 * EF_CODES)
+        tc::tc_image_rows(&es[tid >> 3][0], e2s[tid >> 3], img, K, k0 + (tid >> 3), tid & 7, cA, cA1, cB);
+    // ---- deferred cluster_size store: only after every block has read the old values
+    __threadfence();
+    if (tid == 0) last_s = (atomicAdd(ticket, 1u) == gridDim.x - 1u) ? 1u : 0u;
+    __syncthreads();
+    if (last_s) {
+        if (tid < K) cluster_size[tid] = __fmaf_rn(cnt_s[tid], one_minus_decay, __fmul_rn(cluster_size[tid], decay));
+        if (tid == 0) *ticket = 0u;                             // clean for the next launch
     }
 }
 

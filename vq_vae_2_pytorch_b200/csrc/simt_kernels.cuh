@@ -252,7 +252,9 @@ __device__ __forceinline__ void smem_add(float* p, float v) { atomicAdd(p, v); }
 
 __global__ void __launch_bounds__(CS_THREADS, 1)
 k_code_stats(const float* __restrict__ x, RowLayout L, int D, int K, const int64_t* __restrict__ embed_ind,
-             float* __restrict__ partials /* [gridDim.x][K*(D+1)] */, int chunk /* rows per trip, <= CS_CHUNK */) {
+             float* __restrict__ partials /* [gridDim.x][K*(D+1)] */, int chunk /* rows per trip, <= CS_CHUNK */,
+             int* __restrict__ code_counts /* may be null: [K] += rows per code (integer atomics: exact, order-free) */,
+             unsigned int* __restrict__ n_parts_out /* may be null: receives gridDim.x */) {
     // layout: the int64 array first (dynamic shared memory is 16-byte aligned; behind [K][D] floats it would only be
     // 4-byte aligned when K*D is odd, e.g. Quantize(3, 5): misaligned 8-byte shared stores), then the 4-byte arrays,
     // then the 2-byte arrays
@@ -401,7 +403,11 @@ k_code_stats(const float* __restrict__ x, RowLayout L, int D, int K, const int64
     __syncthreads();
     float* out = partials + (size_t)blockIdx.x * K * (D + 1);
     for (int i = tid; i < K * D; i += CS_THREADS) out[i] = table[i];
-    for (int i = tid; i < K; i += CS_THREADS) out[(size_t)K * D + i] = (float)cnt_total[i];
+    for (int i = tid; i < K; i += CS_THREADS) {
+        out[(size_t)K * D + i] = (float)cnt_total[i];
+        if (code_counts && cnt_total[i]) atomicAdd(code_counts + i, cnt_total[i]);
+    }
+    if (n_parts_out && blockIdx.x == 0 && tid == 0) *n_parts_out = gridDim.x;
 }
 
 // stats[i] (+)= sum over CTAs of partials[c][i].  block = (32, FOLD_Y): 128 consecutive elements per block as four

@@ -80,7 +80,7 @@ int forward_impl(const float* d_x, const RowLayout& L, int dim, int n_embed, con
                  float* d_quantize, int64_t* d_ind, float* d_diff, float* d_stats, void* d_scratch,
                  int engine, bool zero_first, bool finalize, int64_t total_rows, cudaStream_t st,
                  float* dbg_scores = nullptr, int64_t scratch_rows = -1, unsigned long long* prof = nullptr,
-                 float* d_x_dense = nullptr, const float* d_embed_prepare = nullptr) {
+                 float* d_x_dense = nullptr, const float* d_embed_prepare = nullptr, bool defer_fold = false) {
     if (scratch_rows < 0) scratch_rows = total_rows;
     CodebookImage cb = codebook_view(const_cast<void*>(d_codebook), dim, n_embed);
     ForwardScratch sc = scratch_view(d_scratch, scratch_rows, dim, n_embed);
@@ -117,7 +117,8 @@ int forward_impl(const float* d_x, const RowLayout& L, int dim, int n_embed, con
         if (rc) return rc;
     }
     if (zero_first) {
-        if (!header_zeroed) VQ_CUDA(cudaMemsetAsync(sc.diff_acc, 0, 256, st));      // loss accumulator, flagged-row counter, ticket
+        // loss accumulator, flagged-row counter, tickets + the rows-per-code counters behind them
+        if (!header_zeroed) VQ_CUDA(cudaMemsetAsync(sc.diff_acc, 0, 256 + align_up((size_t)n_embed * 4, 256), st));
     } else if (use_tc) {
         VQ_CUDA(cudaMemsetAsync(sc.flagged_count, 0, sizeof(int), st));
     }
@@ -172,8 +173,9 @@ int forward_impl(const float* d_x, const RowLayout& L, int dim, int n_embed, con
             const bool from_dense = use_tc && nchw;
             const RowLayout Ld{L.n_rows, L.n_rows, 0, dim, 1};
             VQ_CUDA(launch_pdl(k_code_stats, dim3(parts), dim3(CS_THREADS), cs_smem, st, from_dense ? d_x_dense : d_x,
-                               from_dense ? Ld : L, dim, n_embed, d_ind, sc.stat_partials, (int)chunk));
+                               from_dense ? Ld : L, dim, n_embed, d_ind, sc.stat_partials, (int)chunk, sc.code_counts, sc.n_parts));
             g_launches.fetch_add(1);
+            if (defer_fold) return VQB200_OK;     // the caller's fold + EMA kernel consumes the per-CTA tables (finalize ran in k_fixup / k_gather_stats)
             // d_stats (+)= sum of the per-CTA tables: overwrite on the first call, accumulate on host-path continuation chunks
             const int nstat = n_embed * (dim + 1);
             VQ_CUDA(launch_pdl(k_stats_fold, dim3((nstat + 127) / 128), dim3(32, FOLD_Y), 0, st, sc.stat_partials, parts, nstat,
@@ -222,6 +224,23 @@ int ema_impl(const float* d_stats, const PeerStats* peers, float* d_cluster_size
         VQ_CUDA(tcw_prepare(cb, dim, n_embed, st));
         g_launches.fetch_add(1);
     }
+    return VQB200_OK;
+}
+
+// fold of the per-CTA statistics tables + [exchange over peer memory] + EMA in one launch (k_ema64f); dim 64, n_embed 256 / 512
+int fold_ema_launch(const ForwardScratch& sc, const PeerFold* peers, float* d_cluster_size, float* d_embed_avg, float* d_embed,
+                    int n_embed, float decay, float one_minus_decay, float eps, cudaStream_t st) {
+    PeerFold none{};
+    const dim3 grid(n_embed / EF_CODES), block(EF_THREADS);
+    if (peers)
+        VQ_CUDA(launch_pdl(k_ema64f<true>, grid, block, 0, st, sc.stat_partials, sc.n_parts, sc.code_counts, *peers, d_cluster_size,
+                           d_embed_avg, d_embed, (float*)nullptr, (float*)nullptr, (unsigned char*)nullptr, n_embed, decay,
+                           one_minus_decay, eps, tc::bound_cA(3), tc::bound_cA(1), tc::BOUND_CB, sc.ema_ticket));
+    else
+        VQ_CUDA(launch_pdl(k_ema64f<false>, grid, block, 0, st, sc.stat_partials, sc.n_parts, sc.code_counts, none, d_cluster_size,
+                           d_embed_avg, d_embed, (float*)nullptr, (float*)nullptr, (unsigned char*)nullptr, n_embed, decay,
+                           one_minus_decay, eps, tc::bound_cA(3), tc::bound_cA(1), tc::BOUND_CB, sc.ema_ticket));
+    g_launches.fetch_add(1);
     return VQB200_OK;
 }
 
@@ -323,12 +342,53 @@ int vqb200_quantize_step(const float* d_x, int64_t n_rows, int32_t dim, int32_t 
         return VQB200_EUNSUPPORTED;
     {
         RowLayout L{n_rows, rows_per_image > 0 ? rows_per_image : 1, image_stride, row_stride, col_stride};
+        // dim 64, n_embed 256 / 512 with the EMA requested: the per-CTA statistics tables are folded INSIDE the EMA kernel
+        // (one launch instead of k_stats_fold + k_ema64; d_stats is not written)
+        if (ema && d_stats && tc_shape_ok(dim, n_embed)) {
+            ForwardScratch sc = scratch_view(d_scratch, n_rows, dim, n_embed);
+            rc = forward_impl(d_x, L, dim, n_embed, d_codebook, d_quantize, d_embed_ind, d_diff, d_stats, d_scratch, engine, true,
+                              true, n_rows, (cudaStream_t)stream, nullptr, -1, nullptr, d_x_dense, d_embed, true);
+            if (rc) return rc;
+            return fold_ema_launch(sc, nullptr, d_cluster_size, d_embed_avg, d_embed, n_embed, decay, one_minus_decay, eps,
+                                   (cudaStream_t)stream);
+        }
         rc = forward_impl(d_x, L, dim, n_embed, d_codebook, d_quantize, d_embed_ind, d_diff, d_stats, d_scratch, engine, true,
                           true, n_rows, (cudaStream_t)stream, nullptr, -1, nullptr, d_x_dense, d_embed);
     }
     if (rc || !ema || !d_stats) return rc;
     return vqb200_ema_update(d_stats, d_cluster_size, d_embed_avg, d_embed, dim, n_embed, decay, one_minus_decay, eps,
                              nullptr, stream);
+}
+
+int vqb200_quantize_step_peers(const float* d_x, int64_t n_rows, int32_t dim, int32_t n_embed, int64_t rows_per_image,
+                               int64_t image_stride, int64_t row_stride, int64_t col_stride, float* d_embed,
+                               float* d_cluster_size, float* d_embed_avg, void* d_codebook, float* d_quantize,
+                               int64_t* d_embed_ind, float* d_diff, void* d_scratch, float* d_x_dense, int32_t engine,
+                               float decay, float one_minus_decay, float eps, void* const* h_push_dst, void* const* h_push_flags,
+                               const void* const* h_recv, void* d_flags, int32_t rank, int32_t world, uint32_t step, void* stream) {
+    if (!d_embed || !d_cluster_size || !d_embed_avg || !d_codebook || !d_scratch || dim <= 0 || n_embed <= 0) return VQB200_EINVAL;
+    if (n_rows < 0 || (n_rows > 0 && (!d_x || !d_embed_ind))) return VQB200_EINVAL;
+    if (!h_push_dst || !h_push_flags || !h_recv || !d_flags) return VQB200_EINVAL;
+    if (world < 1 || world > P2P_MAX_RANKS || rank < 0 || rank >= world || step == 0) return VQB200_EINVAL;
+    if (n_rows > (int64_t)INT32_MAX) return VQB200_EUNSUPPORTED;
+    if (engine < VQB200_ENGINE_AUTO || engine > VQB200_ENGINE_TCGEN05_TF32) return VQB200_EINVAL;
+    if (n_rows > 0 && !layout_ok(n_rows, dim, rows_per_image, image_stride, row_stride, col_stride)) return VQB200_EUNSUPPORTED;
+    if (!tc_shape_ok(dim, n_embed)) return VQB200_EUNSUPPORTED;      // the fold + EMA kernel: dim 64, n_embed 256 / 512
+    PeerFold pf{};
+    for (int r = 0; r < world; ++r) {
+        if (!h_push_dst[r] || !h_push_flags[r] || !h_recv[r]) return VQB200_EINVAL;
+        pf.push_dst[r] = static_cast<float*>(h_push_dst[r]);
+        pf.push_flag[r] = static_cast<unsigned int*>(h_push_flags[r]);
+        pf.recv[r] = static_cast<const float*>(h_recv[r]);
+    }
+    pf.flags = static_cast<unsigned int*>(d_flags);
+    pf.rank = rank; pf.world = world; pf.step = step;
+    RowLayout L{n_rows, rows_per_image > 0 ? rows_per_image : 1, image_stride, row_stride, col_stride};
+    ForwardScratch sc = scratch_view(d_scratch, n_rows, dim, n_embed);
+    int rc = forward_impl(d_x, L, dim, n_embed, d_codebook, d_quantize, d_embed_ind, d_diff, sc.stat_partials, d_scratch, engine,
+                          true, true, n_rows, (cudaStream_t)stream, nullptr, -1, nullptr, d_x_dense, d_embed, true);
+    if (rc) return rc;
+    return fold_ema_launch(sc, &pf, d_cluster_size, d_embed_avg, d_embed, n_embed, decay, one_minus_decay, eps, (cudaStream_t)stream);
 }
 
 int vqb200_repack_rows(const float* d_src, float* d_dst, int64_t n_rows, int32_t dim, int64_t rows_per_image,

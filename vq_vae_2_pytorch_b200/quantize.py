@@ -183,10 +183,11 @@ class Quantize(nn.Module):
 
     # ------------------------------------------------------------------ peer memory for the fused all-reduce
     def _peer_workspace(self, ws, dev):
-        """Symmetric (peer-mapped) statistics buffers of all ranks, set up collectively on the first multi-rank training
-        forward: two packed statistics buffers + two flag arrays per rank (double-buffered by step parity).  Returns None
-        (-> NCCL all-reduce + vqb200_ema_update) when peer memory is unavailable, the world is larger than 8 ranks, the
-        shape is outside the fused EMA kernel, or VQB200_NO_P2P is set."""
+        """Symmetric (peer-mapped) receive buffers of all ranks, set up collectively on the first multi-rank training forward:
+        per step parity, one receive slot per rank for the packed statistics + one flag array (PUSH form of the exchange:
+        every rank's fold kernel stores its statistics into slot `rank` of every rank's buffer, the EMA kernel reads local
+        memory only).  Returns None (-> NCCL all-reduce + vqb200_ema_update) when peer memory is unavailable, the world is
+        larger than 8 ranks, the shape is outside the fused EMA kernel, or VQB200_NO_P2P is set."""
         if "peer" in ws:
             return ws["peer"]
         ws["peer"] = None
@@ -199,7 +200,10 @@ class Quantize(nn.Module):
                 import torch.distributed._symmetric_memory as symm
                 n = _native.load().vqb200_stats_bytes(self.dim, self.n_embed) // 4
                 n_al = (n + 63) // 64 * 64
-                total = 2 * n_al + 2 * 64                      # [stats parity 0 | stats parity 1 | flags 0 | flags 1]
+                slots = world * n_al
+                nb = self.n_embed // 4               # blocks of the fold + EMA kernel: one flag per (rank, block)
+                fl = 8 * 128 + 64                    # flag words per parity: [8 ranks][128 blocks] + time-out words
+                total = 2 * slots + 2 * fl           # [slots parity 0 | slots parity 1 | flags 0 | flags 1]
                 buf = symm.empty(total, dtype=torch.float32, device=dev)
                 hdl = symm.rendezvous(buf, dist.group.WORLD)
                 buf.zero_()
@@ -207,10 +211,14 @@ class Quantize(nn.Module):
                 hdl.barrier()
                 ptrs = [int(p) for p in hdl.buffer_ptrs]
                 mk = lambda vals: (C.c_void_p * world)(*vals)
-                peer = {"buf": buf, "hdl": hdl, "rank": rank, "world": world, "step": 0, "parity": 0,
-                        "stats": [buf[0:n], buf[n_al:n_al + n]],
-                        "stats_ptrs": [mk([p + 4 * par * n_al for p in ptrs]) for par in (0, 1)],
-                        "flag_ptrs": [mk([p + 4 * (2 * n_al + 64 * par) for p in ptrs]) for par in (0, 1)]}
+                peer = {"buf": buf, "hdl": hdl, "rank": rank, "world": world, "step": 0, "parity": 0, "checked": 0,
+                        # where MY statistics go on rank r, and the flag word that tells rank r they are there
+                        "push_dst": [mk([p + 4 * (par * slots + rank * n_al) for p in ptrs]) for par in (0, 1)],
+                        "push_flags": [mk([p + 4 * (2 * slots + fl * par + rank * nb) for p in ptrs]) for par in (0, 1)],
+                        # what the EMA kernel reads: my LOCAL slots (one per rank) and my local flag array
+                        "recv": [mk([ptrs[rank] + 4 * (par * slots + r * n_al) for r in range(world)]) for par in (0, 1)],
+                        "flags": [ptrs[rank] + 4 * (2 * slots + fl * par) for par in (0, 1)],
+                        "err": [buf[2 * slots + fl * par + 1024: 2 * slots + fl * par + 1026].view(torch.int32) for par in (0, 1)]}
             except Exception as exc:  # no peer access / unsupported build: keep the NCCL path
                 peer = None
                 self._peer_error = repr(exc)
@@ -221,6 +229,23 @@ class Quantize(nn.Module):
             peer = None
         ws["peer"] = peer
         return peer
+
+    def _check_peer_timeout(self, peer):
+        """The EMA kernel gives up after 2 s without a peer's statistics and records (step, rank) in its flag array; read
+        the word back every 64 steps without a sync (pinned copy + event) and fail loudly."""
+        pend = peer.get("err_pending")
+        if pend is not None and pend[0].query():
+            peer["err_pending"] = None
+            if int(pend[1][0]) != 0:
+                raise RuntimeError(f"Quantize: rank {int(pend[1][1])} did not publish its codebook statistics for step "
+                                   f"{int(pend[1][0])} within 2 s (fused peer-memory exchange); the replicas are out of sync")
+        if pend is None and peer["step"] - peer["checked"] >= 64 and not torch.cuda.is_current_stream_capturing():
+            peer["checked"] = peer["step"]
+            host = peer.setdefault("err_host", torch.zeros(2, dtype=torch.int32).pin_memory())
+            host.copy_(peer["err"][peer["parity"]], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            peer["err_pending"] = (ev, host)
 
     # ------------------------------------------------------------------ filter precision policy
     # The plain-bf16 tensor-core filter needs 1/3 of the MMAs of the split-bf16 one but certifies fewer rows when
@@ -300,12 +325,13 @@ class Quantize(nn.Module):
         diff = torch.empty((), dtype=torch.float32, device=dev)
         stats = ws["stats"] if self.training else None
         world = dist_fn.get_world_size() if self.training else 1
+        peer = None
         if world > 1:
             peer = self._peer_workspace(ws, dev)
-            if peer is not None:              # this step's statistics go straight into peer-mapped memory
+            if peer is not None:              # this step's statistics go straight into every rank's receive slot
+                self._check_peer_timeout(peer)
                 peer["step"] += 1
                 peer["parity"] = peer["step"] & 1
-                stats = peer["stats"][peer["parity"]]
         x_run, q_run, lay_run, x_dense = x, quantize, lay, None
         strided = n > 0 and (col != 1 or (n > 1 and row != self.dim))
         if strided and self.engine != "simt":
@@ -327,31 +353,33 @@ class Quantize(nn.Module):
         fused_ema = self.training and world == 1
         # the codebook image is re-derived from `embed` on every call: external writes to the buffer
         # (load_state_dict, .data.copy_, DDP buffer broadcast) can never leave it stale
-        _native.check(lib.vqb200_quantize_step(
-            x_run.data_ptr(), n, self.dim, self.n_embed, rpi, img, row, col, self.embed.data_ptr(),
-            self.cluster_size.data_ptr(), self.embed_avg.data_ptr(), image.data_ptr(),
-            q_run.data_ptr() if q_run is not None else None, ind.data_ptr(), diff.data_ptr(),
-            stats.data_ptr() if stats is not None else None, ws["scratch"].data_ptr(),
-            x_dense.data_ptr() if x_dense is not None else None, eng, 1 if fused_ema else 0, float(self.decay), float(1 - self.decay), float(self.eps), stream),
-            "vqb200_quantize_step")                                                           # vqvae.py:43-73
+        if peer is not None:                  # forward + statistics pushed to every rank (vqvae.py:43-56,58-59,72-73)
+            par = peer["parity"]
+            _native.check(lib.vqb200_quantize_step_peers(
+                x_run.data_ptr(), n, self.dim, self.n_embed, rpi, img, row, col, self.embed.data_ptr(),
+                self.cluster_size.data_ptr(), self.embed_avg.data_ptr(), image.data_ptr(),
+                q_run.data_ptr() if q_run is not None else None, ind.data_ptr(), diff.data_ptr(), ws["scratch"].data_ptr(),
+                x_dense.data_ptr() if x_dense is not None else None, eng, float(self.decay), float(1 - self.decay), float(self.eps),
+                peer["push_dst"][par], peer["push_flags"][par], peer["recv"][par], peer["flags"][par], peer["rank"],
+                peer["world"], peer["step"], stream), "vqb200_quantize_step_peers")
+        else:
+            _native.check(lib.vqb200_quantize_step(
+                x_run.data_ptr(), n, self.dim, self.n_embed, rpi, img, row, col, self.embed.data_ptr(),
+                self.cluster_size.data_ptr(), self.embed_avg.data_ptr(), image.data_ptr(),
+                q_run.data_ptr() if q_run is not None else None, ind.data_ptr(), diff.data_ptr(),
+                stats.data_ptr() if stats is not None else None, ws["scratch"].data_ptr(),
+                x_dense.data_ptr() if x_dense is not None else None, eng, 1 if fused_ema else 0, float(self.decay), float(1 - self.decay), float(self.eps), stream),
+                "vqb200_quantize_step")                                                       # vqvae.py:43-73
         if q_run is not quantize:             # dense result -> the input's strides
             _native.check(lib.vqb200_repack_rows(q_run.data_ptr(), quantize.data_ptr(), lay[0], self.dim, lay[1], lay[2],
                                                  lay[3], lay[4], 0, stream), "vqb200_repack_rows")
         self._note_flagged(ws, n, eng, dev)
-        if self.training and not fused_ema:
-            peer = ws.get("peer")
-            if peer is not None:              # all-reduce fused into the EMA kernel over peer memory (vqvae.py:58-70)
-                _native.check(lib.vqb200_ema_update_p2p(
-                    peer["stats_ptrs"][peer["parity"]], peer["flag_ptrs"][peer["parity"]], peer["rank"], peer["world"],
-                    peer["step"], self.cluster_size.data_ptr(), self.embed_avg.data_ptr(), self.embed.data_ptr(),
-                    self.dim, self.n_embed, float(self.decay), float(1 - self.decay), float(self.eps), None, stream),
-                    "vqb200_ema_update_p2p")
-            else:
-                dist_fn.all_reduce(stats[: self.n_embed * (self.dim + 1)])  # vqvae.py:58-59 (one packed call)
-                _native.check(lib.vqb200_ema_update(
-                    stats.data_ptr(), self.cluster_size.data_ptr(), self.embed_avg.data_ptr(),
-                    self.embed.data_ptr(), self.dim, self.n_embed, float(self.decay), float(1 - self.decay),
-                    float(self.eps), None, stream), "vqb200_ema_update")                      # vqvae.py:61-70
+        if self.training and not fused_ema and peer is None:      # multi-rank without peer memory: one packed NCCL all-reduce
+            dist_fn.all_reduce(stats[: self.n_embed * (self.dim + 1)])  # vqvae.py:58-59 (one packed call)
+            _native.check(lib.vqb200_ema_update(
+                stats.data_ptr(), self.cluster_size.data_ptr(), self.embed_avg.data_ptr(),
+                self.embed.data_ptr(), self.dim, self.n_embed, float(self.decay), float(1 - self.decay),
+                float(self.eps), None, stream), "vqb200_ema_update")                          # vqvae.py:61-70
         return quantize, diff, ind, image, lay
 
     def forward(self, input):
