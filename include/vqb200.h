@@ -111,21 +111,22 @@ int vqb200_ema_update_p2p(const void* const* h_stats_ptrs, void* const* h_flag_p
                           uint32_t step, float* d_cluster_size, float* d_embed_avg, float* d_embed,
                           int32_t dim, int32_t n_embed, float decay, float one_minus_decay, float eps,
                           void* d_codebook, void* stream);
-/* Multi-rank training forward in ONE call, PUSH form of the exchange that replaces dist_fn.all_reduce (vqvae.py:58-59 ->
- * distributed/distributed.py:64-72), dim 64 / n_embed 256 or 512: forward as vqb200_quantize_step, then ONE kernel folds the
- * per-CTA statistics tables, stores this rank's packed statistics [K*64 sums | K counts] into h_push_dst[r] = rank r's
- * receive slot for THIS rank (peer-mapped pointers; r == rank: the local slot) block by block, publishes `step` to
- * h_push_flags[r][block] (system-scope release), waits on the LOCAL flag array d_flags [world][K/4] (+ 2 time-out words at
- * word 1024) for every block of every rank, sums the LOCAL receive slots h_recv[0..world) in rank order (bit-identical
- * replicas) and applies vqvae.py:61-70.  No NCCL call, no remote load.  Slots and flags are double-buffered by the caller
- * on the parity of `step` (1, 2, ...).  A peer that does not publish within 2 s: d_flags[1024] = step, [1025] = rank.      */
+/* Multi-rank training forward in ONE call, with the exchange that replaces dist_fn.all_reduce (vqvae.py:58-59 ->
+ * distributed/distributed.py:64-72) fused into the EMA kernel over peer memory; dim 64 / n_embed 256 or 512.  Forward as
+ * vqb200_quantize_step, then ONE kernel folds the per-CTA statistics tables, stores every word of this rank's packed
+ * statistics [K*64 sums | K counts] as an 8-byte {value, step} pair into h_push_dst[r] = rank r's receive slot for THIS rank
+ * (peer-mapped pointers, 8-byte aligned, (K*65) pairs; r == rank: the local slot), polls the words it needs in its LOCAL
+ * receive slots h_recv[0..world) until their tag equals `step` (flag-in-data: no fence, no flag array, no NCCL call, no
+ * remote load), adds them in rank order (bit-identical replicas) and applies vqvae.py:61-70.  Slots are double-buffered by
+ * the caller on the parity of `step` (1, 2, ...).  A word that does not arrive within 2 s: d_err[0] = step, d_err[1] = rank
+ * (d_err: 16 words of local device memory, zero-initialised).                                                            */
 int vqb200_quantize_step_peers(const float* d_x, int64_t n_rows, int32_t dim, int32_t n_embed, int64_t rows_per_image,
                                int64_t image_stride, int64_t row_stride, int64_t col_stride, float* d_embed,
                                float* d_cluster_size, float* d_embed_avg, void* d_codebook, float* d_quantize,
                                int64_t* d_embed_ind, float* d_diff, void* d_scratch, float* d_x_dense, int32_t engine,
                                float decay, float one_minus_decay, float eps, void* const* h_push_dst,
-                               void* const* h_push_flags, const void* const* h_recv, void* d_flags, int32_t rank,
-                               int32_t world, uint32_t step, void* stream);
+                               const void* const* h_recv, void* d_err, int32_t rank, int32_t world, uint32_t step,
+                               void* stream);
 
 /* The module's whole forward in one call (fewer host round trips per step):
  *   vqb200_codebook_prepare(d_embed) + vqb200_quantize_forward(...) and, when `ema` != 0 and d_stats != NULL,
@@ -197,6 +198,11 @@ int vqb200_debug_tc_profile(const float* d_x, int64_t n_rows, int32_t dim, int32
 int vqb200_debug_tc_kernel(const float* d_x, int64_t n_rows, int32_t dim, int32_t n_embed, const void* d_codebook,
                            float* d_quantize, int64_t* d_embed_ind, void* d_scratch, int32_t engine, void* stream);
 int vqb200_tc_profile_slots(void);
+/* Flag ping-pong between two GPUs over peer-mapped memory (tools/p2p_latency.py): `iters` round trips of a system-scope
+ * release store to d_peer_flag and an acquire spin on d_my_flag; *d_ns = elapsed globaltimer nanoseconds.  Both sides must
+ * be running at the same time on DIFFERENT GPUs (never two ranks on one GPU).                                              */
+int vqb200_debug_pingpong(void* d_my_flag, void* d_peer_flag, int32_t iters, int32_t initiator, int32_t with_fence,
+                          uint64_t* d_ns, void* stream);
 /* 1 when vqb200_quantize_forward would take the tcgen05 engine for this shape / layout / pointer alignment */
 int vqb200_tc_supported(const float* d_x, int64_t n_rows, int32_t dim, int32_t n_embed,
                         int64_t rows_per_image, int64_t image_stride, int64_t row_stride, int64_t col_stride);

@@ -70,20 +70,19 @@ def test_p2p_ema_rejects_bad_arguments():
 @pytest.mark.parametrize("K", [512, 256])
 def test_step_peers_with_world_1_equals_single_rank_step(K):
     """What the module runs at world > 1 (vqb200_quantize_step_peers: forward, then ONE kernel that folds the statistics
-    tables, pushes them to every rank's receive slot, publishes per-block flags, waits on the local flags and applies the EMA
-    to the rank-ordered sum of the local slots) driven with world = 1 against the single-rank step on the same inputs:
-    identical indices / outputs, EMA buffers equal to the statistics' summation-order noise, flags carry the step, the
-    time-out words stay clear, and the pushed slot holds the statistics (counts sum to the rows)."""
+    tables, stores them as {value, step} pairs into every rank's receive slot, polls its local slots and applies the EMA to
+    the rank-ordered sum) driven with world = 1 against the single-rank step on the same inputs: identical indices /
+    outputs, EMA buffers equal up to the statistics' summation-order noise, every word of the slot tagged with the step,
+    the time-out words clear, and the slot holding the statistics (counts sum to the rows)."""
     lib = _native.load()
     D = 64
     torch.manual_seed(1)
     a = vq.Quantize(D, K).to(DEV).train()
     b = vq.Quantize(D, K).to(DEV).train()
     b.load_state_dict(a.state_dict())
-    n = lib.vqb200_stats_bytes(D, K) // 4
+    n = K * (D + 1)
     n_al = (n + 63) // 64 * 64
-    fl = 8 * 128 + 64
-    buf = torch.zeros(2 * n_al + 2 * fl, device=DEV)             # [slot parity 0 | slot parity 1 | flags 0 | flags 1]
+    buf = torch.zeros(2 * 2 * n_al + 2 * 64, device=DEV)         # [slot parity 0 | slot parity 1 | err 0 | err 1], 8-byte pairs
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     from vq_vae_2_pytorch_b200 import row_layout
     for step in range(1, 6):
@@ -92,24 +91,25 @@ def test_step_peers_with_world_1_equals_single_rank_step(K):
         qa, da, ia = a(x)                                        # single-rank step (fold fused into the EMA kernel as well)
         nr, rpi, img, row, col = row_layout(x)
         par = step & 1
-        slot = buf[par * n_al: par * n_al + n]
-        flags = buf[2 * n_al + fl * par: 2 * n_al + fl * (par + 1)]
+        slot = buf[par * 2 * n_al: par * 2 * n_al + 2 * n]
+        err = buf[4 * n_al + 64 * par: 4 * n_al + 64 * par + 64]
         ws = b._workspace(x.device, nr)
         quant = torch.empty_strided(x.shape, x.stride(), device=DEV)
         ind = torch.empty(x.shape[:-1], dtype=torch.int64, device=DEV); diff = torch.empty((), device=DEV)
-        dst = (C.c_void_p * 1)(slot.data_ptr()); pfl = (C.c_void_p * 1)(flags.data_ptr()); recv = (C.c_void_p * 1)(slot.data_ptr())
+        dst = (C.c_void_p * 1)(slot.data_ptr()); recv = (C.c_void_p * 1)(slot.data_ptr())
         _native.check(lib.vqb200_quantize_step_peers(x.data_ptr(), nr, D, K, rpi, img, row, col, b.embed.data_ptr(),
                                                      b.cluster_size.data_ptr(), b.embed_avg.data_ptr(), ws["image"].data_ptr(),
                                                      quant.data_ptr(), ind.data_ptr(), diff.data_ptr(), ws["scratch"].data_ptr(), None, 0,
-                                                     0.99, float(1 - 0.99), 1e-5, dst, pfl, recv, flags.data_ptr(), 0, 1, step, st), "step_peers")
+                                                     0.99, float(1 - 0.99), 1e-5, dst, recv, err.data_ptr(), 0, 1, step, st), "step_peers")
         torch.cuda.synchronize()
         assert torch.equal(ind, ia) and torch.equal(quant, qa) and abs(float(diff) - float(da)) <= 1e-6 * abs(float(da))
-        nb = K // 4
-        assert bool((flags[:nb].view(torch.int32) == step).all())          # one flag per block of the fold + EMA kernel
-        assert int(flags[1024:1025].view(torch.int32)) == 0               # no time-out recorded
-        assert abs(float(slot[K * D: K * D + K].sum()) - nr) < 0.5       # the pushed counts
-        assert torch.allclose(slot[: K * D].view(K, D).sum(0), x.reshape(-1, D).sum(0), rtol=1e-4, atol=1e-2)
-        assert torch.equal(a.cluster_size, b.cluster_size)               # integer counts: exact
+        pairs = slot.view(n, 2)
+        assert bool((pairs[:, 1].view(torch.int32) == step).all())          # every word carries the step tag
+        assert int(err[:1].view(torch.int32)) == 0                          # no time-out recorded
+        vals = pairs[:, 0]
+        assert abs(float(vals[K * D: K * D + K].sum()) - nr) < 0.5          # the pushed counts
+        assert torch.allclose(vals[: K * D].view(K, D).sum(0), x.reshape(-1, D).sum(0), rtol=1e-4, atol=1e-2)
+        assert torch.equal(a.cluster_size, b.cluster_size)                  # integer counts: exact
         scale = a.embed_avg.abs().amax(0, keepdim=True).clamp_min(1e-30)
         assert float(((a.embed_avg - b.embed_avg).abs() / scale).max()) <= 2e-6
         b.load_state_dict(a.state_dict())

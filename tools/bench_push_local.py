@@ -49,19 +49,20 @@ def split(i, step):
                                         D, K, 0.99, float(1 - 0.99), 1e-5, None, st), "ema")
 
 
-fl = 8 * 128 + 64
-pbuf = torch.zeros(2 * n_al + 2 * fl, device=dev)
+nw = K * (D + 1)
+nw_al = (nw + 63) // 64 * 64
+pbuf = torch.zeros(2 * 2 * nw_al + 2 * 64, device=dev)
 
 
 def peers_w1(i, step):
     par = step & 1
-    slot = pbuf.data_ptr() + 4 * par * n_al
-    flags = pbuf.data_ptr() + 4 * (2 * n_al + fl * par)
-    dst = (C.c_void_p * 1)(slot); pf = (C.c_void_p * 1)(flags); rc = (C.c_void_p * 1)(slot)
+    slot = pbuf.data_ptr() + 4 * par * 2 * nw_al
+    err = pbuf.data_ptr() + 4 * (4 * nw_al + 64 * par)
+    dst = (C.c_void_p * 1)(slot); rc = (C.c_void_p * 1)(slot)
     _native.check(lib.vqb200_quantize_step_peers(xs[i % 3].data_ptr(), N, D, K, N, 0, D, 1, q.embed.data_ptr(), q.cluster_size.data_ptr(),
                                                  q.embed_avg.data_ptr(), ws["image"].data_ptr(), quant.data_ptr(), ind.data_ptr(),
                                                  diff.data_ptr(), ws["scratch"].data_ptr(), None, eng, 0.99, float(1 - 0.99), 1e-5,
-                                                 dst, pf, rc, C.c_void_p(flags), 0, 1, step, st), "peers")
+                                                 dst, rc, C.c_void_p(err), 0, 1, step, st), "peers")
 
 
 step_no = 0

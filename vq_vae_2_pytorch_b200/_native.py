@@ -35,7 +35,7 @@ SIGNATURES = {
                                        _i32, _i32, _f32, _f32, _f32, _p]),
     "vqb200_ema_update_p2p": (C.c_int, [_p, _p, _i32, _i32, C.c_uint32, _p, _p, _p, _i32, _i32, _f32, _f32, _f32, _p, _p]),
     "vqb200_quantize_step_peers": (C.c_int, [_p, _i64, _i32, _i32, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i32,
-                                             _f32, _f32, _f32, _p, _p, _p, _p, _i32, _i32, C.c_uint32, _p]),
+                                             _f32, _f32, _f32, _p, _p, _p, _i32, _i32, C.c_uint32, _p]),
     "vqb200_repack_rows": (C.c_int, [_p, _p, _i64, _i32, _i64, _i64, _i64, _i64, _i32, _p]),
     "vqb200_embed_code": (C.c_int, [_p, _i64, _p, _i32, _i32, _p, _p, _p]),
     "vqb200_pack_indices": (C.c_int, [_p, _i64, _i32, _i32, _p, _p, _p]),
@@ -46,6 +46,7 @@ SIGNATURES = {
     "vqb200_tc_supported": (C.c_int, [_p, _i64, _i32, _i32, _i64, _i64, _i64, _i64]),
     "vqb200_debug_tc_profile": (C.c_int, [_p, _i64, _i32, _i32, _p, _p, _p, _p, _p, _i32, _p]),
     "vqb200_tc_profile_slots": (C.c_int, []),
+    "vqb200_debug_pingpong": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p]),
     "vqb200_debug_tc_kernel": (C.c_int, [_p, _i64, _i32, _i32, _p, _p, _p, _p, _i32, _p]),
     "vqb200_host_ctx_create": (C.c_int, [_i64, _i32, _i32, C.POINTER(_p)]),
     "vqb200_host_ctx_destroy": (None, [_p]),

@@ -280,33 +280,97 @@ k_fixup(const float* __restrict__ x, RowLayout L, int D, int K, const float* __r
     }
 }
 
+
+// diagnostics: flag ping-pong between two GPUs over peer-mapped memory (tools/p2p_latency.py).  The initiator stores i to the
+// peer's flag and waits for the echo in its own; the responder echoes.  *ns_out = globaltimer nanoseconds for `iters` round trips.
+__global__ void k_pingpong(unsigned int* my_flag, unsigned int* peer_flag, int iters, int initiator, int with_fence,
+                           unsigned long long* ns_out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (int i = 1; i <= iters; ++i) {
+        if (initiator) {
+            if (with_fence) __threadfence_system();
+            st_release_sys(peer_flag, (unsigned int)i);
+            while ((int)(ld_acquire_sys(my_flag) - (unsigned int)i) < 0) {}
+        } else {
+            while ((int)(ld_acquire_sys(my_flag) - (unsigned int)i) < 0) {}
+            if (with_fence) __threadfence_system();
+            st_release_sys(peer_flag, (unsigned int)i);
+        }
+    }
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    *ns_out = t1 - t0;
+}
+
 }  // namespace vqb200
 
 namespace vqb200 {
 
 // ------------------------------------------------------------------------------------------------
-// Fold + [exchange] + EMA in ONE launch (vqvae.py:55-70): replaces k_stats_fold / k_stats_fold_push + k_ema64.
+// Fold + [exchange] + EMA in ONE launch (vqvae.py:55-70): replaces k_stats_fold + [all-reduce] + k_ema64.
 // grid = K / 4 blocks of 1024 threads; block b owns codes 4b .. 4b+3.
 //   fold      the block sums ITS 256 statistics elements over the per-CTA tables of the statistics kernel (4 thread groups,
-//             each over every 4th table, combined in a fixed order -> deterministic); the rows-per-code counts come from the
-//             integer atomics of the statistics kernel (ForwardScratch::code_counts), so nothing else has to be folded;
-//   exchange  (P2P) PUSH form: the block stores its 256 sums + 4 counts into slot `rank` of EVERY rank's receive buffer
-//             (posted NVLink stores), one system-scope fence, then a flag per (rank, block) on every peer; it then waits on
-//             its LOCAL flags for all blocks of all ranks (every block needs all K counts for n = sum cluster_size) and
-//             sums the local slots in RANK ORDER -> identical bits on every rank, no remote load, no NCCL call;
+//             each over every 4th table with all its loads in flight, combined in a fixed order -> deterministic); the
+//             rows-per-code counts come from the integer atomics of the statistics kernel (ForwardScratch::code_counts);
+//   exchange  (P2P) flag-in-data protocol over peer memory (what NCCL calls LL): every statistics word travels as ONE 8-byte
+//             store {value, step} into slot `rank` of every rank's receive buffer -- 8-byte stores are single transactions,
+//             so a word whose tag equals `step` is valid and NO fence, flag array or acknowledgement round trip is needed
+//             (a release flag behind the data cost a full NVLink round trip, 4.9 us measured, before the 2.5 us one-way
+//             trip of the flag itself).  Every thread then polls exactly the words it needs in its LOCAL slots (its element
+//             of every rank; every block needs all K counts for n = sum cluster_size) and adds them in RANK ORDER ->
+//             identical bits on every rank, no remote load, no NCCL call;
 //   EMA       as k_ema64: decay, Laplace-smoothed renormalisation, embed / embed_avg in place, next codebook image,
-//             cluster_size stored by the last block (every block derives n from the OLD values).
-// A peer that does not publish within P2P_TIMEOUT_NS: (step, rank) recorded behind the flags, host raises.
+//             cluster_size stored by the last block (every block derives n from the OLD values).  The old embed_avg /
+//             cluster_size values are loaded BEFORE the fold so that their latency hides behind it.
+// A word that does not arrive within P2P_TIMEOUT_NS: (step, rank) recorded in peers.err, the host raises.
 // ------------------------------------------------------------------------------------------------
 constexpr int EF_CODES = 4, EF_THREADS = 1024;
 struct PeerFold {
-    float* push_dst[P2P_MAX_RANKS];            // rank r's receive slot for MY statistics ([K*64 sums | K counts])
-    unsigned int* push_flag[P2P_MAX_RANKS];    // rank r's flag row for me: one word per EMA block
-    const float* recv[P2P_MAX_RANKS];          // my local receive slots, one per rank
-    unsigned int* flags;                       // my local flags [world][gridDim.x], then 2 time-out words
+    uint2* push_dst[P2P_MAX_RANKS];            // rank r's receive slot for MY statistics: [K*64 sums | K counts] x {value, step}
+    const uint2* recv[P2P_MAX_RANKS];          // my local receive slots, one per rank
+    unsigned int* err;                         // 2 words: (step, rank) of a time-out
     int rank, world;
     unsigned int step;
 };
+
+__device__ __forceinline__ void st_ll(uint2* p, float v, unsigned int tag) {
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag) : "memory");
+}
+__device__ __forceinline__ uint2 ld_ll(const uint2* p) {
+    uint2 v;
+    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+    return v;
+}
+// rank-ordered sum of word i of every rank's local slot, each word polled until its tag is `step`
+__device__ __forceinline__ float ll_gather(const PeerFold& peers, size_t i) {
+    uint2 v[P2P_MAX_RANKS];
+    unsigned int pending = 0;
+#pragma unroll
+    for (int r = 0; r < P2P_MAX_RANKS; ++r)
+        if (r < peers.world) { v[r] = ld_ll(peers.recv[r] + i); pending |= (v[r].y != peers.step) ? (1u << r) : 0u; }
+    unsigned long long t0 = 0;
+    unsigned int spins = 0;
+    while (pending) {
+#pragma unroll
+        for (int r = 0; r < P2P_MAX_RANKS; ++r)
+            if (pending & (1u << r)) { v[r] = ld_ll(peers.recv[r] + i); if (v[r].y == peers.step) pending &= ~(1u << r); }
+        if (pending && (++spins & 255u) == 0) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > P2P_TIMEOUT_NS) {
+                peers.err[1] = (unsigned int)(__ffs(pending) - 1);
+                atomicExch(peers.err, peers.step);
+                break;
+            }
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < P2P_MAX_RANKS; ++r) s += (r < peers.world) ? __uint_as_float(v[r].x) : 0.f;      // + 0.f for absent ranks: exact
+    return s;
+}
 
 template <bool P2P>
 __global__ void __launch_bounds__(EF_THREADS) k_ema64f(const float* __restrict__ partials, const unsigned int* __restrict__ n_parts_ptr,
@@ -319,6 +383,7 @@ __global__ void __launch_bounds__(EF_THREADS) k_ema64f(const float* __restrict__
     __shared__ float es[EF_CODES][65];
     __shared__ float ssum[EF_CODES][65];
     __shared__ float cnt_s[512];                                // K <= 512 (tc_shape_ok)
+    __shared__ float csn_s[512];                                // new cluster sizes
     __shared__ float e2s[EF_CODES];
     __shared__ float part[32];
     __shared__ float n_s;
@@ -327,77 +392,68 @@ __global__ void __launch_bounds__(EF_THREADS) k_ema64f(const float* __restrict__
     pdl_trigger();
     const int k0 = blockIdx.x * EF_CODES, tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
     const int n_parts = (int)*n_parts_ptr, nstat = K * 65;
-    // ---- fold: element e of my 256 (code e / 64, dim e % 64), thread group g over the tables g, g + 4, ...
+#ifdef VQB200_P2P_TRACE
+    unsigned long long tr[5] = {0, 0, 0, 0, 0};
+    auto stamp = [&](int i) { if (P2P && tid == 0 && blockIdx.x == gridDim.x - 1) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr[i])); };
+    stamp(0);
+#endif
+    // ---- old values first: nothing below depends on them until the EMA, so their latency hides behind the fold / exchange
+    float old_avg = 0.f, old_cs = 0.f;
+    if (tid < 64 * EF_CODES) old_avg = embed_avg[(size_t)(tid >> 2) * K + k0 + (tid & 3)];     // 16-byte segments of 4 consecutive codes per dim
+    if (tid < K) old_cs = cluster_size[tid];
+    // ---- fold: element e of my 256 (code e / 64, dim e % 64), thread group g over the tables g, g + 4, ... (<= 40 each)
     {
         const int e = tid & 255, g = tid >> 8;
-        const float* src = partials + (size_t)k0 * 64 + e;
+        const float* src = partials + (size_t)k0 * 64 + e + (size_t)g * nstat;
         float s = 0.f;
-#pragma unroll 8
-        for (int c = g; c < n_parts; c += 4) s += __ldcs(src + (size_t)c * nstat);
+        for (int c0 = 0; c0 < n_parts; c0 += 80) {                // rounds of 20 tables per group, all 20 loads in flight
+            float v[20];
+#pragma unroll
+            for (int u = 0; u < 20; ++u) {
+                const int c = c0 + g + 4 * u;
+                v[u] = c < n_parts ? __ldcs(src + (size_t)(c0 + 4 * u) * nstat) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 20; ++u) s += v[u];
+        }
         red[g][e] = s;
     }
     __syncthreads();
     float tot = 0.f;
     if (tid < 256) tot = ((red[0][tid] + red[1][tid]) + red[2][tid]) + red[3][tid];
+#ifdef VQB200_P2P_TRACE
+    stamp(1);
+#endif
     if constexpr (P2P) {
-        // ---- push my block of statistics to every rank (mine included), then one flag per rank
+        // ---- every word to every rank (mine included) as {value, step}; then poll the words this thread needs
         if (tid < 256) {
 #pragma unroll
             for (int r = 0; r < P2P_MAX_RANKS; ++r)
-                if (r < peers.world) peers.push_dst[r][(size_t)k0 * 64 + tid] = tot;
+                if (r < peers.world) st_ll(peers.push_dst[r] + (size_t)k0 * 64 + tid, tot, peers.step);
         } else if (tid < 256 + EF_CODES) {
             const float c = (float)code_counts[k0 + tid - 256];
 #pragma unroll
             for (int r = 0; r < P2P_MAX_RANKS; ++r)
-                if (r < peers.world) peers.push_dst[r][(size_t)K * 64 + k0 + tid - 256] = c;
+                if (r < peers.world) st_ll(peers.push_dst[r] + (size_t)K * 64 + k0 + tid - 256, c, peers.step);
         }
-        __syncthreads();                          // the block's stores happen-before the flag stores below (cumulative release)
-        if (tid < peers.world) st_release_sys(peers.push_flag[tid] + blockIdx.x, peers.step);
-        // ---- wait for every block of every rank (bounded), on local memory
-        const int n_flags = peers.world * (int)gridDim.x;
-        if (tid < n_flags) {
-            const unsigned int* f = peers.flags + tid;
-            unsigned long long t0 = 0;
-            unsigned int spins = 0;
-            while ((int)(ld_acquire_sys(f) - peers.step) < 0) {
-                __nanosleep(32);
-                if ((++spins & 1023u) == 0) {
-                    unsigned long long now;
-                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-                    if (t0 == 0) t0 = now;
-                    else if (now - t0 > P2P_TIMEOUT_NS) {
-                        unsigned int* err = peers.flags + P2P_MAX_RANKS * 128;
-                        err[1] = (unsigned int)(tid / (int)gridDim.x);
-                        atomicExch(err, peers.step);
-                        break;
-                    }
-                }
-            }
-        }
+#ifdef VQB200_P2P_TRACE
+        stamp(2);
+#endif
+        if (tid < 256) tot = ll_gather(peers, (size_t)k0 * 64 + tid);
+        if (tid >= 512 && tid - 512 < K) cnt_s[tid - 512] = ll_gather(peers, (size_t)K * 64 + tid - 512);
+#ifdef VQB200_P2P_TRACE
         __syncthreads();
-        // ---- rank-ordered sums of the local slots
-        if (tid < 256) {
-            float v[P2P_MAX_RANKS];
-#pragma unroll
-            for (int r = 0; r < P2P_MAX_RANKS; ++r) v[r] = r < peers.world ? __ldcg(peers.recv[r] + (size_t)k0 * 64 + tid) : 0.f;
-            tot = rank_ordered_sum(v);
-        }
-        if (tid >= 512 && tid - 512 < K) {
-            const int k = tid - 512;
-            float v[P2P_MAX_RANKS];
-#pragma unroll
-            for (int r = 0; r < P2P_MAX_RANKS; ++r) v[r] = r < peers.world ? __ldcg(peers.recv[r] + (size_t)K * 64 + k) : 0.f;
-            cnt_s[k] = rank_ordered_sum(v);
-        }
+        stamp(3);
+#endif
     } else {
         if (tid >= 512 && tid - 512 < K) cnt_s[tid - 512] = (float)code_counts[tid - 512];
     }
     if (tid < 256) ssum[tid >> 6][tid & 63] = tot;
     __syncthreads();
     // ---- n = sum_k cluster_size_new[k] from the OLD cluster sizes (vqvae.py:61-65)
-    float s = 0.f;
-    if (tid < K) s = __fmaf_rn(cnt_s[tid], one_minus_decay, __fmul_rn(cluster_size[tid], decay));
-    s = warp_sum(s);
+    float cs_new = 0.f;
+    if (tid < K) { cs_new = __fmaf_rn(cnt_s[tid], one_minus_decay, __fmul_rn(old_cs, decay)); csn_s[tid] = cs_new; }
+    float s = warp_sum(cs_new);
     if (lane == 0) part[w] = s;
     __syncthreads();
     if (tid == 0) {
@@ -410,10 +466,9 @@ __global__ void __launch_bounds__(EF_THREADS) k_ema64f(const float* __restrict__
     const float denom = n + (float)((double)K * (double)eps);
     if (tid < 64 * EF_CODES) {                                   // 16-byte segments of 4 consecutive codes per dim
         const int d = tid >> 2, j = tid & 3, k = k0 + j;
-        const float c = __fmaf_rn(cnt_s[k], one_minus_decay, __fmul_rn(cluster_size[k], decay));
-        const float cs = (c + eps) / denom * n;                 // vqvae.py:66-68
+        const float cs = (csn_s[k] + eps) / denom * n;          // vqvae.py:66-68
         const size_t o = (size_t)d * K + k;
-        const float a = __fmaf_rn(ssum[j][d], one_minus_decay, __fmul_rn(embed_avg[o], decay));       // vqvae.py:64
+        const float a = __fmaf_rn(ssum[j][d], one_minus_decay, __fmul_rn(old_avg, decay));       // vqvae.py:64
         embed_avg[o] = a;
         const float e = a / cs;                                 // vqvae.py:69-70
         embed[o] = e;
@@ -439,9 +494,19 @@ __global__ void __launch_bounds__(EF_THREADS) k_ema64f(const float* __restrict__
     if (tid == 0) last_s = (atomicAdd(ticket, 1u) == gridDim.x - 1u) ? 1u : 0u;
     __syncthreads();
     if (last_s) {
-        if (tid < K) cluster_size[tid] = __fmaf_rn(cnt_s[tid], one_minus_decay, __fmul_rn(cluster_size[tid], decay));
+        if (tid < K) cluster_size[tid] = cs_new;
         if (tid == 0) *ticket = 0u;                             // clean for the next launch
     }
+#ifdef VQB200_P2P_TRACE
+    if constexpr (P2P) {
+        stamp(4);
+        if (tid == 0 && blockIdx.x == gridDim.x - 1) {          // (kernel start, fold, push, wait, rest) of the last block, ns
+            unsigned int* t = peers.err + 4;
+            t[0] = (unsigned int)(tr[0] & 0xffffffffu); t[1] = (unsigned int)(tr[1] - tr[0]); t[2] = (unsigned int)(tr[2] - tr[1]);
+            t[3] = (unsigned int)(tr[3] - tr[2]); t[4] = (unsigned int)(tr[4] - tr[3]); t[5] = peers.step;
+        }
+    }
+#endif
 }
 
 }  // namespace vqb200

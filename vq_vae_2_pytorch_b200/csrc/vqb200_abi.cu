@@ -364,11 +364,11 @@ int vqb200_quantize_step_peers(const float* d_x, int64_t n_rows, int32_t dim, in
                                int64_t image_stride, int64_t row_stride, int64_t col_stride, float* d_embed,
                                float* d_cluster_size, float* d_embed_avg, void* d_codebook, float* d_quantize,
                                int64_t* d_embed_ind, float* d_diff, void* d_scratch, float* d_x_dense, int32_t engine,
-                               float decay, float one_minus_decay, float eps, void* const* h_push_dst, void* const* h_push_flags,
-                               const void* const* h_recv, void* d_flags, int32_t rank, int32_t world, uint32_t step, void* stream) {
+                               float decay, float one_minus_decay, float eps, void* const* h_push_dst,
+                               const void* const* h_recv, void* d_err, int32_t rank, int32_t world, uint32_t step, void* stream) {
     if (!d_embed || !d_cluster_size || !d_embed_avg || !d_codebook || !d_scratch || dim <= 0 || n_embed <= 0) return VQB200_EINVAL;
     if (n_rows < 0 || (n_rows > 0 && (!d_x || !d_embed_ind))) return VQB200_EINVAL;
-    if (!h_push_dst || !h_push_flags || !h_recv || !d_flags) return VQB200_EINVAL;
+    if (!h_push_dst || !h_recv || !d_err) return VQB200_EINVAL;
     if (world < 1 || world > P2P_MAX_RANKS || rank < 0 || rank >= world || step == 0) return VQB200_EINVAL;
     if (n_rows > (int64_t)INT32_MAX) return VQB200_EUNSUPPORTED;
     if (engine < VQB200_ENGINE_AUTO || engine > VQB200_ENGINE_TCGEN05_TF32) return VQB200_EINVAL;
@@ -376,12 +376,12 @@ int vqb200_quantize_step_peers(const float* d_x, int64_t n_rows, int32_t dim, in
     if (!tc_shape_ok(dim, n_embed)) return VQB200_EUNSUPPORTED;      // the fold + EMA kernel: dim 64, n_embed 256 / 512
     PeerFold pf{};
     for (int r = 0; r < world; ++r) {
-        if (!h_push_dst[r] || !h_push_flags[r] || !h_recv[r]) return VQB200_EINVAL;
-        pf.push_dst[r] = static_cast<float*>(h_push_dst[r]);
-        pf.push_flag[r] = static_cast<unsigned int*>(h_push_flags[r]);
-        pf.recv[r] = static_cast<const float*>(h_recv[r]);
+        if (!h_push_dst[r] || !h_recv[r]) return VQB200_EINVAL;
+        if ((reinterpret_cast<uintptr_t>(h_push_dst[r]) | reinterpret_cast<uintptr_t>(h_recv[r])) & 7u) return VQB200_EINVAL;
+        pf.push_dst[r] = static_cast<uint2*>(h_push_dst[r]);
+        pf.recv[r] = static_cast<const uint2*>(h_recv[r]);
     }
-    pf.flags = static_cast<unsigned int*>(d_flags);
+    pf.err = static_cast<unsigned int*>(d_err);
     pf.rank = rank; pf.world = world; pf.step = step;
     RowLayout L{n_rows, rows_per_image > 0 ? rows_per_image : 1, image_stride, row_stride, col_stride};
     ForwardScratch sc = scratch_view(d_scratch, n_rows, dim, n_embed);
@@ -557,6 +557,15 @@ int vqb200_debug_tc_kernel(const float* d_x, int64_t n_rows, int32_t dim, int32_
     return rc ? cuda_fail(cudaGetLastError()) : VQB200_OK;
 }
 int vqb200_tc_profile_slots(void) { return (int)tc::PROF_SLOTS; }
+
+int vqb200_debug_pingpong(void* d_my_flag, void* d_peer_flag, int32_t iters, int32_t initiator, int32_t with_fence,
+                          uint64_t* d_ns, void* stream) {
+    if (!d_my_flag || !d_peer_flag || !d_ns || iters <= 0) return VQB200_EINVAL;
+    k_pingpong<<<1, 32, 0, (cudaStream_t)stream>>>(static_cast<unsigned int*>(d_my_flag), static_cast<unsigned int*>(d_peer_flag), iters,
+                                                    initiator, with_fence, reinterpret_cast<unsigned long long*>(d_ns));
+    VQ_LAUNCH_CHECK();
+    return VQB200_OK;
+}
 
 // ---- host-buffer path ----------------------------------------------------------------------------
 struct vqb200_host_ctx {

@@ -184,9 +184,8 @@ class Quantize(nn.Module):
     # ------------------------------------------------------------------ peer memory for the fused all-reduce
     def _peer_workspace(self, ws, dev):
         """Symmetric (peer-mapped) receive buffers of all ranks, set up collectively on the first multi-rank training forward:
-        per step parity, one receive slot per rank for the packed statistics + one flag array (PUSH form of the exchange:
-        every rank's fold kernel stores its statistics into slot `rank` of every rank's buffer, the EMA kernel reads local
-        memory only).  Returns None (-> NCCL all-reduce + vqb200_ema_update) when peer memory is unavailable, the world is
+        per step parity, one receive slot per rank for the packed statistics (every rank's fold + EMA kernel stores its
+        statistics as {value, step} pairs into slot `rank` of every rank's buffer and polls its own, local, slots).  Returns None (-> NCCL all-reduce + vqb200_ema_update) when peer memory is unavailable, the world is
         larger than 8 ranks, the shape is outside the fused EMA kernel, or VQB200_NO_P2P is set."""
         if "peer" in ws:
             return ws["peer"]
@@ -198,12 +197,11 @@ class Quantize(nn.Module):
         if ok:
             try:
                 import torch.distributed._symmetric_memory as symm
-                n = _native.load().vqb200_stats_bytes(self.dim, self.n_embed) // 4
+                n = self.n_embed * (self.dim + 1)    # packed statistics words [K*D sums | K counts]
                 n_al = (n + 63) // 64 * 64
-                slots = world * n_al
-                nb = self.n_embed // 4               # blocks of the fold + EMA kernel: one flag per (rank, block)
-                fl = 8 * 128 + 64                    # flag words per parity: [8 ranks][128 blocks] + time-out words
-                total = 2 * slots + 2 * fl           # [slots parity 0 | slots parity 1 | flags 0 | flags 1]
+                slot = 2 * n_al                      # floats per receive slot: every word travels as an 8-byte {value, step} pair
+                slots = world * slot
+                total = 2 * slots + 2 * 64           # [slots parity 0 | slots parity 1 | time-out / trace words 0 | 1]
                 buf = symm.empty(total, dtype=torch.float32, device=dev)
                 hdl = symm.rendezvous(buf, dist.group.WORLD)
                 buf.zero_()
@@ -212,13 +210,12 @@ class Quantize(nn.Module):
                 ptrs = [int(p) for p in hdl.buffer_ptrs]
                 mk = lambda vals: (C.c_void_p * world)(*vals)
                 peer = {"buf": buf, "hdl": hdl, "rank": rank, "world": world, "step": 0, "parity": 0, "checked": 0,
-                        # where MY statistics go on rank r, and the flag word that tells rank r they are there
-                        "push_dst": [mk([p + 4 * (par * slots + rank * n_al) for p in ptrs]) for par in (0, 1)],
-                        "push_flags": [mk([p + 4 * (2 * slots + fl * par + rank * nb) for p in ptrs]) for par in (0, 1)],
-                        # what the EMA kernel reads: my LOCAL slots (one per rank) and my local flag array
-                        "recv": [mk([ptrs[rank] + 4 * (par * slots + r * n_al) for r in range(world)]) for par in (0, 1)],
-                        "flags": [ptrs[rank] + 4 * (2 * slots + fl * par) for par in (0, 1)],
-                        "err": [buf[2 * slots + fl * par + 1024: 2 * slots + fl * par + 1026].view(torch.int32) for par in (0, 1)]}
+                        # where MY statistics go on rank r (peer-mapped) ...
+                        "push_dst": [mk([p + 4 * (par * slots + rank * slot) for p in ptrs]) for par in (0, 1)],
+                        # ... and what the kernel polls and sums: my LOCAL slots, one per rank
+                        "recv": [mk([ptrs[rank] + 4 * (par * slots + r * slot) for r in range(world)]) for par in (0, 1)],
+                        "err_ptr": [ptrs[rank] + 4 * (2 * slots + 64 * par) for par in (0, 1)],
+                        "err": [buf[2 * slots + 64 * par: 2 * slots + 64 * par + 2].view(torch.int32) for par in (0, 1)]}
             except Exception as exc:  # no peer access / unsupported build: keep the NCCL path
                 peer = None
                 self._peer_error = repr(exc)
@@ -360,7 +357,7 @@ class Quantize(nn.Module):
                 self.cluster_size.data_ptr(), self.embed_avg.data_ptr(), image.data_ptr(),
                 q_run.data_ptr() if q_run is not None else None, ind.data_ptr(), diff.data_ptr(), ws["scratch"].data_ptr(),
                 x_dense.data_ptr() if x_dense is not None else None, eng, float(self.decay), float(1 - self.decay), float(self.eps),
-                peer["push_dst"][par], peer["push_flags"][par], peer["recv"][par], peer["flags"][par], peer["rank"],
+                peer["push_dst"][par], peer["recv"][par], peer["err_ptr"][par], peer["rank"],
                 peer["world"], peer["step"], stream), "vqb200_quantize_step_peers")
         else:
             _native.check(lib.vqb200_quantize_step(
