@@ -20,6 +20,7 @@
 //   two-class min scan, ONE ALU op per score) | WG2: output (gather, straight-through value, loss) |
 //   WG3: fp32->bf16 converters | WG4: w16 bulk-copy producer, w17 MMA issuer + TMEM owner (w18-19 idle).
 #pragma once
+#include <atomic>
 #include <cuda_bf16.h>
 #include <cudaTypedefs.h>   // CUtensorMap, PFN_cuTensorMapEncodeTiled (resolved at run time: no link-time libcuda dependency)
 
@@ -1198,7 +1199,8 @@ inline bool tc_layout_dense(const RowLayout& L, const float* x, int dim) {
 }
 inline bool tc_supported(const RowLayout& L, const float* x, int dim, int n_embed) {
     if (!tc_any_ok(dim, n_embed) || L.n_rows < 1) return false;
-    if (getenv("VQB200_DISABLE_TC")) return false;
+    static const bool disabled = getenv("VQB200_DISABLE_TC") != nullptr;     // environment switches are read once per process
+    if (disabled) return false;
     return tc_layout_dense(L, x, dim) || tc_layout_nchw(L, x, dim);
 }
 
@@ -1255,11 +1257,11 @@ inline int tc_launch(const tc::Params& prm, cudaStream_t st) {
     auto kern = tc::k_vq_tc<NSPLIT, AS, XS, DBG, CTA2, NCHW>;
     const int smem = (int)P::total(prm.K);
     // opt-in shared-memory size is a per-device function attribute: cache it per device (several GPUs in one process)
-    static int configured_dev[64] = {0};
+    static std::atomic<int> configured_dev[64];          // (atomic: several host threads / GPUs per process)
     int dev_id = 0;
     if (cudaGetDevice(&dev_id) != cudaSuccess || dev_id < 0 || dev_id >= 64) dev_id = 0, configured_dev[0] = 0;
-    int& configured = configured_dev[dev_id];
-    if (configured < smem) {
+    std::atomic<int>& configured = configured_dev[dev_id];
+    if (configured.load(std::memory_order_relaxed) < smem) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 1;
         configured = smem;
     }
@@ -1303,8 +1305,24 @@ inline int tc_forward(const float* x, const RowLayout& L, int dim, int n_embed, 
     if (nchw && dbg) return 1;
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
-    if (nchw && tc_encode_tmap(&tmap, x, L, dim)) return 1;
-    if (nsplit == 0 && tc_encode_tmap_dense_tf(&tmap, x, L.n_rows)) return 1;
+    if (nchw || nsplit == 0) {
+        // tensor maps depend only on (pointer, layout, kind): training loops call with the same few buffers over and over,
+        // so the last maps are kept (cuTensorMapEncodeTiled costs ~1-2 us on the host)
+        struct Entry { const float* x; RowLayout L; int kind; CUtensorMap map; };
+        static thread_local Entry cache[8];
+        static thread_local int next = 0;
+        const int kind = nchw ? 1 : 2;
+        const Entry* hit = nullptr;
+        for (const Entry& e : cache)
+            if (e.x == x && e.kind == kind && e.L.n_rows == L.n_rows && e.L.rows_per_image == L.rows_per_image &&
+                e.L.image_stride == L.image_stride && e.L.row_stride == L.row_stride && e.L.col_stride == L.col_stride) { hit = &e; break; }
+        if (hit) tmap = hit->map;
+        else {
+            if (nchw ? tc_encode_tmap(&tmap, x, L, dim) : tc_encode_tmap_dense_tf(&tmap, x, L.n_rows)) return 1;
+            cache[next] = Entry{x, L, kind, tmap};
+            next = (next + 1) % 8;
+        }
+    }
     for (int sl = 0; sl < n_slices; ++sl) {
         tc::Params prm;
         prm.tmap = tmap;
@@ -1314,7 +1332,8 @@ inline int tc_forward(const float* x, const RowLayout& L, int dim, int n_embed, 
         prm.stat_sums = sums; prm.stat_counts = counts;
         prm.flagged_count = sc.flagged_count; prm.flagged_rows = sc.flagged_rows; prm.dbg_scores = dbg_scores;
         prm.prof = prof;
-        { const char* e = getenv("VQB200_DBG_SKIP"); prm.dbg_skip = e ? atoi(e) : 0; }
+        static const int dbg_skip_env = [] { const char* e = getenv("VQB200_DBG_SKIP"); return e ? atoi(e) : 0; }();
+        prm.dbg_skip = dbg_skip_env;
         prm.cA = tc::bound_cA(nsplit); prm.cB = tc::BOUND_CB;
         prm.rpi = L.rows_per_image; prm.img_stride = L.image_stride; prm.col_stride = L.col_stride;
         prm.x_dense = (nchw && sl == 0) ? x_dense : nullptr;
@@ -1323,7 +1342,7 @@ inline int tc_forward(const float* x, const RowLayout& L, int dim, int n_embed, 
         int rc;
         if (nchw) {                                // x stages x3: the output warps read x from the stage too
             if (nsplit == 3) rc = (pair && K_launch == 512) ? tc_launch<3, 1, 3, false, true, true>(prm, st) : tc_launch<3, 1, 1, false, false, true>(prm, st);
-            else rc = getenv("VQB200_DBG_SKIP") ? tc_launch<1, 2, 3, true, false, true>(prm, st)      // (diagnostics: role skipping)
+            else rc = dbg_skip_env ? tc_launch<1, 2, 3, true, false, true>(prm, st)      // (diagnostics: role skipping)
                                                 : tc_launch<1, 2, 3, false, false, true>(prm, st);
         } else if (nsplit == 0) {
             rc = dbg ? tc_launch<0, 2, 2, true, false>(prm, st) : tc_launch<0, 2, 2, false, false>(prm, st);

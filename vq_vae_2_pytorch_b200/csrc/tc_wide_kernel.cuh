@@ -12,6 +12,7 @@
 //   filter           : plain bf16 (cA = 7.9e-3); rows it cannot certify go to the exact fp32 fix-up (k_fixup)
 //   accumulation term: cB scales with the number of accumulated MMAs (BOUND_CB * DB)
 #pragma once
+#include <atomic>
 #include "tc_kernel.cuh"
 
 namespace vqb200 {
@@ -566,7 +567,8 @@ inline bool tcw_shape_ok(int dim, int n_embed) {
 }
 inline bool tcw_supported(const RowLayout& L, const float* x, int dim, int n_embed) {
     if (!tcw_shape_ok(dim, n_embed) || L.n_rows < 1) return false;
-    if (getenv("VQB200_DISABLE_TC") || getenv("VQB200_DISABLE_TCW")) return false;
+    static const bool disabled = getenv("VQB200_DISABLE_TC") != nullptr || getenv("VQB200_DISABLE_TCW") != nullptr;
+    if (disabled) return false;
     return tc_layout_dense(L, x, dim);
 }
 
@@ -593,11 +595,11 @@ inline int tcw_launch(const tcw::WParams& prm, cudaStream_t st) {
                        tcw::enorm_in_smem(PRE, DB) ? 1 : 0};
     const int smem = (int)P.total();
     // opt-in shared-memory size is a per-device function attribute: cache it per device (several GPUs in one process)
-    static int configured_dev[64] = {0};
+    static std::atomic<int> configured_dev[64];          // (atomic: several host threads / GPUs per process)
     int dev_id = 0;
     if (cudaGetDevice(&dev_id) != cudaSuccess || dev_id < 0 || dev_id >= 64) dev_id = 0, configured_dev[0] = 0;
-    int& configured = configured_dev[dev_id];
-    if (configured < smem) {
+    std::atomic<int>& configured = configured_dev[dev_id];
+    if (configured.load(std::memory_order_relaxed) < smem) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
             fprintf(stderr, "vqb200: wide tensor-core kernel needs %d bytes of shared memory (DB=%d XS=%d KL=%d)\n", smem, DB, XS, prm.KL);
             return 1;

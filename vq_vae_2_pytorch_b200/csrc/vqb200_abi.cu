@@ -40,6 +40,17 @@ inline int cuda_fail(cudaError_t e) {
         VQ_CUDA(cudaGetLastError());   \
     } while (0)
 
+// per (device, kernel slot): the largest opt-in dynamic shared-memory size already configured
+bool smem_attr_needed(int slot, size_t bytes) {
+    static std::atomic<size_t> configured[64][4];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    size_t cur = configured[dev][slot].load(std::memory_order_relaxed);
+    if (cur >= bytes) return false;
+    configured[dev][slot].store(bytes, std::memory_order_relaxed);
+    return true;
+}
+
 bool layout_ok(int64_t n_rows, int32_t dim, int64_t rpi, int64_t img_stride, int64_t row_stride,
                int64_t col_stride) {
     if (n_rows < 0 || dim <= 0 || rpi <= 0 || row_stride <= 0 || col_stride <= 0) return false;
@@ -128,9 +139,12 @@ int forward_impl(const float* d_x, const RowLayout& L, int dim, int n_embed, con
         const bool want_gather = d_quantize || d_diff || sums;
         const size_t gsmem = (size_t)GS_BM * (dim + 1) * sizeof(float);
         if (gsmem > 200 * 1024) return VQB200_EUNSUPPORTED;
-        if (gsmem > 48 * 1024) VQ_CUDA(cudaFuncSetAttribute(k_gather_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+        // opt-in shared-memory sizes are per-device function attributes: set once per (device, size), not on every call
+        if (gsmem > 48 * 1024 && smem_attr_needed(0, gsmem))
+            VQ_CUDA(cudaFuncSetAttribute(k_gather_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
         // k_fixup also carries ~18 KB of static shared memory (the exact re-score tiles): opt in as soon as the sum passes 48 KB
-        if (gsmem > 24 * 1024) VQ_CUDA(cudaFuncSetAttribute(k_fixup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+        if (gsmem > 24 * 1024 && smem_attr_needed(1, gsmem))
+            VQ_CUDA(cudaFuncSetAttribute(k_fixup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
         const int sms = tc_num_sms();
         if (use_tc) {
             // tensor-core filter + fused output for certified rows; flagged rows -> exact SIMT fix-up (one launch:
@@ -162,7 +176,8 @@ int forward_impl(const float* d_x, const RowLayout& L, int dim, int n_embed, con
             }
         }
         if (stats_kernel) {
-            VQ_CUDA(cudaFuncSetAttribute(k_code_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs_smem));
+            if (smem_attr_needed(2, cs_smem))
+                VQ_CUDA(cudaFuncSetAttribute(k_code_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs_smem));
             // rows per trip chosen so the trips divide evenly over the SMs (one CTA per SM, private table each)
             const int sms_cs = std::min(tc_num_sms(), STAT_PARTS);
             int64_t waves = (L.n_rows + (int64_t)sms_cs * CS_CHUNK - 1) / ((int64_t)sms_cs * CS_CHUNK);
