@@ -4,5 +4,6 @@ from .quantize import Quantize, row_layout  # noqa: F401
 from . import distributed  # noqa: F401
 from . import _native  # noqa: F401
 from .egress import CodeEgress, unpack_codes  # noqa: F401
+from .trainer_glue import DeferredMetrics, ddp_wrap, replicas_identical  # noqa: F401
 
-__all__ = ["Quantize", "row_layout", "distributed", "CodeEgress", "unpack_codes"]
+__all__ = ["Quantize", "row_layout", "distributed", "CodeEgress", "unpack_codes", "DeferredMetrics", "ddp_wrap", "replicas_identical"]
