@@ -60,9 +60,10 @@ uint64_t    vqb200_launch_count(void);         /* kernels launched by this libra
 /* ---- workspace sizes (bytes) ------------------------------------------------------------------ */
 /* prepared codebook image: code-major fp32 copy, ||e_k||^2, tensor-core operand images            */
 size_t vqb200_codebook_bytes(int32_t dim, int32_t n_embed);
-/* per-call scratch of the forward (diff accumulator, flagged-row list, counters).  Layout contract used
- * by adaptive callers: int32 at byte offset 16 = number of rows the last tcgen05 forward sent to the
- * exact re-score.                                                                                   */
+/* per-call scratch of the forward (diff accumulator, flagged-row list, counters, rows-per-code counters, per-CTA statistics
+ * tables where the shape allows them).  Layout contract used by adaptive callers: int32 at byte offset 16 = number of
+ * rows the last tcgen05 forward sent to the exact re-score; int32 at byte offset 56 != 0 = the code-statistics kernel
+ * met an index outside [0, n_embed) (internal error: the indices are written by this library's own kernels).         */
 size_t vqb200_forward_scratch_bytes(int64_t n_rows, int32_t dim, int32_t n_embed);
 /* packed codebook statistics: n_embed*dim per-code sums (code-major), then n_embed counts, then 4
  * spare words the EMA kernel uses as scalars; only the first n_embed*(dim+1) floats are all-reduced.
@@ -130,8 +131,10 @@ int vqb200_quantize_step_peers(const float* d_x, int64_t n_rows, int32_t dim, in
 
 /* The module's whole forward in one call (fewer host round trips per step):
  *   vqb200_codebook_prepare(d_embed) + vqb200_quantize_forward(...) and, when `ema` != 0 and d_stats != NULL,
- *   vqb200_ema_update on the statistics of this call (single-process training).  With several ranks the caller
- *   passes ema = 0, all-reduces d_stats (vqvae.py:58-59) and calls vqb200_ema_update itself.
+ *   the EMA of vqvae.py:61-70 on the statistics of this call (single-process training; at dim 64 / n_embed 256 or 512 ONE
+ *   kernel folds the per-CTA statistics tables and applies the EMA, and d_stats is then not written).  With several
+ *   ranks the caller uses vqb200_quantize_step_peers, or passes ema = 0, all-reduces d_stats (vqvae.py:58-59) and calls
+ *   vqb200_ema_update itself.
  * d_cluster_size / d_embed_avg are only touched when the EMA runs.
  * d_x_dense (may be NULL): n_rows*dim floats of scratch, 32-byte aligned (written with 256-bit stores).  With it, NCHW-physical rows (unit row stride, the
  * permute(0,2,3,1) view of vqvae.py:227,235; whole 128-row tiles per image) are consumed IN PLACE by the tensor-core
@@ -214,6 +217,11 @@ int vqb200_tc_split(void);   /* 3 = split-bf16 filter (default), 1 = plain bf16 
  * chunks across internal streams.  The context owns device staging memory sized for max_rows.       */
 typedef struct vqb200_host_ctx vqb200_host_ctx;
 int  vqb200_host_ctx_create(int64_t max_rows, int32_t dim, int32_t n_embed, vqb200_host_ctx** out);
+/* The context's private copy / compute streams are non-blocking.  Every vqb200_host_quantize call first orders them behind
+ * the work already queued on the CALLER's stream (so writes to d_embed / d_cluster_size / d_embed_avg issued there just
+ * before the call are observed), makes the context's device current, and returns only after its own streams have drained.
+ * The caller's stream is the legacy default stream unless set here (e.g. torch.cuda.current_stream().cuda_stream).        */
+int  vqb200_host_ctx_set_stream(vqb200_host_ctx* ctx, void* stream);
 void vqb200_host_ctx_destroy(vqb200_host_ctx* ctx);
 /* device-resident module buffers (embed / cluster_size / embed_avg) stay on the device */
 int  vqb200_host_quantize(vqb200_host_ctx* ctx, const float* h_x, int64_t n_rows,

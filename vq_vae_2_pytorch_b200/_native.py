@@ -49,6 +49,7 @@ SIGNATURES = {
     "vqb200_debug_pingpong": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p]),
     "vqb200_debug_tc_kernel": (C.c_int, [_p, _i64, _i32, _i32, _p, _p, _p, _p, _i32, _p]),
     "vqb200_host_ctx_create": (C.c_int, [_i64, _i32, _i32, C.POINTER(_p)]),
+    "vqb200_host_ctx_set_stream": (C.c_int, [_p, _p]),
     "vqb200_host_ctx_destroy": (None, [_p]),
     "vqb200_host_quantize": (C.c_int, [_p, _p, _i64, _p, _p, _p, _f32, _f32, _f32, _i32, _p, _p, _p, _i32]),
 }

@@ -285,8 +285,12 @@ k_code_stats(const float* __restrict__ x, RowLayout L, int D, int K, const int64
         for (int i = tid; i < K; i += CS_THREADS) hist[i] = 0;
         __syncthreads();
         for (int i = tid; i < rows; i += CS_THREADS) {
-            int k = (int)embed_ind[r0 + i];
-            k = min(max(k, 0), K - 1);
+            const long long kl = embed_ind[r0 + i];
+            int k = (int)kl;
+            if (kl < 0 || kl >= K) {             // cannot happen for indices written by our own kernels: clamp for memory safety AND report
+                if (n_parts_out) atomicExch(n_parts_out + 1, 1u);       // scratch header word 14 (byte 56): internal-error flag
+                k = kl < 0 ? 0 : K - 1;
+            }
             code[i] = (unsigned short)k;
             atomicAdd(&hist[k], 1);
         }

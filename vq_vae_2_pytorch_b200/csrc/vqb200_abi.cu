@@ -596,6 +596,8 @@ struct vqb200_host_ctx {
     void* d_codebook;
     cudaStream_t s_in, s_run, s_out;
     cudaEvent_t ev_in[64], ev_run[64], ev_start;
+    int device;                  // the device the context was created on (made current by every call)
+    cudaStream_t caller;         // stream whose earlier work (writes to d_embed / the EMA buffers) the call must observe
 };
 
 int vqb200_host_ctx_create(int64_t max_rows, int32_t dim, int32_t n_embed, vqb200_host_ctx** out) {
@@ -606,6 +608,8 @@ int vqb200_host_ctx_create(int64_t max_rows, int32_t dim, int32_t n_embed, vqb20
     if (!c) return VQB200_EINVAL;
     std::memset(c, 0, sizeof(*c));
     c->max_rows = max_rows; c->dim = dim; c->n_embed = n_embed;
+    if (cudaGetDevice(&c->device) != cudaSuccess) c->device = 0;
+    c->caller = nullptr;         // legacy default stream (= torch's default stream) until vqb200_host_ctx_set_stream
     // ~8 MiB of fp32 rows per chunk keeps PCIe busy in both directions while the kernels run
     int64_t chunk_mb = 16;      // measured on B200 / PCIe Gen5: 16 MiB chunks move 272 MB per call in 3.43 ms, 8 MiB in 3.75 ms
     if (const char* e = getenv("VQB200_HOST_CHUNK_MB")) { int v = atoi(e); if (v >= 1 && v <= 1024) chunk_mb = v; }
@@ -634,6 +638,12 @@ int vqb200_host_ctx_create(int64_t max_rows, int32_t dim, int32_t n_embed, vqb20
     return VQB200_OK;
 }
 
+int vqb200_host_ctx_set_stream(vqb200_host_ctx* c, void* stream) {
+    if (!c) return VQB200_EINVAL;
+    c->caller = (cudaStream_t)stream;
+    return VQB200_OK;
+}
+
 void vqb200_host_ctx_destroy(vqb200_host_ctx* c) {
     if (!c) return;
     cudaFree(c->d_x); cudaFree(c->d_q); cudaFree(c->d_ind); cudaFree(c->d_diff);
@@ -657,6 +667,11 @@ int vqb200_host_quantize(vqb200_host_ctx* c, const float* h_x, int64_t n_rows, f
     if (n_rows > 0 && (!h_x || !h_embed_ind)) return VQB200_EINVAL;
     if (training && (!d_cluster_size || !d_embed_avg)) return VQB200_EINVAL;
     const int D = c->dim, K = c->n_embed;
+    VQ_CUDA(cudaSetDevice(c->device));
+    // the private streams are non-blocking: order them behind whatever the caller's stream did to d_embed / cluster_size /
+    // embed_avg before this call (the call itself returns only after its own streams have drained)
+    VQ_CUDA(cudaEventRecord(c->ev_start, c->caller));
+    VQ_CUDA(cudaStreamWaitEvent(c->s_run, c->ev_start, 0));
     int rc = prepare_codebook(d_embed, D, K, c->d_codebook, c->s_run);
     if (rc) return rc;
     float* stats = training ? c->d_stats : nullptr;

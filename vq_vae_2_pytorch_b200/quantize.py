@@ -265,6 +265,8 @@ class Quantize(nn.Module):
         if pend is not None and pend[0].query():
             _, host_count, rows, mode_used = pend
             f["pending"] = None
+            if int(host_count[10]) != 0:      # scratch header byte 56: the statistics kernel met an index outside [0, n_embed)
+                raise RuntimeError("Quantize: internal error -- the code-statistics kernel read an out-of-range index")
             if mode_used == "bf16" and int(host_count[0]) > self.FLAG_SWITCH_FRACTION * rows:
                 f["mode"], f["cooldown"] = "split", self.SPLIT_COOLDOWN_CALLS
         if f["mode"] == "split":
@@ -284,8 +286,9 @@ class Quantize(nn.Module):
             return
         host = ws.get("flag_host")
         if host is None:
-            host = ws["flag_host"] = torch.zeros(1, dtype=torch.int32).pin_memory()
-        host.copy_(ws["scratch"][16:20].view(torch.int32), non_blocking=True)   # vqb200.h: int32 at byte 16 of the scratch
+            host = ws["flag_host"] = torch.zeros(11, dtype=torch.int32).pin_memory()
+        # vqb200.h: scratch header -- int32 at byte 16 = rows sent to the exact re-score, int32 at byte 56 = internal-error flag
+        host.copy_(ws["scratch"][16:60].view(torch.int32), non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
         f["pending"] = (ev, host, n, "bf16" if eng == _native.ENGINE_TCGEN05_BF16 else "split")
