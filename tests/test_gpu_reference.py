@@ -227,3 +227,35 @@ def test_unmodified_vqvae_deep_quantize_call_sites(ref):
             assert H.scaled_err(qo.embed_avg, qr.embed_avg, qr.embed_avg.abs().amax(0, keepdim=True).double().clamp_min(1e-30)) <= 1e-5
             H.sync_state(qo, qr)
     free_memory()
+
+
+def test_channels_last_model_feeds_the_dense_fast_path(ref):
+    """INTEGRATION.md recipe: run the (unmodified, class-swapped) reference VQVAE in torch.channels_last.  The 1x1
+    `quantize_conv_*` outputs are then NHWC-physical, so the `permute(0, 2, 3, 1)` views of vqvae.py:227,235 are CONTIGUOUS
+    [B,H,W,D] rows -- the quantizer's dense fast path, no strided kernel variant -- and `quantize.permute(0, 3, 1, 2)` is a
+    channels_last tensor the decoder convolutions consume natively.  Results must equal the NCHW run of the reference."""
+    from vq_vae_2_pytorch_b200 import row_layout
+    ref_model, our_model = build_models(ref, "VQVAE")
+    ref_model.eval()
+    our_model = our_model.to(memory_format=torch.channels_last).eval()
+    seen = []
+    hooks = [m.register_forward_pre_hook(lambda mod, args: seen.append((args[0].is_contiguous(), row_layout(args[0]))))
+             for m in (our_model.quantize_t, our_model.quantize_b)]
+    img = torch.randn(8, 3, 256, 256, device=DEV, generator=torch.Generator(device=DEV).manual_seed(5))
+    with torch.no_grad():
+        rt, rb, rd, rit, rib = ref_model.encode(img)
+        ot, ob, od, oit, oib = our_model.encode(img.contiguous(memory_format=torch.channels_last))
+    for h in hooks:
+        h.remove()
+    assert len(seen) == 2 and all(c for c, _ in seen), "quantizer inputs are not contiguous under channels_last"
+    for _, lay in seen:
+        n, rpi, img_stride, row, col = lay
+        assert (row, col) == (64, 1)                                          # dense rows: the fast path
+    assert ot.is_contiguous(memory_format=torch.channels_last) and ob.is_contiguous(memory_format=torch.channels_last)
+    # cuDNN may pick other algorithms for the other memory format: the latents agree to conv round-off, the ids wherever
+    # the two runs' latents do not straddle a near-tie
+    assert float((oit != rit).float().mean()) <= 1e-3 and float((oib != rib).float().mean()) <= 1e-3
+    same_t = (oit == rit).unsqueeze(1).expand_as(rt)
+    assert torch.allclose(ot[same_t], rt[same_t], rtol=1e-4, atol=1e-5)
+    assert torch.allclose(od, rd, rtol=1e-3, atol=0)
+    free_memory()

@@ -1,4 +1,5 @@
-"""Step time of the training forward at the small batches the reference's trainers really use (B = 8 .. 32 per GPU)."""
+"""Step time of the training forward at the small batches the reference's trainers really use (B = 8 .. 32 per GPU):
+eager calls (host-issue bound below ~50 us) and the same step replayed from a CUDA graph (device time only)."""
 import sys
 
 import torch
@@ -8,6 +9,7 @@ import vq_vae_2_pytorch_b200 as vq  # noqa: E402
 
 dev = "cuda:0"
 torch.manual_seed(0)
+print(f"{'case':14s} {'layout':5s} {'rows':>7s} {'eager us':>9s} {'graph us':>9s}  {'Gvec/s (graph)':>14s}")
 for name, shape in (("top B=8", (8, 32, 32, 64)), ("bottom B=8", (8, 64, 64, 64)), ("bottom B=32", (32, 64, 64, 64)),
                     ("bottom B=128", (128, 64, 64, 64))):
     q = vq.Quantize(64, 512).to(dev).train()
@@ -26,5 +28,17 @@ for name, shape in (("top B=8", (8, 32, 32, 64)), ("bottom B=8", (8, 64, 64, 64)
             q(xx)
         b.record()
         torch.cuda.synchronize()
-        us = a.elapsed_time(b) * 10
-        print(f"{name:14s} {layout:5s} N={n:7d}: {us:7.1f} us/step  {n / us / 1e3:6.2f} Gvec/s")
+        eager = a.elapsed_time(b) * 10
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(10):                       # ten chained training steps per replay
+                out = q(xx)
+        g.replay()
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(10):
+            g.replay()
+        b.record()
+        torch.cuda.synchronize()
+        graph = a.elapsed_time(b) * 10
+        print(f"{name:14s} {layout:5s} {n:7d} {eager:9.1f} {graph:9.1f}  {n / graph / 1e3:14.2f}")
