@@ -361,6 +361,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip reference_gpu / nchw / cfg3 / parity_multi")
+    ap.add_argument("--cfg5", action="store_true", help="also run the cfg-5 codebook sweep (K = 512 .. 8192, D = 64 .. 256, N = 524 288 per GPU, train fwd+EMA)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -617,6 +618,28 @@ def main():
                 torch.cuda.empty_cache()
         if world > 1:
             extras["parity_multi"] = parity_multi(vq, dev, rank, world, dist)
+    if args.cfg5:
+        # cfg-5: scaled codebook sweep, batch 128 (N = 524 288 rows) per GPU, training forward + EMA (statistics all-reduced
+        # across ranks: peer-memory exchange at D = 64 / K = 512, NCCL all-reduce of the packed buffer elsewhere)
+        sweep = []
+        for d5 in (64, 128, 256):
+            for k5 in (512, 1024, 2048, 4096, 8192):
+                torch.manual_seed(0)
+                m5 = vq.Quantize(d5, k5).to(dev).train()
+                e5 = m5.embed.clone()
+                g5 = torch.Generator(device=dev).manual_seed(55 + rank)
+                pick = torch.randint(0, k5, (N_ROWS,), device=dev, generator=g5)
+                x5 = (e5.t()[pick] + 0.1 * torch.randn(N_ROWS, d5, device=dev, generator=g5)).contiguous()
+                m5.cluster_size.data.fill_(float(world * N_ROWS) / k5); m5.embed_avg.data.copy_(e5 * (float(world * N_ROWS) / k5))
+                for _ in range(3):
+                    m5(x5)
+                w_ms, _, _ = timed_windows(lambda i: m5(x5), 5, 3, world, dev, dist)
+                ms = float(np.median(w_ms)) / 5
+                sweep.append({"dim": d5, "n_embed": k5, "ms_per_step": ms, "value": world * N_ROWS / (ms * 1e-3),
+                              "tensor_tflops_algorithmic": 2.0 * world * N_ROWS * d5 * k5 / (ms * 1e-3) / 1e12})
+                del m5, x5
+                torch.cuda.empty_cache()
+        extras["cfg5"] = {"unit": UNIT, "rows_per_gpu": N_ROWS, "mode": "train fwd+EMA, clustered rows", "points": sweep}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
