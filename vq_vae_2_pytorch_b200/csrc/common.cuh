@@ -66,6 +66,8 @@ struct ForwardScratch {
     unsigned int* ema_ticket;  // 1 word: last-block-done ticket of the fold + EMA kernel
     unsigned int* n_parts;     // 1 word: number of per-CTA statistics tables the statistics kernel of this call wrote
     int* code_counts;      // [n_embed] rows per code of this call (integer atomics of the statistics kernel; cleared with the header)
+    unsigned int* fix_tickets;         // [FIX_CAP / 64] per-chunk tickets of the code-block-parallel fix-up (cleared with the header)
+    unsigned long long* fix_partial;   // [min(n_rows, FIX_CAP)][FIX_KB] partial arg-min keys of the flagged rows
     int* flagged_rows;     // [n_rows] row ids
     float4* partial;       // [n_rows] running (m1, m2, winner, ||e_winner||) of the sliced tensor-core engine (n_embed > 512), else null
     float* stat_partials;  // [STAT_PARTS][K*(D+1)] per-CTA statistics tables
@@ -75,6 +77,12 @@ struct ForwardScratch {
     float* wide_norm;      // [tiles][128] ||x_row||
 };
 constexpr int STAT_PARTS = 160;
+// fix-up of few flagged rows: the exact re-score of a 64-row chunk is split over the 64-code blocks of the codebook (up to
+// FIX_KB of them) so that a handful of chunks still fills the GPU; at most FIX_CAP rows take that route
+constexpr int FIX_CAP = 65536, FIX_KB = 8;
+__host__ __device__ inline size_t scratch_header_bytes(int n_embed) {     // header + code counters + fix-up tickets (zeroed per call)
+    return 256 + align_up((size_t)n_embed * 4, 256) + (size_t)(FIX_CAP / 64) * 4;
+}
 __host__ __device__ inline bool scratch_has_partial(int dim, int n_embed) {
     return (dim == 64 && n_embed > 512) || (dim == 128 && n_embed > 512) || (dim == 256 && n_embed > 256);   // sliced tensor-core launches
 }
@@ -88,8 +96,9 @@ __host__ __device__ inline size_t scratch_wide_bytes(int64_t n_rows, int dim) {
 __host__ __device__ inline bool scratch_has_stat_tables(int dim, int n_embed) {
     return (size_t)n_embed * dim * 4 + (size_t)(4 * n_embed + 2) * 4 + 4096 * 12 + 16 <= 200 * 1024 && n_embed <= 65535;   // = code_stats_smem_bytes <= 200 KB
 }
+__host__ __device__ inline int64_t std_min64(int64_t a, int64_t b) { return a < b ? a : b; }
 __host__ __device__ inline size_t forward_scratch_bytes(int64_t n_rows, int dim, int n_embed) {
-    return 256 + align_up((size_t)n_embed * 4, 256) + align_up((size_t)n_rows * 4, 256) +
+    return scratch_header_bytes(n_embed) + (size_t)std_min64(n_rows, FIX_CAP) * FIX_KB * 8 + align_up((size_t)n_rows * 4, 256) +
            (scratch_has_partial(dim, n_embed) ? align_up((size_t)n_rows * 16, 256) : 0) +
            (scratch_has_wide(dim, n_embed) ? scratch_wide_bytes(n_rows, dim) : 0) +
            (scratch_has_stat_tables(dim, n_embed) ? (size_t)STAT_PARTS * n_embed * (dim + 1) * 4 : 0);
@@ -103,7 +112,10 @@ __host__ __device__ inline ForwardScratch scratch_view(void* base, int64_t n_row
     s.ema_ticket = (unsigned int*)(p + 48);
     s.n_parts = (unsigned int*)(p + 52);
     s.code_counts = (int*)(p + 256);
-    p += 256 + align_up((size_t)n_embed * 4, 256);
+    s.fix_tickets = (unsigned int*)(p + 256 + align_up((size_t)n_embed * 4, 256));
+    p += scratch_header_bytes(n_embed);
+    s.fix_partial = (unsigned long long*)p;
+    p += (size_t)std_min64(n_rows, FIX_CAP) * FIX_KB * 8;
     s.flagged_rows = (int*)p;
     p += align_up((size_t)n_rows * 4, 256);
     s.partial = nullptr;

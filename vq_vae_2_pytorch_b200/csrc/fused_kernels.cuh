@@ -27,6 +27,10 @@ __global__ void __launch_bounds__(256) k_prepare64(const float* __restrict__ emb
     if (zero_header) {                        // (saves a memset node in the chain)
         if (blockIdx.x == 0 && tid < 64) zero_header[tid] = 0u;              // loss accumulator, flagged-row counter, tickets
         if (tid < PREP_CODES) zero_header[64 + k0 + tid] = 0u;               // rows-per-code counters of this call (ForwardScratch::code_counts)
+        // per-chunk tickets of the fix-up (ForwardScratch::fix_tickets, behind the 256-byte aligned counters)
+        const int n_tick = FIX_CAP / 64, per = (n_tick + (int)gridDim.x - 1) / (int)gridDim.x;
+        const int tbase = 64 + (int)(align_up((size_t)K * 4, 256) / 4);
+        if (tid < per && blockIdx.x * per + tid < n_tick) zero_header[tbase + blockIdx.x * per + tid] = 0u;
     }
     for (int i = tid; i < 64 * PREP_CODES; i += 256) {          // 32-byte segments of 8 consecutive codes per dim
         const int d = i >> 3, j = i & 7;
@@ -235,32 +239,64 @@ __global__ void __launch_bounds__(256) k_ema64(const float* __restrict__ stats, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// flagged-row fix-up of the tcgen05 engine in one launch: exact fp32 re-score (assign_chunk), then gather /
-// straight-through value / loss / statistics (gather_chunk) of the same rows by the same block, then -- by the last
-// block to finish -- the loss finalisation diff = acc * inv_count.  Exits after the ticket when no row was flagged.
+// flagged-row fix-up of the tcgen05 engine in one launch: exact fp32 re-score, then gather / straight-through value /
+// loss / statistics (gather_chunk) of the same rows, then -- by the last block to finish -- the loss finalisation
+// diff = acc * inv_count.  Exits after the ticket when no row was flagged.
+//   many rows : one work item = one 64-row chunk against the whole codebook (assign_chunk); 4 CTAs per SM keep the loads of
+//               several chunks in flight (one CTA per SM ran at 5 TFLOP/s).
+//   few rows  (<= FIX_CAP rows and fewer chunks than 2 x CTAs, codebooks of 2 .. FIX_KB 64-code blocks): one work item = one
+//               chunk against ONE 64-code block; the partial arg-mins are 64-bit (distance, code) keys whose integer
+//               minimum is the reference's arg-min; the last block of a chunk (per-chunk ticket) merges them and produces the
+//               chunk's outputs.  492 flagged rows (split-bf16 filter on N(0,1) rows) used to occupy 8 CTAs for ~100 us.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(AS_THREADS)
+__global__ void __launch_bounds__(AS_THREADS, 2)
 k_fixup(const float* __restrict__ x, RowLayout L, int D, int K, const float* __restrict__ cbT,
         const float* __restrict__ ee, int64_t* __restrict__ embed_ind, float* __restrict__ quantize,
         double* __restrict__ diff_acc, float* __restrict__ stat_sums, float* __restrict__ stat_counts,
         const int* __restrict__ row_list, const int* __restrict__ row_count, int want_gather,
-        float* __restrict__ diff, double inv_count, unsigned int* __restrict__ ticket) {
+        float* __restrict__ diff, double inv_count, unsigned int* __restrict__ ticket,
+        unsigned long long* __restrict__ fix_partial, unsigned int* __restrict__ fix_tickets) {
     extern __shared__ float gs_tile[];
     __shared__ float warp_part[AS_THREADS / 32];
     __shared__ unsigned int last_s;
+    __shared__ unsigned int chunk_last_s;
     pdl_wait();
     pdl_trigger();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t total = (int64_t)(*row_count);
+    const int64_t chunks = (total + AS_BM - 1) / AS_BM;
+    const int KB = (K + AS_BN - 1) / AS_BN;
+    const bool split = fix_partial && fix_tickets && KB > 1 && KB <= FIX_KB && total <= FIX_CAP && chunks < 2 * (int64_t)gridDim.x;
+    const int64_t items = split ? chunks * KB : chunks;
     float acc = 0.f;
-    for (int64_t n0 = (int64_t)blockIdx.x * AS_BM; n0 < total; n0 += (int64_t)gridDim.x * AS_BM) {
-        assign_chunk(x, L, D, K, cbT, ee, embed_ind, row_list, total, n0);
+    for (int64_t w = blockIdx.x; w < items; w += gridDim.x) {
+        const int64_t chunk = split ? w / KB : w;
+        const int64_t n0 = chunk * AS_BM;
+        if (split) {
+            const int kb = (int)(w - chunk * KB);
+            assign_part(x, L, D, K, cbT, ee, row_list, total, n0, kb * AS_BN, min(K, (kb + 1) * AS_BN), fix_partial + kb, FIX_KB);
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) chunk_last_s = (atomicAdd(fix_tickets + chunk, 1u) == (unsigned int)(KB - 1)) ? 1u : 0u;
+            __syncthreads();
+            if (!chunk_last_s) continue;                        // (block-uniform)
+            __threadfence();
+            if (tid < AS_BM && n0 + tid < total) {              // merge the code blocks' partial arg-mins of my row
+                const volatile unsigned long long* pr = fix_partial + (size_t)(n0 + tid) * FIX_KB;
+                unsigned long long best = pr[0];
+                for (int b = 1; b < KB; ++b) { const unsigned long long v = pr[b]; best = v < best ? v : best; }
+                embed_ind[row_list[n0 + tid]] = (int64_t)(unsigned int)(best & 0xffffffffull);
+            }
+            if (tid == 0) fix_tickets[chunk] = 0u;              // clean for the next call
+        } else {
+            assign_chunk(x, L, D, K, cbT, ee, embed_ind, row_list, total, n0);
+        }
         if (want_gather) {
             __syncthreads();                                    // the chunk's indices are written (same block reads them)
             for (int64_t g0 = n0; g0 < min(total, n0 + AS_BM); g0 += GS_BM)
                 gather_chunk(x, L, D, cbT, embed_ind, quantize, stat_sums, stat_counts, row_list, total, g0, gs_tile, acc);
         }
     }
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (want_gather && diff_acc) {
         acc = warp_sum(acc);
         if (lane == 0) warp_part[warp] = acc;

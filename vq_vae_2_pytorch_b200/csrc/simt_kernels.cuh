@@ -42,18 +42,29 @@ __global__ void k_codebook_norms(const float* __restrict__ cbT, float* __restric
 // ------------------------------------------------------------------------------------------------
 constexpr int AS_BM = 64, AS_BN = 64, AS_DC = 32, AS_THREADS = 256;
 
-// one chunk of AS_BM rows starting at position n0; rows come either from [0, total) or, when row_list != nullptr,
-// from row_list[0 .. total)
-__device__ __forceinline__ void assign_chunk(const float* __restrict__ x, const RowLayout& L, int D, int K,
-                                             const float* __restrict__ cbT, const float* __restrict__ ee,
-                                             int64_t* __restrict__ embed_ind, const int* __restrict__ row_list,
-                                             int64_t total, int64_t n0) {
+// (distance, code) as ONE unsigned 64-bit key whose integer order is the reference's order: smaller distance first (fp32
+// bits mapped to an order-preserving unsigned), lower code index on exact ties -- partial arg-mins of different code blocks
+// of one row are merged with a plain integer minimum
+__device__ __forceinline__ unsigned long long dist_key(float dist, int k) {
+    unsigned int u = __float_as_uint(dist);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    return ((unsigned long long)u << 32) | (unsigned int)k;
+}
+
+// exact distance + arg-min (vqvae.py:44-49) of one chunk of AS_BM rows starting at position n0 against the codes [c_lo, c_hi):
+// register-tiled fp32 FMA, 64 rows x 64 codes per step.  Rows come either from [0, total) or, when row_list != nullptr,
+// from row_list[0 .. total).  The result of row position n0 + r goes to embed_ind[row] (whole codebook) and / or, as a
+// (distance, code) key, to part[(n0 + r) * part_stride] (partial arg-min of a code block).
+__device__ __forceinline__ void assign_core(const float* __restrict__ x, const RowLayout& L, int D, int K,
+                                            const float* __restrict__ cbT, const float* __restrict__ ee,
+                                            const int* __restrict__ row_list, int64_t total, int64_t n0, int c_lo, int c_hi,
+                                            int64_t* __restrict__ embed_ind, unsigned long long* __restrict__ part, int part_stride) {
     __shared__ __align__(16) float xs[AS_DC][AS_BM + 4];
     __shared__ __align__(16) float es[AS_DC][AS_BN + 4];
     __shared__ int64_t row_off[AS_BM];
     __shared__ int row_id[AS_BM];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    __syncthreads();                              // previous chunk's row_id / row_off readers are done
+    __syncthreads();
     if (tid < AS_BM) {
         int64_t i = n0 + tid;
         int64_t n = -1;
@@ -62,22 +73,18 @@ __device__ __forceinline__ void assign_chunk(const float* __restrict__ x, const 
         row_off[tid] = n >= 0 ? row_offset(L, n) : 0;
     }
     __syncthreads();
-
     float best[4];
     int best_k[4];
     float xx[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { best[i] = INFINITY; best_k[i] = 0; }
-
-    for (int c0 = 0; c0 < K; c0 += AS_BN) {
+    for (int i = 0; i < 4; ++i) { best[i] = INFINITY; best_k[i] = c_lo; }
+    for (int c0 = c_lo; c0 < c_hi; c0 += AS_BN) {
         float acc[4][4];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-
         for (int d0 = 0; d0 < D; d0 += AS_DC) {
-            // x tile: pick the thread->element map that coalesces for this layout
             for (int i = tid; i < AS_BM * AS_DC; i += AS_THREADS) {
                 int r, dd;
                 if (L.col_stride == 1) { r = i / AS_DC; dd = i % AS_DC; } else { dd = i / AS_BM; r = i % AS_BM; }
@@ -100,7 +107,7 @@ __device__ __forceinline__ void assign_chunk(const float* __restrict__ x, const 
                 float er[4] = {ev.x, ev.y, ev.z, ev.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    if (c0 == 0) xx[i] = fmaf(xr[i], xr[i], xx[i]);
+                    if (c0 == c_lo) xx[i] = fmaf(xr[i], xr[i], xx[i]);      // same summation order as assign_chunk
 #pragma unroll
                     for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xr[i], er[j], acc[i][j]);
                 }
@@ -110,7 +117,7 @@ __device__ __forceinline__ void assign_chunk(const float* __restrict__ x, const 
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             int k = c0 + tx * 4 + j;
-            if (k < K) {
+            if (k < K && k < c_hi) {
                 float e2 = ee[k];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -120,7 +127,6 @@ __device__ __forceinline__ void assign_chunk(const float* __restrict__ x, const 
             }
         }
     }
-    // lexicographic (dist, k) min across the 16 code-lanes that share a row group
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         float b = best[i];
@@ -132,8 +138,23 @@ __device__ __forceinline__ void assign_chunk(const float* __restrict__ x, const 
             if (ob < b || (ob == b && obk < bk)) { b = ob; bk = obk; }
         }
         int r = ty * 4 + i;
-        if (tx == 0 && row_id[r] >= 0) embed_ind[row_id[r]] = (int64_t)bk;
+        if (tx == 0 && row_id[r] >= 0) {
+            if (embed_ind) embed_ind[row_id[r]] = (int64_t)bk;
+            if (part) part[(size_t)(n0 + r) * part_stride] = dist_key(b, bk);
+        }
     }
+}
+__device__ __forceinline__ void assign_chunk(const float* __restrict__ x, const RowLayout& L, int D, int K,
+                                             const float* __restrict__ cbT, const float* __restrict__ ee,
+                                             int64_t* __restrict__ embed_ind, const int* __restrict__ row_list,
+                                             int64_t total, int64_t n0) {
+    assign_core(x, L, D, K, cbT, ee, row_list, total, n0, 0, K, embed_ind, nullptr, 0);
+}
+__device__ __forceinline__ void assign_part(const float* __restrict__ x, const RowLayout& L, int D, int K,
+                                            const float* __restrict__ cbT, const float* __restrict__ ee,
+                                            const int* __restrict__ row_list, int64_t total, int64_t n0, int c_lo, int c_hi,
+                                            unsigned long long* __restrict__ part, int part_stride) {
+    assign_core(x, L, D, K, cbT, ee, row_list, total, n0, c_lo, c_hi, nullptr, part, part_stride);
 }
 
 __global__ void __launch_bounds__(AS_THREADS)

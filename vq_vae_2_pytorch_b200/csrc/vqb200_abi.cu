@@ -129,7 +129,7 @@ int forward_impl(const float* d_x, const RowLayout& L, int dim, int n_embed, con
     }
     if (zero_first) {
         // loss accumulator, flagged-row counter, tickets + the rows-per-code counters behind them
-        if (!header_zeroed) VQ_CUDA(cudaMemsetAsync(sc.diff_acc, 0, 256 + align_up((size_t)n_embed * 4, 256), st));
+        if (!header_zeroed) VQ_CUDA(cudaMemsetAsync(sc.diff_acc, 0, scratch_header_bytes(n_embed), st));
     } else if (use_tc) {
         VQ_CUDA(cudaMemsetAsync(sc.flagged_count, 0, sizeof(int), st));
     }
@@ -156,9 +156,9 @@ int forward_impl(const float* d_x, const RowLayout& L, int dim, int n_embed, con
                                        counts, dbg_scores, st, prof, nsplit, nullptr, (nchw && stats_kernel) ? d_x_dense : nullptr);
             g_launches.fetch_add(wide ? wide_launches : 1ull);
             if (rc) return cuda_fail(cudaGetLastError());
-            VQ_CUDA(launch_pdl(k_fixup, dim3(sms), dim3(AS_THREADS), gsmem, st, d_x, L, dim, n_embed, cb.cbT, cb.ee, d_ind,
+            VQ_CUDA(launch_pdl(k_fixup, dim3(2 * sms), dim3(AS_THREADS), gsmem, st, d_x, L, dim, n_embed, cb.cbT, cb.ee, d_ind,
                                d_quantize, d_diff ? sc.diff_acc : nullptr, sums, counts, sc.flagged_rows, sc.flagged_count,
-                               want_gather ? 1 : 0, fin_diff, inv, sc.ticket));
+                               want_gather ? 1 : 0, fin_diff, inv, sc.ticket, sc.fix_partial, sc.fix_tickets));
             g_launches.fetch_add(1);
             finalized = true;
         } else {

@@ -249,7 +249,7 @@ class Quantize(nn.Module):
     # the two nearest codes are almost equidistant (e.g. N(0,1) inputs against a random codebook); uncertified rows
     # cost an exact fp32 re-score.  The number of re-scored rows of a call is read back asynchronously (no sync) and
     # decides the precision of later calls.  Either way the returned indices are the exact arg-min.
-    FLAG_SWITCH_FRACTION = 3e-3
+    FLAG_SWITCH_FRACTION = 1e-2               # (the fix-up of <= 1 % of the rows costs less than the split filter's extra MMAs)
     SPLIT_COOLDOWN_CALLS = 64
     FLAG_SAMPLE_EVERY = 8                     # bf16-mode calls between two read-backs of the counter
 
