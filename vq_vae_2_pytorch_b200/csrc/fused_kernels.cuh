@@ -244,7 +244,8 @@ __global__ void __launch_bounds__(256) k_ema64(const float* __restrict__ stats, 
 // diff = acc * inv_count.  Exits after the ticket when no row was flagged.
 //   many rows : one work item = one 64-row chunk against the whole codebook (assign_chunk); 4 CTAs per SM keep the loads of
 //               several chunks in flight (one CTA per SM ran at 5 TFLOP/s).
-//   few rows  (<= FIX_CAP rows and fewer chunks than 2 x CTAs, codebooks of 2 .. FIX_KB 64-code blocks): one work item = one
+//   few rows  (fewer chunks than half the CTAs -- measured: beyond that the 8x re-read of the x tiles costs more than the
+//               idle SMs --, codebooks of 2 .. FIX_KB 64-code blocks): one work item = one
 //               chunk against ONE 64-code block; the partial arg-mins are 64-bit (distance, code) keys whose integer
 //               minimum is the reference's arg-min; the last block of a chunk (per-chunk ticket) merges them and produces the
 //               chunk's outputs.  492 flagged rows (split-bf16 filter on N(0,1) rows) used to occupy 8 CTAs for ~100 us.
@@ -266,7 +267,7 @@ k_fixup(const float* __restrict__ x, RowLayout L, int D, int K, const float* __r
     const int64_t total = (int64_t)(*row_count);
     const int64_t chunks = (total + AS_BM - 1) / AS_BM;
     const int KB = (K + AS_BN - 1) / AS_BN;
-    const bool split = fix_partial && fix_tickets && KB > 1 && KB <= FIX_KB && total <= FIX_CAP && chunks < 2 * (int64_t)gridDim.x;
+    const bool split = fix_partial && fix_tickets && KB > 1 && KB <= FIX_KB && total <= FIX_CAP && 2 * chunks < (int64_t)gridDim.x;
     const int64_t items = split ? chunks * KB : chunks;
     float acc = 0.f;
     for (int64_t w = blockIdx.x; w < items; w += gridDim.x) {
