@@ -380,6 +380,20 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # several ranks share one host: keep this rank's threads -- and with them its pinned buffers (first touch) -- on the CPUs
+        # / NUMA node next to its GPU, so that the e2e copies do not cross the socket interconnect
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByUUID(str(torch.cuda.get_device_properties(dev).uuid).encode()
+                                            if hasattr(torch.cuda.get_device_properties(dev), "uuid") else b""))
+        except Exception:
+            try:
+                import pynvml
+                pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+            except Exception:
+                pass
+    if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     lib = _native.load()
