@@ -260,7 +260,7 @@ class Quantize(nn.Module):
             return _native.ENGINE_AUTO
         f = self._filter
         pend = f["pending"]
-        if torch.cuda.is_current_stream_capturing():      # CUDA-graph capture: no event queries, keep the filter as it is
+        if pend is not None and torch.cuda.is_current_stream_capturing():   # CUDA-graph capture: no event queries, keep the filter as it is
             return _native.ENGINE_TCGEN05_BF16 if f["mode"] == "bf16" else _native.ENGINE_TCGEN05
         if pend is not None and pend[0].query():
             _, host_count, rows, mode_used = pend
@@ -279,10 +279,10 @@ class Quantize(nn.Module):
         f = self._filter
         if eng != _native.ENGINE_TCGEN05_BF16 or self.engine != "auto" or f["pending"] is not None or n == 0:
             return
-        if torch.cuda.is_current_stream_capturing():      # no pinned read-back / event inside a captured forward
-            return
         f["calls"] = f.get("calls", 0) + 1
         if f["calls"] % self.FLAG_SAMPLE_EVERY != 1:
+            return
+        if torch.cuda.is_current_stream_capturing():      # no pinned read-back / event inside a captured forward
             return
         host = ws.get("flag_host")
         if host is None:
@@ -332,6 +332,8 @@ class Quantize(nn.Module):
                 self._check_peer_timeout(peer)
                 peer["step"] += 1
                 peer["parity"] = peer["step"] & 1
+        bufs = self._buffers                  # (nn.Module.__getattr__ costs ~0.3 us per access)
+        embed, cluster_size, embed_avg = bufs["embed"], bufs["cluster_size"], bufs["embed_avg"]
         x_run, q_run, lay_run, x_dense = x, quantize, lay, None
         strided = n > 0 and (col != 1 or (n > 1 and row != self.dim))
         if strided and self.engine != "simt":
@@ -356,16 +358,16 @@ class Quantize(nn.Module):
         if peer is not None:                  # forward + statistics pushed to every rank (vqvae.py:43-56,58-59,72-73)
             par = peer["parity"]
             _native.check(lib.vqb200_quantize_step_peers(
-                x_run.data_ptr(), n, self.dim, self.n_embed, rpi, img, row, col, self.embed.data_ptr(),
-                self.cluster_size.data_ptr(), self.embed_avg.data_ptr(), image.data_ptr(),
+                x_run.data_ptr(), n, self.dim, self.n_embed, rpi, img, row, col, embed.data_ptr(),
+                cluster_size.data_ptr(), embed_avg.data_ptr(), image.data_ptr(),
                 q_run.data_ptr() if q_run is not None else None, ind.data_ptr(), diff.data_ptr(), ws["scratch"].data_ptr(),
                 x_dense.data_ptr() if x_dense is not None else None, eng, float(self.decay), float(1 - self.decay), float(self.eps),
                 peer["push_dst"][par], peer["recv"][par], peer["err_ptr"][par], peer["rank"],
                 peer["world"], peer["step"], stream), "vqb200_quantize_step_peers")
         else:
             _native.check(lib.vqb200_quantize_step(
-                x_run.data_ptr(), n, self.dim, self.n_embed, rpi, img, row, col, self.embed.data_ptr(),
-                self.cluster_size.data_ptr(), self.embed_avg.data_ptr(), image.data_ptr(),
+                x_run.data_ptr(), n, self.dim, self.n_embed, rpi, img, row, col, embed.data_ptr(),
+                cluster_size.data_ptr(), embed_avg.data_ptr(), image.data_ptr(),
                 q_run.data_ptr() if q_run is not None else None, ind.data_ptr(), diff.data_ptr(),
                 stats.data_ptr() if stats is not None else None, ws["scratch"].data_ptr(),
                 x_dense.data_ptr() if x_dense is not None else None, eng, 1 if fused_ema else 0, float(self.decay), float(1 - self.decay), float(self.eps), stream),
@@ -377,8 +379,8 @@ class Quantize(nn.Module):
         if self.training and not fused_ema and peer is None:      # multi-rank without peer memory: one packed NCCL all-reduce
             dist_fn.all_reduce(stats[: self.n_embed * (self.dim + 1)])  # vqvae.py:58-59 (one packed call)
             _native.check(lib.vqb200_ema_update(
-                stats.data_ptr(), self.cluster_size.data_ptr(), self.embed_avg.data_ptr(),
-                self.embed.data_ptr(), self.dim, self.n_embed, float(self.decay), float(1 - self.decay),
+                stats.data_ptr(), cluster_size.data_ptr(), embed_avg.data_ptr(),
+                embed.data_ptr(), self.dim, self.n_embed, float(self.decay), float(1 - self.decay),
                 float(self.eps), None, stream), "vqb200_ema_update")                          # vqvae.py:61-70
         return quantize, diff, ind, image, lay
 
