@@ -329,6 +329,11 @@ class Quantize(nn.Module):
         if world > 1:
             peer = self._peer_workspace(ws, dev)
             if peer is not None:              # this step's statistics go straight into every rank's receive slot
+                if torch.cuda.is_current_stream_capturing():
+                    # the exchange tags every word with the step number, a kernel ARGUMENT: a replayed graph would resend
+                    # old tags and its peers would wait for ever (until the 2-s time-out)
+                    raise RuntimeError("Quantize: a multi-rank training forward cannot be captured in a CUDA graph "
+                                       "(set VQB200_NO_P2P=1 to use the capturable NCCL all-reduce path)")
                 self._check_peer_timeout(peer)
                 peer["step"] += 1
                 peer["parity"] = peer["step"] & 1
