@@ -115,18 +115,22 @@ int vqb200_ema_update_p2p(const void* const* h_stats_ptrs, void* const* h_flag_p
 /* Multi-rank training forward in ONE call, with the exchange that replaces dist_fn.all_reduce (vqvae.py:58-59 ->
  * distributed/distributed.py:64-72) fused into the EMA kernel over peer memory; dim 64 / n_embed 256 or 512.  Forward as
  * vqb200_quantize_step, then ONE kernel folds the per-CTA statistics tables, stores every word of this rank's packed
- * statistics [K*64 sums | K counts] as an 8-byte {value, step} pair into h_push_dst[r] = rank r's receive slot for THIS rank
- * (peer-mapped pointers, 8-byte aligned, (K*65) pairs; r == rank: the local slot), polls the words it needs in its LOCAL
- * receive slots h_recv[0..world) until their tag equals `step` (flag-in-data: no fence, no flag array, no NCCL call, no
- * remote load), adds them in rank order (bit-identical replicas) and applies vqvae.py:61-70.  Slots are double-buffered by
- * the caller on the parity of `step` (1, 2, ...).  A word that does not arrive within 2 s: d_err[0] = step, d_err[1] = rank
- * (d_err: 16 words of local device memory, zero-initialised).                                                            */
+ * statistics [K*64 sums | K counts] as an 8-byte {value, step} pair into rank r's receive slot for THIS rank (peer-mapped
+ * pointers, 8-byte aligned, K*65 pairs each; r == rank: the local slot), polls the words it needs in its LOCAL receive slots
+ * until their tag equals `step` (flag-in-data: no fence, no flag array, no NCCL call, no remote load), adds them in rank
+ * order (bit-identical replicas) and applies vqvae.py:61-70.
+ *   h_push_dst / h_recv : [2][world] pointers, parity-major -- the slots are double-buffered on the parity of the step;
+ *   d_step_counter      : one local device word, zero-initialised once, owned by the kernel: step = counter + 1, advanced
+ *                         by the last block -- the tag never passes through the host, so the call sequence can be replayed
+ *                         from a CUDA graph and a host-side exception cannot put one rank out of step;
+ *   d_err               : 16 words of local device memory, zero-initialised; a word that does not arrive within 2 s makes
+ *                         the kernel record d_err[0] = step, d_err[1] = missing rank and carry on.                          */
 int vqb200_quantize_step_peers(const float* d_x, int64_t n_rows, int32_t dim, int32_t n_embed, int64_t rows_per_image,
                                int64_t image_stride, int64_t row_stride, int64_t col_stride, float* d_embed,
                                float* d_cluster_size, float* d_embed_avg, void* d_codebook, float* d_quantize,
                                int64_t* d_embed_ind, float* d_diff, void* d_scratch, float* d_x_dense, int32_t engine,
                                float decay, float one_minus_decay, float eps, void* const* h_push_dst,
-                               const void* const* h_recv, void* d_err, int32_t rank, int32_t world, uint32_t step,
+                               const void* const* h_recv, void* d_err, void* d_step_counter, int32_t rank, int32_t world,
                                void* stream);
 
 /* The module's whole forward in one call (fewer host round trips per step):

@@ -82,7 +82,10 @@ def test_step_peers_with_world_1_equals_single_rank_step(K):
     b.load_state_dict(a.state_dict())
     n = K * (D + 1)
     n_al = (n + 63) // 64 * 64
-    buf = torch.zeros(2 * 2 * n_al + 2 * 64, device=DEV)         # [slot parity 0 | slot parity 1 | err 0 | err 1], 8-byte pairs
+    buf = torch.zeros(2 * 2 * n_al + 64, device=DEV)             # [slot parity 0 | slot parity 1 | err (2) .. step counter (+32)]
+    err = buf[4 * n_al: 4 * n_al + 64]
+    slots = [buf[par * 2 * n_al: par * 2 * n_al + 2 * n] for par in (0, 1)]
+    dst = (C.c_void_p * 2)(*[t.data_ptr() for t in slots]); recv = (C.c_void_p * 2)(*[t.data_ptr() for t in slots])
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     from vq_vae_2_pytorch_b200 import row_layout
     for step in range(1, 6):
@@ -90,22 +93,20 @@ def test_step_peers_with_world_1_equals_single_rank_step(K):
         x = torch.randn(2, D, 32, 32, device=DEV, generator=g).permute(0, 2, 3, 1) if step % 2 else torch.randn(128 * 29 + 3, D, device=DEV, generator=g)
         qa, da, ia = a(x)                                        # single-rank step (fold fused into the EMA kernel as well)
         nr, rpi, img, row, col = row_layout(x)
-        par = step & 1
-        slot = buf[par * 2 * n_al: par * 2 * n_al + 2 * n]
-        err = buf[4 * n_al + 64 * par: 4 * n_al + 64 * par + 64]
+        slot = slots[step & 1]                                   # the kernel's own counter picks the parity: step = counter + 1
         ws = b._workspace(x.device, nr)
         quant = torch.empty_strided(x.shape, x.stride(), device=DEV)
         ind = torch.empty(x.shape[:-1], dtype=torch.int64, device=DEV); diff = torch.empty((), device=DEV)
-        dst = (C.c_void_p * 1)(slot.data_ptr()); recv = (C.c_void_p * 1)(slot.data_ptr())
         _native.check(lib.vqb200_quantize_step_peers(x.data_ptr(), nr, D, K, rpi, img, row, col, b.embed.data_ptr(),
                                                      b.cluster_size.data_ptr(), b.embed_avg.data_ptr(), ws["image"].data_ptr(),
                                                      quant.data_ptr(), ind.data_ptr(), diff.data_ptr(), ws["scratch"].data_ptr(), None, 0,
-                                                     0.99, float(1 - 0.99), 1e-5, dst, recv, err.data_ptr(), 0, 1, step, st), "step_peers")
+                                                     0.99, float(1 - 0.99), 1e-5, dst, recv, err.data_ptr(), err[32:].data_ptr(), 0, 1, st), "step_peers")
         torch.cuda.synchronize()
         assert torch.equal(ind, ia) and torch.equal(quant, qa) and abs(float(diff) - float(da)) <= 1e-6 * abs(float(da))
         pairs = slot.view(n, 2)
         assert bool((pairs[:, 1].view(torch.int32) == step).all())          # every word carries the step tag
         assert int(err[:1].view(torch.int32)) == 0                          # no time-out recorded
+        assert int(err[32:33].view(torch.int32)) == step                    # the device-side exchange counter advanced
         vals = pairs[:, 0]
         assert abs(float(vals[K * D: K * D + K].sum()) - nr) < 0.5          # the pushed counts
         assert torch.allclose(vals[: K * D].view(K, D).sum(0), x.reshape(-1, D).sum(0), rtol=1e-4, atol=1e-2)

@@ -51,18 +51,17 @@ def split(i, step):
 
 nw = K * (D + 1)
 nw_al = (nw + 63) // 64 * 64
-pbuf = torch.zeros(2 * 2 * nw_al + 2 * 64, device=dev)
+pbuf = torch.zeros(2 * 2 * nw_al + 64, device=dev)
 
 
 def peers_w1(i, step):
-    par = step & 1
-    slot = pbuf.data_ptr() + 4 * par * 2 * nw_al
-    err = pbuf.data_ptr() + 4 * (4 * nw_al + 64 * par)
-    dst = (C.c_void_p * 1)(slot); rc = (C.c_void_p * 1)(slot)
+    slot = [pbuf.data_ptr() + 4 * par * 2 * nw_al for par in (0, 1)]
+    err = pbuf.data_ptr() + 4 * (4 * nw_al)
+    dst = (C.c_void_p * 2)(*slot); rc = (C.c_void_p * 2)(*slot)
     _native.check(lib.vqb200_quantize_step_peers(xs[i % 3].data_ptr(), N, D, K, N, 0, D, 1, q.embed.data_ptr(), q.cluster_size.data_ptr(),
                                                  q.embed_avg.data_ptr(), ws["image"].data_ptr(), quant.data_ptr(), ind.data_ptr(),
                                                  diff.data_ptr(), ws["scratch"].data_ptr(), None, eng, 0.99, float(1 - 0.99), 1e-5,
-                                                 dst, rc, C.c_void_p(err), 0, 1, step, st), "peers")
+                                                 dst, rc, C.c_void_p(err), C.c_void_p(err + 128), 0, 1, st), "peers")
 
 
 step_no = 0

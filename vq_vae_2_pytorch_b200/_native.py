@@ -35,7 +35,7 @@ SIGNATURES = {
                                        _i32, _i32, _f32, _f32, _f32, _p]),
     "vqb200_ema_update_p2p": (C.c_int, [_p, _p, _i32, _i32, C.c_uint32, _p, _p, _p, _i32, _i32, _f32, _f32, _f32, _p, _p]),
     "vqb200_quantize_step_peers": (C.c_int, [_p, _i64, _i32, _i32, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i32,
-                                             _f32, _f32, _f32, _p, _p, _p, _i32, _i32, C.c_uint32, _p]),
+                                             _f32, _f32, _f32, _p, _p, _p, _p, _i32, _i32, _p]),
     "vqb200_repack_rows": (C.c_int, [_p, _p, _i64, _i32, _i64, _i64, _i64, _i64, _i32, _p]),
     "vqb200_embed_code": (C.c_int, [_p, _i64, _p, _i32, _i32, _p, _p, _p]),
     "vqb200_pack_indices": (C.c_int, [_p, _i64, _i32, _i32, _p, _p, _p]),

@@ -364,11 +364,12 @@ namespace vqb200 {
 // ------------------------------------------------------------------------------------------------
 constexpr int EF_CODES = 4, EF_THREADS = 1024;
 struct PeerFold {
-    uint2* push_dst[P2P_MAX_RANKS];            // rank r's receive slot for MY statistics: [K*64 sums | K counts] x {value, step}
-    const uint2* recv[P2P_MAX_RANKS];          // my local receive slots, one per rank
+    uint2* push_dst[2][P2P_MAX_RANKS];         // [step parity][rank r]: r's receive slot for MY statistics: [K*64 sums | K counts] x {value, step}
+    const uint2* recv[2][P2P_MAX_RANKS];       // [step parity][rank]: my local receive slots, one per rank
     unsigned int* err;                         // 2 words: (step, rank) of a time-out
+    unsigned int* step_counter;                // local device word: number of exchanges completed so far (the step tag lives on the
+                                               // device, so a captured graph can be replayed and the host cannot fall out of step)
     int rank, world;
-    unsigned int step;
 };
 
 __device__ __forceinline__ void st_ll(uint2* p, float v, unsigned int tag) {
@@ -380,25 +381,26 @@ __device__ __forceinline__ uint2 ld_ll(const uint2* p) {
     return v;
 }
 // rank-ordered sum of word i of every rank's local slot, each word polled until its tag is `step`
-__device__ __forceinline__ float ll_gather(const PeerFold& peers, size_t i) {
+__device__ __forceinline__ float ll_gather(const PeerFold& peers, unsigned int step, size_t i) {
+    const int par = (int)(step & 1u);
     uint2 v[P2P_MAX_RANKS];
     unsigned int pending = 0;
 #pragma unroll
     for (int r = 0; r < P2P_MAX_RANKS; ++r)
-        if (r < peers.world) { v[r] = ld_ll(peers.recv[r] + i); pending |= (v[r].y != peers.step) ? (1u << r) : 0u; }
+        if (r < peers.world) { v[r] = ld_ll(peers.recv[par][r] + i); pending |= (v[r].y != step) ? (1u << r) : 0u; }
     unsigned long long t0 = 0;
     unsigned int spins = 0;
     while (pending) {
 #pragma unroll
         for (int r = 0; r < P2P_MAX_RANKS; ++r)
-            if (pending & (1u << r)) { v[r] = ld_ll(peers.recv[r] + i); if (v[r].y == peers.step) pending &= ~(1u << r); }
+            if (pending & (1u << r)) { v[r] = ld_ll(peers.recv[par][r] + i); if (v[r].y == step) pending &= ~(1u << r); }
         if (pending && (++spins & 255u) == 0) {
             unsigned long long now;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
             if (t0 == 0) t0 = now;
             else if (now - t0 > P2P_TIMEOUT_NS) {
                 peers.err[1] = (unsigned int)(__ffs(pending) - 1);
-                atomicExch(peers.err, peers.step);
+                atomicExch(peers.err, step);
                 break;
             }
         }
@@ -429,6 +431,9 @@ __global__ void __launch_bounds__(EF_THREADS) k_ema64f(const float* __restrict__
     pdl_trigger();
     const int k0 = blockIdx.x * EF_CODES, tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
     const int n_parts = (int)*n_parts_ptr, nstat = K * 65;
+    // exchange number of this launch (1, 2, ...): every block reads the counter before the last block (ticket) advances it
+    unsigned int step = 0;
+    if constexpr (P2P) step = *reinterpret_cast<volatile unsigned int*>(peers.step_counter) + 1u;
 #ifdef VQB200_P2P_TRACE
     unsigned long long tr[5] = {0, 0, 0, 0, 0};
     auto stamp = [&](int i) { if (P2P && tid == 0 && blockIdx.x == gridDim.x - 1) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr[i])); };
@@ -466,18 +471,18 @@ __global__ void __launch_bounds__(EF_THREADS) k_ema64f(const float* __restrict__
         if (tid < 256) {
 #pragma unroll
             for (int r = 0; r < P2P_MAX_RANKS; ++r)
-                if (r < peers.world) st_ll(peers.push_dst[r] + (size_t)k0 * 64 + tid, tot, peers.step);
+                if (r < peers.world) st_ll(peers.push_dst[step & 1u][r] + (size_t)k0 * 64 + tid, tot, step);
         } else if (tid < 256 + EF_CODES) {
             const float c = (float)code_counts[k0 + tid - 256];
 #pragma unroll
             for (int r = 0; r < P2P_MAX_RANKS; ++r)
-                if (r < peers.world) st_ll(peers.push_dst[r] + (size_t)K * 64 + k0 + tid - 256, c, peers.step);
+                if (r < peers.world) st_ll(peers.push_dst[step & 1u][r] + (size_t)K * 64 + k0 + tid - 256, c, step);
         }
 #ifdef VQB200_P2P_TRACE
         stamp(2);
 #endif
-        if (tid < 256) tot = ll_gather(peers, (size_t)k0 * 64 + tid);
-        if (tid >= 512 && tid - 512 < K) cnt_s[tid - 512] = ll_gather(peers, (size_t)K * 64 + tid - 512);
+        if (tid < 256) tot = ll_gather(peers, step, (size_t)k0 * 64 + tid);
+        if (tid >= 512 && tid - 512 < K) cnt_s[tid - 512] = ll_gather(peers, step, (size_t)K * 64 + tid - 512);
 #ifdef VQB200_P2P_TRACE
         __syncthreads();
         stamp(3);
@@ -532,7 +537,10 @@ __global__ void __launch_bounds__(EF_THREADS) k_ema64f(const float* __restrict__
     __syncthreads();
     if (last_s) {
         if (tid < K) cluster_size[tid] = cs_new;
-        if (tid == 0) *ticket = 0u;                             // clean for the next launch
+        if (tid == 0) {
+            *ticket = 0u;                                       // clean for the next launch
+            if constexpr (P2P) *peers.step_counter = step;
+        }
     }
 #ifdef VQB200_P2P_TRACE
     if constexpr (P2P) {
@@ -540,7 +548,7 @@ __global__ void __launch_bounds__(EF_THREADS) k_ema64f(const float* __restrict__
         if (tid == 0 && blockIdx.x == gridDim.x - 1) {          // (kernel start, fold, push, wait, rest) of the last block, ns
             unsigned int* t = peers.err + 4;
             t[0] = (unsigned int)(tr[0] & 0xffffffffu); t[1] = (unsigned int)(tr[1] - tr[0]); t[2] = (unsigned int)(tr[2] - tr[1]);
-            t[3] = (unsigned int)(tr[3] - tr[2]); t[4] = (unsigned int)(tr[4] - tr[3]); t[5] = peers.step;
+            t[3] = (unsigned int)(tr[3] - tr[2]); t[4] = (unsigned int)(tr[4] - tr[3]); t[5] = step;
         }
     }
 #endif

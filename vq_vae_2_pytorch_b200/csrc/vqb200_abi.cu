@@ -380,24 +380,29 @@ int vqb200_quantize_step_peers(const float* d_x, int64_t n_rows, int32_t dim, in
                                float* d_cluster_size, float* d_embed_avg, void* d_codebook, float* d_quantize,
                                int64_t* d_embed_ind, float* d_diff, void* d_scratch, float* d_x_dense, int32_t engine,
                                float decay, float one_minus_decay, float eps, void* const* h_push_dst,
-                               const void* const* h_recv, void* d_err, int32_t rank, int32_t world, uint32_t step, void* stream) {
+                               const void* const* h_recv, void* d_err, void* d_step_counter, int32_t rank, int32_t world,
+                               void* stream) {
     if (!d_embed || !d_cluster_size || !d_embed_avg || !d_codebook || !d_scratch || dim <= 0 || n_embed <= 0) return VQB200_EINVAL;
     if (n_rows < 0 || (n_rows > 0 && (!d_x || !d_embed_ind))) return VQB200_EINVAL;
-    if (!h_push_dst || !h_recv || !d_err) return VQB200_EINVAL;
-    if (world < 1 || world > P2P_MAX_RANKS || rank < 0 || rank >= world || step == 0) return VQB200_EINVAL;
+    if (!h_push_dst || !h_recv || !d_err || !d_step_counter) return VQB200_EINVAL;
+    if (world < 1 || world > P2P_MAX_RANKS || rank < 0 || rank >= world) return VQB200_EINVAL;
     if (n_rows > (int64_t)INT32_MAX) return VQB200_EUNSUPPORTED;
     if (engine < VQB200_ENGINE_AUTO || engine > VQB200_ENGINE_TCGEN05_TF32) return VQB200_EINVAL;
     if (n_rows > 0 && !layout_ok(n_rows, dim, rows_per_image, image_stride, row_stride, col_stride)) return VQB200_EUNSUPPORTED;
     if (!tc_shape_ok(dim, n_embed)) return VQB200_EUNSUPPORTED;      // the fold + EMA kernel: dim 64, n_embed 256 / 512
     PeerFold pf{};
-    for (int r = 0; r < world; ++r) {
-        if (!h_push_dst[r] || !h_recv[r]) return VQB200_EINVAL;
-        if ((reinterpret_cast<uintptr_t>(h_push_dst[r]) | reinterpret_cast<uintptr_t>(h_recv[r])) & 7u) return VQB200_EINVAL;
-        pf.push_dst[r] = static_cast<uint2*>(h_push_dst[r]);
-        pf.recv[r] = static_cast<const uint2*>(h_recv[r]);
-    }
+    for (int par = 0; par < 2; ++par)
+        for (int r = 0; r < world; ++r) {           // h_push_dst / h_recv: [2 parities][world] pointers, parity-major
+            void* dst = h_push_dst[par * world + r];
+            const void* rcv = h_recv[par * world + r];
+            if (!dst || !rcv) return VQB200_EINVAL;
+            if ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(rcv)) & 7u) return VQB200_EINVAL;
+            pf.push_dst[par][r] = static_cast<uint2*>(dst);
+            pf.recv[par][r] = static_cast<const uint2*>(rcv);
+        }
     pf.err = static_cast<unsigned int*>(d_err);
-    pf.rank = rank; pf.world = world; pf.step = step;
+    pf.step_counter = static_cast<unsigned int*>(d_step_counter);
+    pf.rank = rank; pf.world = world;
     RowLayout L{n_rows, rows_per_image > 0 ? rows_per_image : 1, image_stride, row_stride, col_stride};
     ForwardScratch sc = scratch_view(d_scratch, n_rows, dim, n_embed);
     int rc = forward_impl(d_x, L, dim, n_embed, d_codebook, d_quantize, d_embed_ind, d_diff, sc.stat_partials, d_scratch, engine,

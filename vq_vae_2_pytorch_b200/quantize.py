@@ -201,21 +201,22 @@ class Quantize(nn.Module):
                 n_al = (n + 63) // 64 * 64
                 slot = 2 * n_al                      # floats per receive slot: every word travels as an 8-byte {value, step} pair
                 slots = world * slot
-                total = 2 * slots + 2 * 64           # [slots parity 0 | slots parity 1 | time-out / trace words 0 | 1]
+                total = 2 * slots + 64               # [slots parity 0 | slots parity 1 | time-out (2) / trace words ... step counter (+32)]
                 buf = symm.empty(total, dtype=torch.float32, device=dev)
                 hdl = symm.rendezvous(buf, dist.group.WORLD)
                 buf.zero_()
                 torch.cuda.synchronize(dev)
                 hdl.barrier()
                 ptrs = [int(p) for p in hdl.buffer_ptrs]
-                mk = lambda vals: (C.c_void_p * world)(*vals)
-                peer = {"buf": buf, "hdl": hdl, "rank": rank, "world": world, "step": 0, "parity": 0, "checked": 0,
-                        # where MY statistics go on rank r (peer-mapped) ...
-                        "push_dst": [mk([p + 4 * (par * slots + rank * slot) for p in ptrs]) for par in (0, 1)],
+                mk = lambda vals: (C.c_void_p * (2 * world))(*vals)
+                peer = {"buf": buf, "hdl": hdl, "rank": rank, "world": world, "calls": 0, "checked": 0,
+                        # [parity][rank r]: where MY statistics go on rank r (peer-mapped) ...
+                        "push_dst": mk([p + 4 * (par * slots + rank * slot) for par in (0, 1) for p in ptrs]),
                         # ... and what the kernel polls and sums: my LOCAL slots, one per rank
-                        "recv": [mk([ptrs[rank] + 4 * (par * slots + r * slot) for r in range(world)]) for par in (0, 1)],
-                        "err_ptr": [ptrs[rank] + 4 * (2 * slots + 64 * par) for par in (0, 1)],
-                        "err": [buf[2 * slots + 64 * par: 2 * slots + 64 * par + 2].view(torch.int32) for par in (0, 1)]}
+                        "recv": mk([ptrs[rank] + 4 * (par * slots + r * slot) for par in (0, 1) for r in range(world)]),
+                        "err_ptr": ptrs[rank] + 4 * (2 * slots),            # 16 words: time-out record (+ trace words)
+                        "step_ptr": ptrs[rank] + 4 * (2 * slots + 32),      # the kernel's own exchange counter
+                        "err": buf[2 * slots: 2 * slots + 2].view(torch.int32)}
             except Exception as exc:  # no peer access / unsupported build: keep the NCCL path
                 peer = None
                 self._peer_error = repr(exc)
@@ -236,10 +237,10 @@ class Quantize(nn.Module):
             if int(pend[1][0]) != 0:
                 raise RuntimeError(f"Quantize: rank {int(pend[1][1])} did not publish its codebook statistics for step "
                                    f"{int(pend[1][0])} within 2 s (fused peer-memory exchange); the replicas are out of sync")
-        if pend is None and peer["step"] - peer["checked"] >= 64 and not torch.cuda.is_current_stream_capturing():
-            peer["checked"] = peer["step"]
+        if pend is None and peer["calls"] - peer["checked"] >= 64 and not torch.cuda.is_current_stream_capturing():
+            peer["checked"] = peer["calls"]
             host = peer.setdefault("err_host", torch.zeros(2, dtype=torch.int32).pin_memory())
-            host.copy_(peer["err"][peer["parity"]], non_blocking=True)
+            host.copy_(peer["err"], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record()
             peer["err_pending"] = (ev, host)
@@ -329,14 +330,8 @@ class Quantize(nn.Module):
         if world > 1:
             peer = self._peer_workspace(ws, dev)
             if peer is not None:              # this step's statistics go straight into every rank's receive slot
-                if torch.cuda.is_current_stream_capturing():
-                    # the exchange tags every word with the step number, a kernel ARGUMENT: a replayed graph would resend
-                    # old tags and its peers would wait for ever (until the 2-s time-out)
-                    raise RuntimeError("Quantize: a multi-rank training forward cannot be captured in a CUDA graph "
-                                       "(set VQB200_NO_P2P=1 to use the capturable NCCL all-reduce path)")
                 self._check_peer_timeout(peer)
-                peer["step"] += 1
-                peer["parity"] = peer["step"] & 1
+                peer["calls"] += 1            # (the step tag of the exchange lives on the device: nothing here can fall out of step)
         bufs = self._buffers                  # (nn.Module.__getattr__ costs ~0.3 us per access)
         embed, cluster_size, embed_avg = bufs["embed"], bufs["cluster_size"], bufs["embed_avg"]
         x_run, q_run, lay_run, x_dense = x, quantize, lay, None
@@ -361,14 +356,13 @@ class Quantize(nn.Module):
         # the codebook image is re-derived from `embed` on every call: external writes to the buffer
         # (load_state_dict, .data.copy_, DDP buffer broadcast) can never leave it stale
         if peer is not None:                  # forward + statistics pushed to every rank (vqvae.py:43-56,58-59,72-73)
-            par = peer["parity"]
             _native.check(lib.vqb200_quantize_step_peers(
                 x_run.data_ptr(), n, self.dim, self.n_embed, rpi, img, row, col, embed.data_ptr(),
                 cluster_size.data_ptr(), embed_avg.data_ptr(), image.data_ptr(),
                 q_run.data_ptr() if q_run is not None else None, ind.data_ptr(), diff.data_ptr(), ws["scratch"].data_ptr(),
                 x_dense.data_ptr() if x_dense is not None else None, eng, float(self.decay), float(1 - self.decay), float(self.eps),
-                peer["push_dst"][par], peer["recv"][par], peer["err_ptr"][par], peer["rank"],
-                peer["world"], peer["step"], stream), "vqb200_quantize_step_peers")
+                peer["push_dst"], peer["recv"], peer["err_ptr"], peer["step_ptr"], peer["rank"], peer["world"], stream),
+                "vqb200_quantize_step_peers")
         else:
             _native.check(lib.vqb200_quantize_step(
                 x_run.data_ptr(), n, self.dim, self.n_embed, rpi, img, row, col, embed.data_ptr(),
