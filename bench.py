@@ -541,11 +541,10 @@ def main():
         hi = torch.empty(N_ROWS, dtype=torch.int64).pin_memory()
         hd = torch.empty(1).pin_memory()
         e_steps = max(5, min(steps, 20))
+        # through the host-buffer C ABI (pinned host in / out, copies inside the timed region, chunks overlapped)
+        ctx = C.c_void_p()
+        _native.check(lib.vqb200_host_ctx_create(N_ROWS, D, K, C.byref(ctx)), "host_ctx_create")
         if world == 1:
-            # through the host-buffer C ABI (pinned host in / out, copies inside the timed region, chunks overlapped)
-            ctx = C.c_void_p()
-            _native.check(lib.vqb200_host_ctx_create(N_ROWS, D, K, C.byref(ctx)), "host_ctx_create")
-
             def host_step(i):
                 _native.check(lib.vqb200_host_quantize(ctx, C.c_void_p(hx[i % 2].data_ptr()), N_ROWS, _native.ptr(q.embed),
                                                        _native.ptr(q.cluster_size), _native.ptr(q.embed_avg), 0.99,
@@ -553,15 +552,22 @@ def main():
                                                        C.c_void_p(hi.data_ptr()), C.c_void_p(hd.data_ptr()), eng), "host_quantize")
             api = "vqb200_host_quantize (C ABI, pinned host buffers, row chunks pipelined over three streams)"
         else:
-            # through the module (the call a user makes), so that the cross-rank exchange of vqvae.py:58-59 is inside
-            xdev = torch.empty(N_ROWS, D, device=dev)
+            # the data-parallel form of the same call: statistics left on the device, reduced where the reference calls
+            # dist_fn.all_reduce (vqvae.py:58-59), then the EMA of vqvae.py:61-70 -- all inside the timed region
+            stats = torch.zeros(lib.vqb200_stats_bytes(D, K) // 4, device=dev)
+            st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _native.check(lib.vqb200_host_ctx_set_stream(ctx, st), "host_ctx_set_stream")
 
             def host_step(i):
-                xdev.copy_(hx[i % 2], non_blocking=True)
-                qo, do, io = q(xdev)
-                hq.copy_(qo, non_blocking=True); hi.copy_(io, non_blocking=True); hd.copy_(do.reshape(1), non_blocking=True)
+                _native.check(lib.vqb200_host_quantize_stats(ctx, C.c_void_p(hx[i % 2].data_ptr()), N_ROWS, _native.ptr(q.embed),
+                                                             _native.ptr(stats), C.c_void_p(hq.data_ptr()),
+                                                             C.c_void_p(hi.data_ptr()), C.c_void_p(hd.data_ptr()), eng), "host_quantize_stats")
+                dist.all_reduce(stats[: K * (D + 1)])
+                _native.check(lib.vqb200_ema_update(_native.ptr(stats), _native.ptr(q.cluster_size), _native.ptr(q.embed_avg),
+                                                    _native.ptr(q.embed), D, K, 0.99, float(1 - 0.99), 1e-5, None, st), "ema_update")
                 torch.cuda.synchronize()
-            api = "Quantize.forward on a device copy of pinned host x (exchange across ranks included), results copied back to pinned host memory"
+            api = ("vqb200_host_quantize_stats (C ABI, pinned host buffers, row chunks pipelined over three streams) + one NCCL "
+                   "all-reduce of the packed statistics + vqb200_ema_update, per rank")
         for i in range(3):
             host_step(i)
         if world > 1:
@@ -570,9 +576,8 @@ def main():
         for i in range(e_steps):
             host_step(i)
         dt = time.perf_counter() - t0
-        if world == 1:
-            lib.vqb200_host_ctx_destroy(ctx)
-        else:
+        lib.vqb200_host_ctx_destroy(ctx)
+        if world > 1:
             t = torch.tensor([dt], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())

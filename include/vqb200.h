@@ -232,6 +232,12 @@ int  vqb200_host_quantize(vqb200_host_ctx* ctx, const float* h_x, int64_t n_rows
                           float* d_embed, float* d_cluster_size, float* d_embed_avg,
                           float decay, float one_minus_decay, float eps, int32_t training,
                           float* h_quantize, int64_t* h_embed_ind, float* h_diff, int32_t engine);
+/* Data-parallel form: the same pipelined forward, with the batch statistics of vqvae.py:55-56 left in the caller's
+ * DEVICE buffer d_stats (vqb200_stats_bytes) and NO EMA -- the caller reduces d_stats across ranks where the reference
+ * calls dist_fn.all_reduce (vqvae.py:58-59; one all-reduce of the packed buffer) and then applies vqvae.py:61-70 with
+ * vqb200_ema_update(d_stats, ...).                                                                                       */
+int  vqb200_host_quantize_stats(vqb200_host_ctx* ctx, const float* h_x, int64_t n_rows, float* d_embed, float* d_stats,
+                                float* h_quantize, int64_t* h_embed_ind, float* h_diff, int32_t engine);
 
 #ifdef __cplusplus
 }

@@ -321,3 +321,47 @@ def test_host_buffer_path_matches_device_path():
     assert rel_err(q2.cluster_size.cpu().numpy(), q.cluster_size.cpu().numpy()) <= 1e-6
     assert col_rel_err(q2.embed_avg.cpu().numpy(), q.embed_avg.cpu().numpy()) <= REL_TOL
     assert col_rel_err(q2.embed.cpu().numpy(), q.embed.cpu().numpy()) <= REL_TOL
+
+
+def test_host_buffer_path_data_parallel_form():
+    """vqb200_host_quantize_stats (statistics left on the device, no EMA) + vqb200_ema_update == vqb200_host_quantize with
+    training = 1: the split a data-parallel caller uses to all-reduce the statistics in between (vqvae.py:58-59)."""
+    lib = _native.load()
+    D, K, N = 64, 512, 50000
+    torch.manual_seed(4)
+    q = vq.Quantize(D, K).to(DEV).train()
+    q2 = vq.Quantize(D, K).to(DEV).train()
+    q2.load_state_dict(q.state_dict())
+    x_h = torch.randn(N, D).pin_memory()
+    stats = torch.zeros(lib.vqb200_stats_bytes(D, K) // 4, device=DEV)
+    ctx = C.c_void_p()
+    _native.check(lib.vqb200_host_ctx_create(N, D, K, C.byref(ctx)), "ctx")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    try:
+        out = [(torch.empty(N, D).pin_memory(), torch.empty(N, dtype=torch.int64).pin_memory(), torch.empty(1).pin_memory())
+               for _ in range(2)]
+        torch.cuda.synchronize()
+        for step in range(2):                                    # two steps: the second sees the first one's EMA update
+            qh, ih, dh = out[0]
+            _native.check(lib.vqb200_host_quantize(ctx, C.c_void_p(x_h.data_ptr()), N, _native.ptr(q.embed),
+                                                   _native.ptr(q.cluster_size), _native.ptr(q.embed_avg), 0.99,
+                                                   float(1 - 0.99), 1e-5, 1, C.c_void_p(qh.data_ptr()),
+                                                   C.c_void_p(ih.data_ptr()), C.c_void_p(dh.data_ptr()), 0), "host_quantize")
+            qs, is_, ds = out[1]
+            _native.check(lib.vqb200_host_quantize_stats(ctx, C.c_void_p(x_h.data_ptr()), N, _native.ptr(q2.embed),
+                                                         _native.ptr(stats), C.c_void_p(qs.data_ptr()),
+                                                         C.c_void_p(is_.data_ptr()), C.c_void_p(ds.data_ptr()), 0), "host_quantize_stats")
+            assert abs(float(stats[K * D: K * D + K].sum()) - N) < 0.5
+            _native.check(lib.vqb200_ema_update(_native.ptr(stats), _native.ptr(q2.cluster_size), _native.ptr(q2.embed_avg),
+                                                _native.ptr(q2.embed), D, K, 0.99, float(1 - 0.99), 1e-5, None, st), "ema_update")
+            torch.cuda.synchronize()
+            if step == 0:
+                assert torch.equal(ih, is_) and torch.equal(qh, qs)
+            else:
+                assert float((ih != is_).float().mean()) <= 1e-4
+            assert abs(float(dh) - float(ds)) <= 1e-5 * float(dh)
+            assert rel_err(q2.cluster_size.cpu().numpy(), q.cluster_size.cpu().numpy()) <= 1e-6
+            assert col_rel_err(q2.embed_avg.cpu().numpy(), q.embed_avg.cpu().numpy()) <= REL_TOL
+            assert col_rel_err(q2.embed.cpu().numpy(), q.embed.cpu().numpy()) <= REL_TOL
+    finally:
+        lib.vqb200_host_ctx_destroy(ctx)

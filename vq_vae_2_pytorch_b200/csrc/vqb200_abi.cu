@@ -664,13 +664,14 @@ void vqb200_host_ctx_destroy(vqb200_host_ctx* c) {
     delete c;
 }
 
-int vqb200_host_quantize(vqb200_host_ctx* c, const float* h_x, int64_t n_rows, float* d_embed,
-                         float* d_cluster_size, float* d_embed_avg, float decay, float one_minus_decay,
-                         float eps, int32_t training, float* h_quantize, int64_t* h_embed_ind, float* h_diff,
-                         int32_t engine) {
+// `stats_out` != nullptr: leave the batch statistics there and skip the EMA (the caller reduces them across ranks first)
+static int host_run(vqb200_host_ctx* c, const float* h_x, int64_t n_rows, float* d_embed,
+                    float* d_cluster_size, float* d_embed_avg, float decay, float one_minus_decay,
+                    float eps, int32_t training, float* stats_out, float* h_quantize, int64_t* h_embed_ind, float* h_diff,
+                    int32_t engine) {
     if (!c || !d_embed || n_rows < 0 || n_rows > c->max_rows) return VQB200_EINVAL;
     if (n_rows > 0 && (!h_x || !h_embed_ind)) return VQB200_EINVAL;
-    if (training && (!d_cluster_size || !d_embed_avg)) return VQB200_EINVAL;
+    if (training && !stats_out && (!d_cluster_size || !d_embed_avg)) return VQB200_EINVAL;
     const int D = c->dim, K = c->n_embed;
     VQ_CUDA(cudaSetDevice(c->device));
     // the private streams are non-blocking: order them behind whatever the caller's stream did to d_embed / cluster_size /
@@ -679,7 +680,7 @@ int vqb200_host_quantize(vqb200_host_ctx* c, const float* h_x, int64_t n_rows, f
     VQ_CUDA(cudaStreamWaitEvent(c->s_run, c->ev_start, 0));
     int rc = prepare_codebook(d_embed, D, K, c->d_codebook, c->s_run);
     if (rc) return rc;
-    float* stats = training ? c->d_stats : nullptr;
+    float* stats = stats_out ? stats_out : training ? c->d_stats : nullptr;
     // row chunks: full-size chunks in the middle (large copies keep both PCIe directions efficient), a short ramp at
     // the start (the first device->host copy can begin early) and at the end (short tail after the last host->device copy)
     int64_t begin[65];
@@ -727,7 +728,7 @@ int vqb200_host_quantize(vqb200_host_ctx* c, const float* h_x, int64_t n_rows, f
         }
     }
     if (h_diff) VQ_CUDA(cudaMemcpyAsync(h_diff, c->d_diff, 4, cudaMemcpyDeviceToHost, c->s_run));
-    if (training) {
+    if (training && !stats_out) {
         rc = ema_impl(c->d_stats, nullptr, d_cluster_size, d_embed_avg, d_embed, D, K, decay, one_minus_decay, eps,
                       c->d_codebook, c->s_run);
         if (rc) return rc;
@@ -735,6 +736,21 @@ int vqb200_host_quantize(vqb200_host_ctx* c, const float* h_x, int64_t n_rows, f
     VQ_CUDA(cudaStreamSynchronize(c->s_out));
     VQ_CUDA(cudaStreamSynchronize(c->s_run));
     return VQB200_OK;
+}
+
+int vqb200_host_quantize(vqb200_host_ctx* c, const float* h_x, int64_t n_rows, float* d_embed,
+                         float* d_cluster_size, float* d_embed_avg, float decay, float one_minus_decay,
+                         float eps, int32_t training, float* h_quantize, int64_t* h_embed_ind, float* h_diff,
+                         int32_t engine) {
+    return host_run(c, h_x, n_rows, d_embed, d_cluster_size, d_embed_avg, decay, one_minus_decay, eps, training, nullptr,
+                    h_quantize, h_embed_ind, h_diff, engine);
+}
+
+int vqb200_host_quantize_stats(vqb200_host_ctx* c, const float* h_x, int64_t n_rows, float* d_embed, float* d_stats,
+                               float* h_quantize, int64_t* h_embed_ind, float* h_diff, int32_t engine) {
+    if (!d_stats) return VQB200_EINVAL;
+    return host_run(c, h_x, n_rows, d_embed, nullptr, nullptr, 0.f, 0.f, 0.f, 1, d_stats, h_quantize, h_embed_ind, h_diff,
+                    engine);
 }
 
 }  // extern "C"
