@@ -138,7 +138,9 @@ def compare_step(tag, ref_q, our_q, x, ref_chunk=None, check_strides=True):
     assert oi.dtype == torch.int64 and oi.shape == x.shape[:-1] and oi.is_contiguous()
     assert oq.shape == x.shape and oq.dtype == torch.float32 and od.dim() == 0 and od.dtype == torch.float32
     if check_strides and not ref_chunk:
-        assert oq.stride() == rq.stride(), f"{tag}: quantize strides {oq.stride()} != reference {rq.stride()}"
+        # (strides of size-1 dimensions are arbitrary in torch: compared where they address anything)
+        assert all(a == b for a, b, n in zip(oq.stride(), rq.stride(), x.shape) if n > 1), \
+            f"{tag}: quantize strides {oq.stride()} != reference {rq.stride()}"
     flat = x.reshape(-1, D)
     n = flat.shape[0]
     n_differ, n_bad, rows, codes = index_mismatches(flat, before["embed"], oi, ri)

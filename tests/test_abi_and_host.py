@@ -159,3 +159,19 @@ def test_tensor_core_shape_coverage_table():
     assert lib.vqb200_tc_supported(p, 4 * 1024, 64, 512, 1024, 64 * 1024, 1, 1024) == 1
     assert lib.vqb200_tc_supported(p, 4 * 1024, 256, 512, 1024, 256 * 1024, 1, 1024) == 0
     assert lib.vqb200_tc_supported(p, 0, 64, 512, 1, 0, 64, 1) == 0
+
+
+def test_output_layout_rule_matches_torch_elementwise_ops():
+    """vqvae.py:73 returns `input + (...)`: x's own strides when x is non-overlapping and dense, else a dense tensor in x's
+    dimension order (what clone(preserve_format) / empty_like allocate).  The module uses the same rule."""
+    from vq_vae_2_pytorch_b200.quantize import _non_overlapping_and_dense as dense
+    x = torch.zeros(2, 8, 16, 64)
+    cases = [x, x.permute(0, 3, 1, 2), x.permute(0, 2, 1, 3), x[:, :, ::2], x[..., ::2], torch.zeros(5, 64),
+             torch.zeros(1, 64).expand(5, 64), torch.zeros(2, 64, 8, 16).permute(0, 2, 3, 1)[:, :, ::2], torch.zeros(1, 1, 4, 64)]
+    for t in cases:
+        ref_out = t + (torch.zeros(t.shape) - t)                    # the reference's expression, on CPU
+        if dense(t):
+            assert ref_out.stride() == t.stride()
+        else:
+            assert ref_out.stride() == t.clone(memory_format=torch.preserve_format).stride() != t.stride()
+        assert torch.empty_like(t).stride() == ref_out.stride()

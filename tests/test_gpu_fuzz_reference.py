@@ -1,0 +1,104 @@
+"""Seeded fuzz against THE REFERENCE's own `Quantize` (oracle/_ref/vqvae.py, unmodified, on the same B200, TF32 off):
+random row counts (ragged: not multiples of the 128-row tile), layouts (2-D, NHWC-dense, NCHW-physical permuted views,
+non-contiguous slices), codebook sizes on and off the tensor-core engines' shapes, D in {64, 128, 256} and odd dims on the
+exact SIMT engine, input scales from 1e-3 to 1e3, duplicate codes (exact ties), train and eval, 3 chained steps each on the
+reference's trajectory.  Every case runs through tests/ref_harness.compare_step: indices exact except float64 near-ties
+< 1e-6, everything else within 1e-5 element by element.  The reference is the judge; nothing here compares the repo with
+itself."""
+import random
+
+import pytest
+import torch
+
+import vq_vae_2_pytorch_b200 as vq
+from vq_vae_2_pytorch_b200 import _native
+import ref_harness as H
+from oracle import reference_module
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def ref():
+    try:
+        mod = reference_module.load("vqvae")
+    except reference_module.ReferenceUnavailable as exc:
+        pytest.skip(f"reference not staged: {exc}")
+    H.fp32_reference_backends()
+    yield mod
+    H.dump_report("parity_report_fuzz.json")
+
+
+def draw_case(rng):
+    D = rng.choice([64, 64, 64, 128, 256, 48, 20, 7])
+    if D in (64, 128, 256):
+        K = rng.choice([256, 512, 512, 1024, 2048, 384, 100, 16])
+    else:
+        K = rng.choice([512, 100, 33, 16])
+    layout = rng.choice(["2d", "nhwc", "nchw", "nchw", "sliced"])
+    if layout == "2d":
+        shape = (rng.choice([1, 5, 127, 128, 129, 1000, 4097, 20000, 70001]), D)
+    else:
+        b = rng.choice([1, 2, 3, 8])
+        h = rng.choice([1, 3, 8, 16, 31, 32])
+        w = rng.choice([1, 4, 8, 17, 32, 64])
+        shape = (b, h, w, D)
+    scale = rng.choice([1e-3, 0.1, 1.0, 1.0, 30.0, 1e3])
+    return {"D": D, "K": K, "layout": layout, "shape": shape, "scale": scale, "train": rng.random() < 0.7,
+            "dup": rng.random() < 0.25, "kind": rng.choice(["randn", "clustered", "clustered", "on_code"]),
+            "engine": rng.choice(["auto", "auto", "auto", "tcgen05", "tcgen05_bf16", "tcgen05_tf32", "simt"])}
+
+
+def make_x(case, embed, seed):
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    D, shape = case["D"], case["shape"]
+    n = 1
+    for s in shape[:-1]:
+        n *= s
+    K = embed.shape[1]
+    if case["kind"] == "randn":
+        x = case["scale"] * torch.randn(n, D, device=DEV, generator=g)
+    else:
+        norms = embed.pow(2).sum(0)
+        live = torch.nonzero(norms < 100.0 * norms.min().clamp_min(1e-12)).reshape(-1)
+        pick = live[torch.randint(0, live.numel(), (n,), device=DEV, generator=g)]
+        x = embed.t()[pick].clone()
+        if case["kind"] == "clustered":
+            x += 0.1 * float(embed[:, live].abs().mean()) * torch.randn(n, D, device=DEV, generator=g)
+        # "on_code": rows EQUAL to a code (distance 0; with duplicates an exact tie -> lowest index, vqvae.py:49)
+    x = x.reshape(shape)
+    if case["layout"] == "nchw":
+        x = x.permute(0, 3, 1, 2).contiguous().permute(0, 2, 3, 1)
+    elif case["layout"] == "sliced":                     # every other pixel column of a wider tensor: exotic strides
+        wide = torch.zeros(shape[0], shape[1], 2 * shape[2], D, device=DEV)
+        wide[:, :, ::2] = x
+        x = wide[:, :, ::2]
+    return x
+
+
+@pytest.mark.parametrize("seed", range(96))
+def test_fuzz_case_vs_reference(ref, seed):
+    rng = random.Random(9000 + seed)
+    case = draw_case(rng)
+    D, K = case["D"], case["K"]
+    torch.manual_seed(seed)
+    r = ref.Quantize(D, K).to(DEV).train(case["train"])
+    with torch.no_grad():
+        r.embed.mul_(case["scale"])
+        if case["dup"] and K >= 8:                       # duplicate columns: exact ties
+            r.embed[:, K // 2] = r.embed[:, 1]
+            r.embed[:, K - 1] = r.embed[:, 1]
+        r.embed_avg.copy_(r.embed)
+    o = vq.Quantize(D, K).to(DEV).train(case["train"])
+    o.load_state_dict(r.state_dict(), strict=True)
+    for step in range(3):
+        x = make_x(case, r.embed.detach(), 77 * seed + step)
+        # an explicitly requested tensor-core engine raises on a shape it does not cover (by design): pin it where it applies
+        lay = vq.row_layout(x) if x.numel() else None
+        covered = lay is not None and bool(_native.load().vqb200_tc_supported(x.data_ptr(), lay[0], D, K, *lay[1:]))
+        o.engine = case["engine"] if (covered or case["engine"] in ("auto", "simt")) else "auto"
+        e = H.compare_step(f"fuzz{seed}-{case['layout']}-D{D}-K{K}-{case['kind']}-{case['engine']}-s{step}", r, o, x)
+        n = e["rows"]
+        if case["kind"] != "on_code":
+            assert e["index_differ_near_tie"] <= max(2, n // 100000)

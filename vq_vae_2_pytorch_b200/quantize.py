@@ -96,6 +96,18 @@ def _row_layout(shape, stride):
     return None
 
 
+def _non_overlapping_and_dense(x: torch.Tensor) -> bool:
+    """True when x's elements tile one gap-free block of memory in SOME dimension order (then torch's element-wise ops,
+    and vqvae.py:73 with them, return a tensor with exactly x's strides)."""
+    dims = sorted((st, n) for n, st in zip(x.shape, x.stride()) if n != 1)
+    expect = 1
+    for st, n in dims:
+        if st != expect:
+            return False
+        expect *= n
+    return True
+
+
 class _QuantizeFunction(torch.autograd.Function):
     """forward = CUDA kernels; backward = straight-through + commitment gradient (vqvae.py:72-73)."""
 
@@ -385,12 +397,20 @@ class Quantize(nn.Module):
 
     def forward(self, input):
         self._check_input(input)
-        if row_layout(input) is None:         # exotic strides: one explicit copy, like reshape() in vqvae.py:43
+        out_like = None
+        if not _non_overlapping_and_dense(input):
+            # strided slices, expanded views: vqvae.py:73 (`input + (...)`) returns a DENSE tensor in the input's dimension
+            # order -- exactly what clone(preserve_format) allocates; the kernels then work on / return that layout
+            input = input.clone(memory_format=torch.preserve_format)
+        if row_layout(input) is None:         # dense, but in a dimension order the kernels do not address: one explicit
+            out_like = input                  # copy, like reshape() in vqvae.py:43, and the result goes back to that order
             input = input.contiguous()
         if input.requires_grad and torch.is_grad_enabled():
             quantize, diff, embed_ind = _QuantizeFunction.apply(input, self)
         else:
             quantize, diff, embed_ind, _, _ = self._run_forward(input)
+        if out_like is not None:
+            quantize = torch.empty_like(out_like).copy_(quantize)
         return quantize, diff, embed_ind
 
     @torch.no_grad()
