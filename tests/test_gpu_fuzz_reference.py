@@ -102,3 +102,48 @@ def test_fuzz_case_vs_reference(ref, seed):
         n = e["rows"]
         if case["kind"] != "on_code":
             assert e["index_differ_near_tie"] <= max(2, n // 100000)
+
+
+@pytest.mark.parametrize("seed", range(32))
+def test_fuzz_backward_vs_reference_autograd(ref, seed):
+    """The implied backward (graph of vqvae.py:72-73): x.grad of  sum(w * quantize) + c * diff  from the module's autograd
+    Function against the reference's own autograd graph, same fuzzed shapes / layouts, element by element at 1e-5 of the
+    magnitude of the two terms the gradient sums."""
+    rng = random.Random(5000 + seed)
+    case = draw_case(rng)
+    D, K = case["D"], case["K"]
+    torch.manual_seed(seed)
+    r = ref.Quantize(D, K).to(DEV).train(case["train"])
+    with torch.no_grad():
+        r.embed.mul_(case["scale"])
+        r.embed_avg.copy_(r.embed)
+    o = vq.Quantize(D, K).to(DEV).train(case["train"])
+    o.load_state_dict(r.state_dict(), strict=True)
+    if case["kind"] == "on_code":
+        case["kind"] = "clustered"                       # (x - q == 0 exactly would test nothing)
+    x = make_x(case, r.embed.detach(), 31 * seed)
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    w = torch.randn(x.shape, device=DEV, generator=g)
+    c = float(rng.choice([0.0, 0.25, 1.0, 1e3]))
+    xr = x.detach().clone(memory_format=torch.preserve_format).requires_grad_(True)
+    xo = x.detach().clone(memory_format=torch.preserve_format).requires_grad_(True)
+    if case["layout"] == "sliced":                       # keep the non-dense view in the graph
+        base_r = torch.zeros(x.shape[0], x.shape[1], 2 * x.shape[2], D, device=DEV).requires_grad_(True)
+        base_o = torch.zeros_like(base_r).requires_grad_(True)
+        with torch.no_grad():
+            base_r[:, :, ::2] = x
+            base_o[:, :, ::2] = x
+        xr, xo = base_r[:, :, ::2], base_o[:, :, ::2]
+    qr, dr, ir = r(xr)
+    qo, do, io = o(xo)
+    assert torch.equal(ir, io)
+    ((w * qr).sum() + c * dr).backward()
+    ((w * qo).sum() + c * do).backward()
+    gr = (base_r.grad[:, :, ::2] if case["layout"] == "sliced" else xr.grad)
+    go = (base_o.grad[:, :, ::2] if case["layout"] == "sliced" else xo.grad)
+    n_el = x.numel()
+    scale = (w.abs() + c * 2.0 * (x - qr.detach()).abs() / n_el).double().clamp_min(1e-30)
+    err = float(((gr.double() - go.double()).abs() / scale).max())
+    assert err <= 1e-5, f"backward fuzz {seed} ({case['layout']}, D={D}, K={K}): gradient off by {err:.3e}"
+    if case["layout"] != "sliced":
+        assert all(a == b for a, b, n in zip(go.stride(), gr.stride(), x.shape) if n > 1)
