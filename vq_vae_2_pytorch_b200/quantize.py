@@ -201,6 +201,9 @@ class Quantize(nn.Module):
         larger than 8 ranks, the shape is outside the fused EMA kernel, or VQB200_NO_P2P is set."""
         if "peer" in ws:
             return ws["peer"]
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("Quantize: the first multi-rank training forward sets up peer memory collectively and cannot "
+                               "be captured -- run one eager forward on every rank before capturing the CUDA graph")
         ws["peer"] = None
         import torch.distributed as dist
         world, rank = dist.get_world_size(), dist.get_rank()
