@@ -112,6 +112,14 @@ int vqb200_ema_update_p2p(const void* const* h_stats_ptrs, void* const* h_flag_p
                           uint32_t step, float* d_cluster_size, float* d_embed_avg, float* d_embed,
                           int32_t dim, int32_t n_embed, float decay, float one_minus_decay, float eps,
                           void* d_codebook, void* stream);
+/* The same exchange for ANY packed statistics buffer (shapes outside the fused kernel below: D = 128 / 256, K >= 1024):
+ * an in-place all-reduce (SUM) of d_stats[0 .. n_words) over peer memory -- what dist_fn.all_reduce does at vqvae.py:58-59,
+ * without NCCL: every word is stored as a {value, step} pair into every rank's receive slot and the local slots are summed
+ * in rank order (bit-identical replicas).  Pointer arrays, d_err and d_step_counter as in vqb200_quantize_step_peers; every
+ * slot holds n_words pairs; d_step_counter points at TWO zero-initialised words (counter, launch ticket).  Follow with
+ * vqb200_ema_update(d_stats, ...).                                                                                      */
+int vqb200_stats_exchange_peers(float* d_stats, int64_t n_words, void* const* h_push_dst, const void* const* h_recv,
+                                void* d_err, void* d_step_counter, int32_t rank, int32_t world, void* stream);
 /* Multi-rank training forward in ONE call, with the exchange that replaces dist_fn.all_reduce (vqvae.py:58-59 ->
  * distributed/distributed.py:64-72) fused into the EMA kernel over peer memory; dim 64 / n_embed 256 or 512.  Forward as
  * vqb200_quantize_step, then ONE kernel folds the per-CTA statistics tables, stores every word of this rank's packed

@@ -67,6 +67,7 @@ def test_argument_validation_without_a_gpu():
     assert lib.vqb200_quantize_step_peers(None, 10, 64, 512, 10, 0, 64, 1, None, None, None, None, None, None, None, None, None, 0,
                                           0.99, 0.01, 1e-5, None, None, None, None, 0, 2, None) == -1
     assert lib.vqb200_host_quantize_stats(None, None, 10, None, None, None, None, None, 0) == -1
+    assert lib.vqb200_stats_exchange_peers(None, 10, None, None, None, None, 0, 2, None) == -1
     assert lib.vqb200_debug_tc_kernel(None, 10, 64, 512, None, None, None, None, 2, None) == -1
 
 

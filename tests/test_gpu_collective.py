@@ -114,3 +114,30 @@ def test_step_peers_with_world_1_equals_single_rank_step(K):
         scale = a.embed_avg.abs().amax(0, keepdim=True).clamp_min(1e-30)
         assert float(((a.embed_avg - b.embed_avg).abs() / scale).max()) <= 2e-6
         b.load_state_dict(a.state_dict())
+
+
+def test_stats_exchange_with_world_1_is_the_identity_and_counts_steps():
+    """vqb200_stats_exchange_peers (the in-place all-reduce over peer memory that shapes outside the fused kernel use) with
+    world = 1: the rank-ordered sum over one rank is the buffer itself; every slot word carries the step tag; the device-side
+    counter advances by one per launch and the ticket word returns to zero; parity alternates between the two slots."""
+    lib = _native.load()
+    n = 256 * 257 + 3                                            # not a multiple of anything
+    n_al = (n + 63) // 64 * 64
+    buf = torch.zeros(2 * 2 * n_al + 64, device=DEV)
+    slots = [buf[par * 2 * n_al: par * 2 * n_al + 2 * n] for par in (0, 1)]
+    err = buf[4 * n_al: 4 * n_al + 64]
+    ptrs = (C.c_void_p * 2)(*[t.data_ptr() for t in slots])
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for step in range(1, 5):
+        stats = torch.randn(n, device=DEV, generator=torch.Generator(device=DEV).manual_seed(step))
+        want = stats.clone()
+        _native.check(lib.vqb200_stats_exchange_peers(stats.data_ptr(), n, ptrs, ptrs, err.data_ptr(), err[32:].data_ptr(), 0, 1, st),
+                      "stats_exchange")
+        torch.cuda.synchronize()
+        assert torch.equal(stats, want)
+        pairs = slots[step & 1].view(n, 2)
+        assert torch.equal(pairs[:, 0], want) and bool((pairs[:, 1].view(torch.int32) == step).all())
+        words = err.view(torch.int32)
+        assert int(words[0]) == 0 and int(words[32]) == step and int(words[33]) == 0
+    assert lib.vqb200_stats_exchange_peers(None, n, ptrs, ptrs, err.data_ptr(), err[32:].data_ptr(), 0, 1, st) == -1
+    assert lib.vqb200_stats_exchange_peers(buf.data_ptr(), n, ptrs, ptrs, err.data_ptr(), err[32:].data_ptr(), 1, 1, st) == -1

@@ -3,7 +3,8 @@ calling the reference's own `dist_fn.all_reduce` (oracle/_ref/distributed/distri
 GPU, against the drop-in module on its default data-parallel path (statistics exchange fused into the EMA kernel over peer
 memory) -- same per-rank inputs, four chained training steps through tests/ref_harness.compare_step on every rank
 (indices exact bar fp64 near-ties, everything else 1e-5 element-wise), replicas bit-identical afterwards.  Also the NCCL
-fallback path (VQB200_NO_P2P=1) and a D = 256 deep-fork shape (vqvae_deep.py:252), which always takes the fallback.
+fallback path (VQB200_NO_P2P=1), and the separate in-place exchange kernel that shapes outside the fused kernel take: the
+D = 256 deep-fork shape (vqvae_deep.py:252), a sliced codebook (K = 1024) and an odd shape on the SIMT engine.
 Needs 2 GPUs (skipped on a 1-GPU box); the per-rank report goes to gpurun_out/parity_report_collective.json."""
 import json
 import os
@@ -44,7 +45,9 @@ def _worker(rank, world, port, out):
         for name, D, K, shape, no_p2p in (("peer_memory_D64_K512", 64, 512, (16, 64, 64, 64), False),
                                           ("peer_memory_D64_K256_nchw", 64, 256, (8, 32, 32, 64), False),
                                           ("nccl_fallback_D64_K512", 64, 512, (16, 32, 32, 64), True),
-                                          ("deep_fork_D256_K512", 256, 512, (4, 32, 32, 256), False)):
+                                          ("deep_fork_D256_K512", 256, 512, (4, 32, 32, 256), False),
+                                          ("sliced_D64_K1024", 64, 1024, (8, 32, 32, 64), False),
+                                          ("odd_D48_K100", 48, 100, (4, 16, 16, 48), False)):
             torch.manual_seed(11)                         # same initial codebook on every rank (DDP would broadcast it)
             r = ref.Quantize(D, K).to(dev).train()
             o = vq.Quantize(D, K).to(dev).train()
@@ -86,8 +89,10 @@ def test_two_rank_training_vs_reference_with_its_own_all_reduce():
     for rank in (0, 1):
         p = res[rank]["paths"]
         assert p["peer_memory_D64_K512"] == "peer memory" and p["peer_memory_D64_K256_nchw"] == "peer memory", p
-        assert p["nccl_fallback_D64_K512"] == "nccl" and p["deep_fork_D256_K512"] == "nccl", p
-        assert len(res[rank]["report"]) == 16
+        assert p["nccl_fallback_D64_K512"] == "nccl", p
+        # shapes outside the fused fold + EMA kernel: the separate in-place exchange kernel (vqb200_stats_exchange_peers)
+        assert p["deep_fork_D256_K512"] == p["sliced_D64_K1024"] == p["odd_D48_K100"] == "peer memory", p
+        assert len(res[rank]["report"]) == 24
     path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
     os.makedirs(path, exist_ok=True)
     with open(os.path.join(path, "parity_report_collective.json"), "w") as f:

@@ -52,6 +52,7 @@ SIGNATURES = {
     "vqb200_host_ctx_set_stream": (C.c_int, [_p, _p]),
     "vqb200_host_ctx_destroy": (None, [_p]),
     "vqb200_host_quantize": (C.c_int, [_p, _p, _i64, _p, _p, _p, _f32, _f32, _f32, _i32, _p, _p, _p, _i32]),
+    "vqb200_stats_exchange_peers": (C.c_int, [_p, _i64, _p, _p, _p, _p, _i32, _i32, _p]),
     "vqb200_host_quantize_stats": (C.c_int, [_p, _p, _i64, _p, _p, _p, _p, _p, _i32]),
 }
 

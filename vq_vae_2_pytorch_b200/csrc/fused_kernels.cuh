@@ -554,4 +554,35 @@ __global__ void __launch_bounds__(EF_THREADS) k_ema64f(const float* __restrict__
 #endif
 }
 
+// The same flag-in-data exchange for ANY packed statistics buffer (shapes outside the fused fold + EMA kernel: D = 128 / 256,
+// K >= 1024): every thread stores its words of d_stats as {value, step} pairs into every rank's receive slot, then polls
+// the LOCAL slots and overwrites d_stats with the rank-ordered sum -- an in-place all-reduce without NCCL, bit-identical on
+// every rank.  One wave of CTAs (grid <= SM count): every CTA pushes ALL its words before it polls any, so no CTA waits
+// for a word whose sender cannot run.  peers.step_counter[1] is the launch's ticket word.
+__global__ void __launch_bounds__(1024, 1) k_exchange_ll(float* __restrict__ stats, int n, PeerFold peers) {
+    __shared__ unsigned int last_s;
+    pdl_wait();
+    pdl_trigger();
+    const unsigned int step = *reinterpret_cast<volatile unsigned int*>(peers.step_counter) + 1u;
+    const int par = (int)(step & 1u);
+    const int stride = (int)(gridDim.x * blockDim.x);
+    const int first = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    for (int i = first; i < n; i += stride) {
+        const float v = stats[i];
+#pragma unroll
+        for (int r = 0; r < P2P_MAX_RANKS; ++r)
+            if (r < peers.world) st_ll(peers.push_dst[par][r] + i, v, step);
+    }
+    for (int i = first; i < n; i += stride) stats[i] = ll_gather(peers, step, (size_t)i);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        last_s = (atomicAdd(peers.step_counter + 1, 1u) == gridDim.x - 1u) ? 1u : 0u;
+        if (last_s) {
+            peers.step_counter[1] = 0u;
+            *peers.step_counter = step;
+        }
+    }
+}
+
 }  // namespace vqb200

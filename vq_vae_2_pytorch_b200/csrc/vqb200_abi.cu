@@ -341,6 +341,37 @@ int vqb200_ema_update_p2p(const void* const* h_stats_ptrs, void* const* h_flag_p
                     d_codebook, (cudaStream_t)stream);
 }
 
+static int fill_peer_fold(PeerFold& pf, void* const* h_push_dst, const void* const* h_recv, void* d_err, void* d_step_counter,
+                          int rank, int world) {
+    if (!h_push_dst || !h_recv || !d_err || !d_step_counter) return VQB200_EINVAL;
+    if (world < 1 || world > P2P_MAX_RANKS || rank < 0 || rank >= world) return VQB200_EINVAL;
+    for (int par = 0; par < 2; ++par)
+        for (int r = 0; r < world; ++r) {           // h_push_dst / h_recv: [2 parities][world] pointers, parity-major
+            void* dst = h_push_dst[par * world + r];
+            const void* rcv = h_recv[par * world + r];
+            if (!dst || !rcv) return VQB200_EINVAL;
+            if ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(rcv)) & 7u) return VQB200_EINVAL;
+            pf.push_dst[par][r] = static_cast<uint2*>(dst);
+            pf.recv[par][r] = static_cast<const uint2*>(rcv);
+        }
+    pf.err = static_cast<unsigned int*>(d_err);
+    pf.step_counter = static_cast<unsigned int*>(d_step_counter);
+    pf.rank = rank; pf.world = world;
+    return VQB200_OK;
+}
+
+int vqb200_stats_exchange_peers(float* d_stats, int64_t n_words, void* const* h_push_dst, const void* const* h_recv,
+                                void* d_err, void* d_step_counter, int32_t rank, int32_t world, void* stream) {
+    if (!d_stats || n_words <= 0 || n_words > (int64_t)(1 << 24)) return VQB200_EINVAL;
+    PeerFold pf{};
+    int rc = fill_peer_fold(pf, h_push_dst, h_recv, d_err, d_step_counter, rank, world);
+    if (rc) return rc;
+    const int blocks = (int)std::min<int64_t>((n_words + 1023) / 1024, tc_num_sms());     // ONE wave (see the kernel)
+    VQ_CUDA(launch_pdl(k_exchange_ll, dim3(blocks), dim3(1024), 0, (cudaStream_t)stream, d_stats, (int)n_words, pf));
+    g_launches.fetch_add(1);
+    return VQB200_OK;
+}
+
 int vqb200_quantize_step(const float* d_x, int64_t n_rows, int32_t dim, int32_t n_embed, int64_t rows_per_image,
                          int64_t image_stride, int64_t row_stride, int64_t col_stride, float* d_embed,
                          float* d_cluster_size, float* d_embed_avg, void* d_codebook, float* d_quantize,
@@ -384,25 +415,15 @@ int vqb200_quantize_step_peers(const float* d_x, int64_t n_rows, int32_t dim, in
                                void* stream) {
     if (!d_embed || !d_cluster_size || !d_embed_avg || !d_codebook || !d_scratch || dim <= 0 || n_embed <= 0) return VQB200_EINVAL;
     if (n_rows < 0 || (n_rows > 0 && (!d_x || !d_embed_ind))) return VQB200_EINVAL;
-    if (!h_push_dst || !h_recv || !d_err || !d_step_counter) return VQB200_EINVAL;
-    if (world < 1 || world > P2P_MAX_RANKS || rank < 0 || rank >= world) return VQB200_EINVAL;
     if (n_rows > (int64_t)INT32_MAX) return VQB200_EUNSUPPORTED;
     if (engine < VQB200_ENGINE_AUTO || engine > VQB200_ENGINE_TCGEN05_TF32) return VQB200_EINVAL;
     if (n_rows > 0 && !layout_ok(n_rows, dim, rows_per_image, image_stride, row_stride, col_stride)) return VQB200_EUNSUPPORTED;
     if (!tc_shape_ok(dim, n_embed)) return VQB200_EUNSUPPORTED;      // the fold + EMA kernel: dim 64, n_embed 256 / 512
     PeerFold pf{};
-    for (int par = 0; par < 2; ++par)
-        for (int r = 0; r < world; ++r) {           // h_push_dst / h_recv: [2 parities][world] pointers, parity-major
-            void* dst = h_push_dst[par * world + r];
-            const void* rcv = h_recv[par * world + r];
-            if (!dst || !rcv) return VQB200_EINVAL;
-            if ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(rcv)) & 7u) return VQB200_EINVAL;
-            pf.push_dst[par][r] = static_cast<uint2*>(dst);
-            pf.recv[par][r] = static_cast<const uint2*>(rcv);
-        }
-    pf.err = static_cast<unsigned int*>(d_err);
-    pf.step_counter = static_cast<unsigned int*>(d_step_counter);
-    pf.rank = rank; pf.world = world;
+    {
+        int prc = fill_peer_fold(pf, h_push_dst, h_recv, d_err, d_step_counter, rank, world);
+        if (prc) return prc;
+    }
     RowLayout L{n_rows, rows_per_image > 0 ? rows_per_image : 1, image_stride, row_stride, col_stride};
     ForwardScratch sc = scratch_view(d_scratch, n_rows, dim, n_embed);
     int rc = forward_impl(d_x, L, dim, n_embed, d_codebook, d_quantize, d_embed_ind, d_diff, sc.stat_partials, d_scratch, engine,

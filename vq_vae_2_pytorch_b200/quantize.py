@@ -207,7 +207,9 @@ class Quantize(nn.Module):
         ws["peer"] = None
         import torch.distributed as dist
         world, rank = dist.get_world_size(), dist.get_rank()
-        ok = (world <= 8 and self.dim == 64 and self.n_embed in (256, 512) and not os.environ.get("VQB200_NO_P2P"))
+        # fused into the fold + EMA kernel at dim 64 / n_embed 256, 512; a separate exchange kernel for every other shape
+        # whose packed statistics fit the slots (<= 1 Mi words: up to D = 256, K = 4096 ... D = 64, K = 16384)
+        ok = (world <= 8 and self.n_embed * (self.dim + 1) <= (1 << 20) and not os.environ.get("VQB200_NO_P2P"))
         peer = None
         if ok:
             try:
@@ -224,7 +226,8 @@ class Quantize(nn.Module):
                 hdl.barrier()
                 ptrs = [int(p) for p in hdl.buffer_ptrs]
                 mk = lambda vals: (C.c_void_p * (2 * world))(*vals)
-                peer = {"buf": buf, "hdl": hdl, "rank": rank, "world": world, "calls": 0, "checked": 0,
+                peer = {"buf": buf, "hdl": hdl, "rank": rank, "world": world, "calls": 0, "checked": 0, "words": n,
+                        "fused": self.dim == 64 and self.n_embed in (256, 512),
                         # [parity][rank r]: where MY statistics go on rank r (peer-mapped) ...
                         "push_dst": mk([p + 4 * (par * slots + rank * slot) for par in (0, 1) for p in ptrs]),
                         # ... and what the kernel polls and sums: my LOCAL slots, one per rank
@@ -370,7 +373,7 @@ class Quantize(nn.Module):
         fused_ema = self.training and world == 1
         # the codebook image is re-derived from `embed` on every call: external writes to the buffer
         # (load_state_dict, .data.copy_, DDP buffer broadcast) can never leave it stale
-        if peer is not None:                  # forward + statistics pushed to every rank (vqvae.py:43-56,58-59,72-73)
+        if peer is not None and peer["fused"]:    # forward + statistics pushed to every rank (vqvae.py:43-56,58-59,72-73)
             _native.check(lib.vqb200_quantize_step_peers(
                 x_run.data_ptr(), n, self.dim, self.n_embed, rpi, img, row, col, embed.data_ptr(),
                 cluster_size.data_ptr(), embed_avg.data_ptr(), image.data_ptr(),
@@ -390,8 +393,13 @@ class Quantize(nn.Module):
             _native.check(lib.vqb200_repack_rows(q_run.data_ptr(), quantize.data_ptr(), lay[0], self.dim, lay[1], lay[2],
                                                  lay[3], lay[4], 0, stream), "vqb200_repack_rows")
         self._note_flagged(ws, n, eng, dev)
-        if self.training and not fused_ema and peer is None:      # multi-rank without peer memory: one packed NCCL all-reduce
-            dist_fn.all_reduce(stats[: self.n_embed * (self.dim + 1)])  # vqvae.py:58-59 (one packed call)
+        if self.training and not fused_ema and not (peer is not None and peer["fused"]):
+            if peer is not None:              # vqvae.py:58-59 as an in-place exchange over peer memory (any shape)
+                _native.check(lib.vqb200_stats_exchange_peers(
+                    stats.data_ptr(), peer["words"], peer["push_dst"], peer["recv"], peer["err_ptr"], peer["step_ptr"],
+                    peer["rank"], peer["world"], stream), "vqb200_stats_exchange_peers")
+            else:                             # no peer memory: one packed NCCL all-reduce
+                dist_fn.all_reduce(stats[: self.n_embed * (self.dim + 1)])
             _native.check(lib.vqb200_ema_update(
                 stats.data_ptr(), cluster_size.data_ptr(), embed_avg.data_ptr(),
                 embed.data_ptr(), self.dim, self.n_embed, float(self.decay), float(1 - self.decay),
