@@ -639,7 +639,7 @@ def main():
             extras["parity_multi"] = parity_multi(vq, dev, rank, world, dist)
     if args.cfg5:
         # cfg-5: scaled codebook sweep, batch 128 (N = 524 288 rows) per GPU, training forward + EMA (statistics all-reduced
-        # across ranks: peer-memory exchange at D = 64 / K = 512, NCCL all-reduce of the packed buffer elsewhere)
+        # across ranks over peer memory: fused into the EMA kernel at D = 64 / K = 512, the separate in-place exchange kernel elsewhere)
         sweep = []
         for d5 in (64, 128, 256):
             for k5 in (512, 1024, 2048, 4096, 8192):
