@@ -288,6 +288,8 @@ k_code_stats(const float* __restrict__ x, RowLayout L, int D, int K, const int64
     int* cursor = start + K + 1;                              // [K]
     unsigned short* code = reinterpret_cast<unsigned short*>(cursor + K);         // [CS_CHUNK] code of row i
     unsigned short* scode = code + CS_CHUNK;                  // [CS_CHUNK] code at sorted position p
+    __shared__ int warp_tot[CS_THREADS / 32];
+    static_assert(CS_THREADS / 32 == 32, "the scan folds one warp total per lane");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = CS_THREADS / 32;
 
     pdl_trigger();
@@ -302,41 +304,71 @@ k_code_stats(const float* __restrict__ x, RowLayout L, int D, int K, const int64
     for (int64_t j = n_chunks - 1 - blockIdx.x; j >= 0; j -= gridDim.x) {
         const int64_t r0 = j * chunk;
         const int rows = (int)min((int64_t)chunk, L.n_rows - r0);
+        // --- bucket the rows of this trip by code (counting sort).  The (at most CS_CHUNK / CS_THREADS = 4) codes of a thread
+        // are loaded up front -- independent loads, all in flight together -- and stay in registers for both passes.
+        int kk[CS_CHUNK / CS_THREADS];
+#pragma unroll
+        for (int u = 0; u < CS_CHUNK / CS_THREADS; ++u) {
+            const int i = tid + u * CS_THREADS;
+            kk[u] = -1;
+            if (i < rows) {
+                const long long kl = embed_ind[r0 + i];
+                int k = (int)kl;
+                if (kl < 0 || kl >= K) {         // cannot happen for indices written by our own kernels: clamp for memory safety AND report
+                    if (n_parts_out) atomicExch(n_parts_out + 1, 1u);   // scratch header word 14 (byte 56): internal-error flag
+                    k = kl < 0 ? 0 : K - 1;
+                }
+                kk[u] = k;
+            }
+        }
         __syncthreads();
         for (int i = tid; i < K; i += CS_THREADS) hist[i] = 0;
         __syncthreads();
-        for (int i = tid; i < rows; i += CS_THREADS) {
-            const long long kl = embed_ind[r0 + i];
-            int k = (int)kl;
-            if (kl < 0 || kl >= K) {             // cannot happen for indices written by our own kernels: clamp for memory safety AND report
-                if (n_parts_out) atomicExch(n_parts_out + 1, 1u);       // scratch header word 14 (byte 56): internal-error flag
-                k = kl < 0 ? 0 : K - 1;
-            }
-            code[i] = (unsigned short)k;
-            atomicAdd(&hist[k], 1);
-        }
+#pragma unroll
+        for (int u = 0; u < CS_CHUNK / CS_THREADS; ++u)
+            if (kk[u] >= 0) atomicAdd(&hist[kk[u]], 1);
         __syncthreads();
-        if (warp == 0) {                                      // exclusive scan of hist -> start
+        {                                                     // exclusive scan of hist -> start, all warps: warp w owns SB bins
+            const int SB = ((K + nwarps - 1) / nwarps + 31) / 32 * 32;
+            const int b_lo = min(K, warp * SB), b_hi = min(K, b_lo + SB);
             int carry = 0;
-            for (int b = 0; b < K; b += 32) {
-                int v = (b + lane < K) ? hist[b + lane] : 0;
+            for (int b = b_lo; b < b_hi; b += 32) {
+                const int v = (b + lane < b_hi) ? hist[b + lane] : 0;
                 int incl = v;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
-                    int t = __shfl_up_sync(0xffffffffu, incl, o);
+                    const int t = __shfl_up_sync(0xffffffffu, incl, o);
                     if (lane >= o) incl += t;
                 }
-                if (b + lane < K) { start[b + lane] = carry + incl - v; cursor[b + lane] = carry + incl - v; }
+                if (b + lane < b_hi) start[b + lane] = carry + incl - v;
                 carry += __shfl_sync(0xffffffffu, incl, 31);
             }
-            if (lane == 0) start[K] = carry;
+            if (lane == 0) warp_tot[warp] = carry;
+            __syncthreads();
+            const int t = warp_tot[lane];                     // nwarps == 32: one total per lane
+            int incl = t;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += u;
+            }
+            const int offset = __shfl_sync(0xffffffffu, incl - t, warp);
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            for (int b = b_lo + lane; b < b_hi; b += 32) {
+                const int st = start[b] + offset;
+                start[b] = st;
+                cursor[b] = st;
+            }
+            if (tid == 0) start[K] = total;
         }
         __syncthreads();
-        for (int i = tid; i < rows; i += CS_THREADS) {
-            const int k = code[i];
-            const int dst = atomicAdd(&cursor[k], 1);
-            order[dst] = row_offset(L, r0 + i);
-            scode[dst] = (unsigned short)k;
+#pragma unroll
+        for (int u = 0; u < CS_CHUNK / CS_THREADS; ++u) {
+            if (kk[u] >= 0) {
+                const int dst = atomicAdd(&cursor[kk[u]], 1);
+                order[dst] = row_offset(L, r0 + tid + u * CS_THREADS);
+                scode[dst] = (unsigned short)kk[u];
+            }
         }
         for (int k = tid; k < K; k += CS_THREADS) cnt_total[k] += hist[k];
         __syncthreads();
