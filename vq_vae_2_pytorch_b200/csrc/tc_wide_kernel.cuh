@@ -111,8 +111,9 @@ __global__ void __launch_bounds__(256) k_convert_wide(const float* __restrict__ 
 
 struct Plan {
     int KL, DB, XS, AS, NP, NSLOT, ENORM;
-    __host__ __device__ uint32_t off_bmisc() const { return (uint32_t)KL * 128u * (uint32_t)DB; }
-    __host__ __device__ uint32_t off_a() const { return off_bmisc() + (uint32_t)KL * 32u; }
+    int BDIV = 1;                                // 2: CTA pair, every CTA holds half of the B rows of each 128-code unit
+    __host__ __device__ uint32_t off_bmisc() const { return (uint32_t)(KL / BDIV) * 128u * (uint32_t)DB; }
+    __host__ __device__ uint32_t off_a() const { return off_bmisc() + (uint32_t)(KL / BDIV) * 32u; }
     __host__ __device__ uint32_t off_am() const { return off_a() + (uint32_t)AS * A_STAGE; }
     __host__ __device__ uint32_t off_x() const { return off_am() + 2u * AM_STAGE; }
     __host__ __device__ uint32_t off_small() const { return off_x() + (uint32_t)XS * X_STAGE; }
@@ -151,7 +152,7 @@ struct WParams {
 };
 
 enum WBar { WB_B = 0, WB_XF = 1, WB_XE = 5, WB_AF = 9, WB_AE = 13, WB_TF = 17, WB_TE = 21, WB_RF = 25, WB_RE = 27, WB_PF = 29,
-            WB_PE = 31, WB_COUNT = 33 };
+            WB_PE = 31, WB_PB = 33, WB_COUNT = 34 };
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar, uint64_t policy) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
@@ -160,32 +161,44 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int 
 
 // four K = 16 MMAs of one 64-dim block into one accumulator unit (converged warp, one elected lane issues); the first one
 // overwrites the accumulator when acc0 == 0
+template <bool CTA2 = false>
 __device__ __forceinline__ void issue_block4(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t acc0) {
-#define VQW_KS(KS)                                                                           \
+#define VQW_KS(CG, KS)                                                                       \
     "add.u32 ta, %1, " KS ";\n\tadd.u32 tb, %2, " KS ";\n\t"                                   \
     "mov.b64 da, {ta, %3};\n\tmov.b64 db, {tb, %3};\n\t"                                        \
-    "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, pt;\n\t"
-    asm volatile("{\n\t.reg .pred pa, pt, pe;\n\t.reg .b64 da, db;\n\t.reg .b32 ta, tb;\n\t"
-                 "elect.sync _|pe, 0xffffffff;\n\t"
-                 "setp.ne.b32 pa, %5, 0;\n\tsetp.eq.b32 pt, %4, %4;\n\t"
-                 "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
-                 "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, pa;\n\t"
-                 VQW_KS("2") VQW_KS("4") VQW_KS("6") "}"
-                 :: "r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(DESC_HI_SW128), "r"(IDESC), "r"(acc0) : "memory");
+    "@pe tcgen05.mma.cta_group::" CG ".kind::f16 [%0], da, db, %4, pt;\n\t"
+#define VQW_BLOCK4(CG)                                                                       \
+    asm volatile("{\n\t.reg .pred pa, pt, pe;\n\t.reg .b64 da, db;\n\t.reg .b32 ta, tb;\n\t"  \
+                 "elect.sync _|pe, 0xffffffff;\n\t"                                           \
+                 "setp.ne.b32 pa, %5, 0;\n\tsetp.eq.b32 pt, %4, %4;\n\t"                      \
+                 "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"                          \
+                 "@pe tcgen05.mma.cta_group::" CG ".kind::f16 [%0], da, db, %4, pa;\n\t"        \
+                 VQW_KS(CG, "2") VQW_KS(CG, "4") VQW_KS(CG, "6") "}"                          \
+                 :: "r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(DESC_HI_SW128), "r"(CTA2 ? IDESC2 : IDESC), "r"(acc0) : "memory")
+    if constexpr (CTA2) VQW_BLOCK4("2"); else VQW_BLOCK4("1");
+#undef VQW_BLOCK4
 #undef VQW_KS
 }
 // the misc MMA (K = 16, 32-byte swizzle rows): accumulates bias, row offset and error bound onto the finished products
+template <bool CTA2 = false>
 __device__ __forceinline__ void issue_misc(uint32_t d_tmem, uint32_t am_lo, uint32_t bm_lo) {
-    asm volatile("{\n\t.reg .pred pt, pe;\n\t.reg .b64 da, db;\n\t"
-                 "elect.sync _|pe, 0xffffffff;\n\t"
-                 "setp.eq.b32 pt, %4, %4;\n\t"
-                 "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
-                 "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, pt;\n\t}"
-                 :: "r"(d_tmem), "r"(am_lo), "r"(bm_lo), "r"(DESC_HI_SW32), "r"(IDESC) : "memory");
+#define VQW_MISC(CG)                                                                         \
+    asm volatile("{\n\t.reg .pred pt, pe;\n\t.reg .b64 da, db;\n\t"                            \
+                 "elect.sync _|pe, 0xffffffff;\n\t"                                           \
+                 "setp.eq.b32 pt, %4, %4;\n\t"                                                \
+                 "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"                          \
+                 "@pe tcgen05.mma.cta_group::" CG ".kind::f16 [%0], da, db, %4, pt;\n\t}"       \
+                 :: "r"(d_tmem), "r"(am_lo), "r"(bm_lo), "r"(DESC_HI_SW32), "r"(CTA2 ? IDESC2 : IDESC) : "memory")
+    if constexpr (CTA2) VQW_MISC("2"); else VQW_MISC("1");
+#undef VQW_MISC
 }
 
-template <int DB, int XS, bool DBG, bool PRE>
+// CTA2 = true (conversion path only): clusters of two CTAs share ONE tcgen05.mma.cta_group::2 stream (M = 256) issued by the
+// leader; every CTA converts, scans and writes its own 128-row tile but holds only its 64 rows of each 128-code unit of the
+// operand image -- KL = 512 codes stay resident at D = 256 (128 KB per CTA), i.e. ONE pass over x instead of two.
+template <int DB, int XS, bool DBG, bool PRE, bool CTA2 = false>
 __global__ void __launch_bounds__(THREADS, 1) k_vq_tcw(const __grid_constant__ WParams p) {
+    static_assert(!(CTA2 && PRE), "the CTA-pair variant converts in the kernel");
     constexpr int D = 64 * DB;
     constexpr int AS = PRE ? as_pre(DB) : AS_CONV;
     constexpr int NP = n_partials(PRE, DB), NSLOT = n_part_slots(PRE, DB);
@@ -201,8 +214,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tcw(const __grid_constant__ W
     // scheduler instead of two: the scan is bound by TMEM-load / dependent-minimum latency).
     const bool helper = PRE && DB == 2 && !DBG && U == 4 && !p.pass_last;
     const int NGRP = helper ? 4 : 2;
-    const Plan P{KL, DB, PRE ? 0 : XS, AS, NP, NSLOT, ENORM_S ? 1 : 0};
+    const Plan P{KL, DB, PRE ? 0 : XS, AS, NP, NSLOT, ENORM_S ? 1 : 0, CTA2 ? 2 : 1};
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int KLB = CTA2 ? KL / 2 : KL;          // operand-image rows resident in this CTA
+    constexpr uint32_t UROWS = CTA2 ? UNIT_N / 2 : UNIT_N;    // ... of each 128-code unit
+    const uint32_t crank = CTA2 ? cluster_ctarank() : 0u;
 
     const uint32_t sB = base, sBm = base + P.off_bmisc(), sA = base + P.off_a(), sAm = base + P.off_am(), sX = base + P.off_x();
     float* enorm_s = reinterpret_cast<float*>(sm + P.off_small());
@@ -216,18 +232,22 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tcw(const __grid_constant__ W
     pdl_wait();
     pdl_trigger();
     const int64_t n_tiles = (p.n_rows + TILE_M - 1) / TILE_M;
-    const uint32_t n_iter = (int64_t)blockIdx.x < n_tiles ? (uint32_t)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;
+    // both CTAs of a pair run the same number of trips (the pair's second tile may lie past the end on the last one)
+    const int64_t first_tile = CTA2 ? (int64_t)(blockIdx.x & ~1u) : (int64_t)blockIdx.x;
+    const uint32_t n_iter = first_tile < n_tiles ? (uint32_t)((n_tiles - first_tile + gridDim.x - 1) / gridDim.x) : 0u;
+    constexpr uint32_t PAIR_WARPS = CTA2 ? 8u : 4u;           // arriving warps on the barriers the MMA issuer waits on
 
     if (threadIdx.x == 0) {
         mbar_init(bar(WB_B), 1);
+        mbar_init(bar(WB_PB), 1);
         for (int s = 0; s < XS; ++s) { mbar_init(bar(WB_XF + s), 1); mbar_init(bar(WB_XE + s), 4); }
-        for (int s = 0; s < AS; ++s) { mbar_init(bar(WB_AF + s), PRE ? 1 : 4); mbar_init(bar(WB_AE + s), 1); }
-        for (int s = 0; s < NBUF; ++s) { mbar_init(bar(WB_TF + s), 1); mbar_init(bar(WB_TE + s), 4); }
+        for (int s = 0; s < AS; ++s) { mbar_init(bar(WB_AF + s), PRE ? 1 : PAIR_WARPS); mbar_init(bar(WB_AE + s), 1); }
+        for (int s = 0; s < NBUF; ++s) { mbar_init(bar(WB_TF + s), 1); mbar_init(bar(WB_TE + s), PAIR_WARPS); }
         for (int s = 0; s < RES_RING; ++s) { mbar_init(bar(WB_RF + s), 4); mbar_init(bar(WB_RE + s), 8); }
         for (int s = 0; s < 2; ++s) { mbar_init(bar(WB_PF + s), helper ? 12 : 4); mbar_init(bar(WB_PE + s), 4); }
         fence_barrier_init();
     }
-    if (warp == W_MMA) tmem_alloc(smem_u32(tmem_ptr_s), 512);
+    if (warp == W_MMA) { if (CTA2) tmem_alloc2(smem_u32(tmem_ptr_s), 512); else tmem_alloc(smem_u32(tmem_ptr_s), 512); }
     for (int i = threadIdx.x; i < 2 * TILE_M; i += THREADS)      // constant zero half of the A misc rows
         *reinterpret_cast<uint4*>(sm + P.off_am() + (i / TILE_M) * AM_STAGE + sw32_chunk_off((uint32_t)(i % TILE_M), 1)) = make_uint4(0, 0, 0, 0);
     fence_async_smem();
@@ -239,17 +259,32 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tcw(const __grid_constant__ W
     }
     tc_fence_before();
     const bool cb_bad = __syncthreads_or(bad) != 0;
+    if (CTA2) cluster_sync_all();                 // the peer's barriers exist before anybody arrives on them remotely
     tc_fence_after();
+    // barriers the (leader's) MMA issuer waits on live in the leader CTA; both CTAs arrive there
+    auto arrive_mma_side = [&](int id) {
+        if (CTA2) mbar_arrive_cluster(mapa_rank(bar(id), 0)); else mbar_arrive(bar(id));
+    };
     const uint32_t tmem_base = *tmem_ptr_s;
 
     if (warp == W_PROD) {
         // ================= producer: resident operand image once, then one 2-D TMA box per (tile, block) ==========
         reg_dec<24>();
         if (lane == 0) {
-            const uint32_t img_bytes = (uint32_t)KL * 128u * DB, misc_bytes = (uint32_t)KL * 32u;
+            const uint32_t img_bytes = (uint32_t)KLB * 128u * DB, misc_bytes = (uint32_t)KLB * 32u;
             mbar_expect_tx(bar(WB_B), img_bytes + misc_bytes);
-            for (uint32_t o = 0; o < img_bytes; o += 16384u) bulk_g2s(sB + o, p.image + o, 16384u, bar(WB_B));
-            bulk_g2s(sBm, p.image + wimage_off_misc(KL, DB), misc_bytes, bar(WB_B));
+            if constexpr (CTA2) {                // my 64 rows of every 128-code unit, block by block
+                for (int b = 0; b < DB; ++b)
+                    for (int u = 0; u < U; ++u)
+                        bulk_g2s(sB + ((uint32_t)b * KLB + (uint32_t)u * UROWS) * 128u,
+                                 p.image + ((size_t)b * KL + (size_t)u * UNIT_N + (size_t)crank * UROWS) * 128u, UROWS * 128u, bar(WB_B));
+                for (int u = 0; u < U; ++u)
+                    bulk_g2s(sBm + (uint32_t)u * UROWS * 32u, p.image + wimage_off_misc(KL, DB) + ((size_t)u * UNIT_N + (size_t)crank * UROWS) * 32u,
+                             UROWS * 32u, bar(WB_B));
+            } else {
+                for (uint32_t o = 0; o < img_bytes; o += 16384u) bulk_g2s(sB + o, p.image + o, 16384u, bar(WB_B));
+                bulk_g2s(sBm, p.image + wimage_off_misc(KL, DB), misc_bytes, bar(WB_B));
+            }
             const uint64_t keep = l2_policy_evict_last();       // the output warps read the tile again through L2
             for (uint32_t it = 0; it < n_iter; ++it) {
                 const int64_t t = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
@@ -279,8 +314,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tcw(const __grid_constant__ W
         // ================= MMA issuer (converged warp; tcgen05 instructions predicated on one elected lane) ======
         reg_dec<24>();
         mbar_wait(bar(WB_B), 0);
+        if (CTA2) {
+            if (crank != 0) { if (lane == 0) mbar_arrive_cluster(mapa_rank(bar(WB_PB), 0)); }   // my half of B has landed
+            else mbar_wait_cluster(bar(WB_PB), 0);
+        }
         const uint32_t b_lo0 = desc_lo(sB), bm_lo0 = desc_lo(sBm);
-        for (uint32_t it = 0; it < n_iter; ++it) {
+        for (uint32_t it = 0; it < (crank == 0 ? n_iter : 0u); ++it) {     // the leader issues for the pair
             const uint32_t am_lo = desc_lo(sAm + (it & 1u) * AM_STAGE);
             if constexpr (PRE && DB * 2 <= AS) {
                 // Streamed operands and two whole tiles fit in the A ring: UNIT-outer order.  The units of a tile finish one
@@ -305,23 +344,23 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tcw(const __grid_constant__ W
             } else
             for (int b = 0; b < DB; ++b) {
                 const uint32_t g = it * DB + b, sa = g % AS, pha = (g / AS) & 1u;
-                mbar_wait(bar(WB_AF + sa), pha);
+                if (CTA2) mbar_wait_cluster(bar(WB_AF + sa), pha); else mbar_wait(bar(WB_AF + sa), pha);
                 tc_fence_after();
                 const uint32_t a_lo = desc_lo(sA + sa * A_STAGE);
                 for (int u = 0; u < U; ++u) {
                     const uint32_t uc = it * (uint32_t)U + (uint32_t)u, buf = uc % NBUF, pht = (uc / NBUF) & 1u;
                     if (b == 0) {
-                        mbar_wait(bar(WB_TE + buf), pht ^ 1u);
+                        if (CTA2) mbar_wait_cluster(bar(WB_TE + buf), pht ^ 1u); else mbar_wait(bar(WB_TE + buf), pht ^ 1u);
                         tc_fence_after();
                     }
-                    issue_block4(tmem_base + buf * UNIT_N, a_lo, b_lo0 + ((((uint32_t)b * KL + (uint32_t)u * UNIT_N) * 128u) >> 4),
-                                 b != 0 ? 1u : 0u);
+                    issue_block4<CTA2>(tmem_base + buf * UNIT_N, a_lo, b_lo0 + ((((uint32_t)b * KLB + (uint32_t)u * UROWS) * 128u) >> 4),
+                                       b != 0 ? 1u : 0u);
                     if (b == DB - 1) {           // the misc rows of this tile were written before the last block's AF arrival
-                        issue_misc(tmem_base + buf * UNIT_N, am_lo, bm_lo0 + (((uint32_t)u * UNIT_N * 32u) >> 4));
-                        commit_elected<false>(bar(WB_TF + buf));
+                        issue_misc<CTA2>(tmem_base + buf * UNIT_N, am_lo, bm_lo0 + (((uint32_t)u * UROWS * 32u) >> 4));
+                        commit_elected<CTA2>(bar(WB_TF + buf));
                     }
                 }
-                commit_elected<false>(bar(WB_AE + sa));          // also covers every earlier MMA (the misc rows of older tiles)
+                commit_elected<CTA2>(bar(WB_AE + sa));           // also covers every earlier MMA (the misc rows of older tiles)
             }
         }
     } else if (warp > W_MMA) {
@@ -388,7 +427,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tcw(const __grid_constant__ W
                 }
                 fence_async_smem();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar(WB_AF + sa));
+                if (lane == 0) arrive_mma_side(WB_AF + sa);
             }
         }
     } else if (warp < W_OUT || helper) {
@@ -414,7 +453,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tcw(const __grid_constant__ W
                 scan_buffer<0, DBG>(lane_base + buf * UNIT_N, rA, rB, dbg ? dbg + g * UNIT_N : nullptr);
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar(WB_TE + buf));
+                if (lane == 0) arrive_mma_side(WB_TE + buf);
             }
             if (U == 4 && !helper) {   // second unit (codes 128*(g+2) ..)
                 const uint32_t uc = it * 4u + (uint32_t)g + 2u, buf = uc % NBUF, pht = (uc / NBUF) & 1u;
@@ -423,7 +462,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tcw(const __grid_constant__ W
                 scan_buffer<4, DBG>(lane_base + buf * UNIT_N, rA, rB, dbg ? dbg + (g + 2) * UNIT_N - 4 * 32 : nullptr);
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar(WB_TE + buf));
+                if (lane == 0) arrive_mma_side(WB_TE + buf);
             }
             float m1, m2;
             int k1;
@@ -550,7 +589,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tcw(const __grid_constant__ W
 
     tc_fence_before();
     __syncthreads();
-    if (warp == W_MMA) tmem_dealloc(tmem_base, 512);
+    if (CTA2) cluster_sync_all();                 // nobody leaves while the pair still reads its smem / arrives on its barriers
+    if (warp == W_MMA) { if (CTA2) tmem_dealloc2(tmem_base, 512); else tmem_dealloc(tmem_base, 512); }
 }
 
 }  // namespace tcw
@@ -559,7 +599,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tcw(const __grid_constant__ W
 // host side
 // ---------------------------------------------------------------------------------------------------
 // codes per launch: the bf16 operand image of a launch is 128 KB of shared memory
-inline int tcw_slice(int dim, int n_embed) { return (dim == 128 && n_embed >= 512) ? 512 : 256; }   // 2 or 4 units of 128 codes
+// CTA-pair variant (VQB200_TCW_CTA2, default on): D = 256, K = 512 -- the deep fork's quantizers (vqvae_deep.py:252,257) -- keeps
+// all 512 codes resident over a pair of SMs (128 KB of image per CTA) and runs ONE pass over x instead of two
+inline bool tcw_pair(int dim, int n_embed) {
+    static const bool on = [] { const char* e = getenv("VQB200_TCW_CTA2"); return e ? atoi(e) != 0 : true; }();
+    return on && dim == 256 && n_embed == 512;
+}
+inline int tcw_slice(int dim, int n_embed) {                  // codes per launch: 2 or 4 units of 128 codes
+    return ((dim == 128 && n_embed >= 512) || tcw_pair(dim, n_embed)) ? 512 : 256;
+}
 inline bool tcw_shape_ok(int dim, int n_embed) {
     if (dim != 128 && dim != 256) return false;
     if (n_embed < 256 || n_embed > 16384) return false;
@@ -588,11 +636,11 @@ inline int tcw_encode_tmap(CUtensorMap* tm, const float* x, int64_t n_rows, int 
                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS;
 }
 
-template <int DB, int XS, bool DBG, bool PRE>
+template <int DB, int XS, bool DBG, bool PRE, bool CTA2 = false>
 inline int tcw_launch(const tcw::WParams& prm, cudaStream_t st) {
-    auto kern = tcw::k_vq_tcw<DB, XS, DBG, PRE>;
+    auto kern = tcw::k_vq_tcw<DB, XS, DBG, PRE, CTA2>;
     const tcw::Plan P{prm.KL, DB, PRE ? 0 : XS, PRE ? tcw::as_pre(DB) : tcw::AS_CONV, tcw::n_partials(PRE, DB), tcw::n_part_slots(PRE, DB),
-                       tcw::enorm_in_smem(PRE, DB) ? 1 : 0};
+                       tcw::enorm_in_smem(PRE, DB) ? 1 : 0, CTA2 ? 2 : 1};
     const int smem = (int)P.total();
     // opt-in shared-memory size is a per-device function attribute: cache it per device (several GPUs in one process)
     static std::atomic<int> configured_dev[64];          // (atomic: several host threads / GPUs per process)
@@ -606,7 +654,24 @@ inline int tcw_launch(const tcw::WParams& prm, cudaStream_t st) {
         }
         configured = smem;
     }
-    const cudaError_t e = launch_pdl(kern, dim3((unsigned)tc_grid(prm.n_rows, false)), dim3(tc::THREADS), (size_t)smem, st, prm);
+    cudaError_t e;
+    if (!CTA2) {
+        e = launch_pdl(kern, dim3((unsigned)tc_grid(prm.n_rows, false)), dim3(tc::THREADS), (size_t)smem, st, prm);
+    } else {                                     // clusters of two CTAs (one SM pair each), programmatic dependent launch as everywhere
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)tc_grid(prm.n_rows, true));
+        cfg.blockDim = dim3(tc::THREADS);
+        cfg.dynamicSmemBytes = (size_t)smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 2;
+        e = cudaLaunchKernelEx(&cfg, kern, prm);
+    }
     if (e != cudaSuccess) fprintf(stderr, "vqb200: wide tensor-core kernel launch failed: %s (smem %d)\n", cudaGetErrorString(e), smem);
     return e != cudaSuccess;
 }
@@ -680,6 +745,8 @@ inline int tcw_forward(const float* x, const RowLayout& L, int dim, int n_embed,
             } else if (DB == 2) {
                 if (KL == 512) rc = dbg_scores ? tcw_launch<2, 2, true, false>(prm, st) : tcw_launch<2, 2, false, false>(prm, st);
                 else rc = dbg_scores ? tcw_launch<2, 4, true, false>(prm, st) : tcw_launch<2, 4, false, false>(prm, st);
+            } else if (KL == 512) {              // D = 256, all 512 codes resident over a CTA pair
+                rc = dbg_scores ? tcw_launch<4, 2, true, false, true>(prm, st) : tcw_launch<4, 2, false, false, true>(prm, st);
             } else {
                 rc = dbg_scores ? tcw_launch<4, 2, true, false>(prm, st) : tcw_launch<4, 2, false, false>(prm, st);
             }
