@@ -111,7 +111,7 @@ def test_cfg4_inference_b1024_vs_reference(ref, kind):
 
 
 # --------------------------------------------------------------------------------------------- cfg-5
-@pytest.mark.parametrize("D,K", [(64, 8192), (128, 8192), (256, 8192), (64, 2048), (128, 1024), (256, 512), (64, 4096)])
+@pytest.mark.parametrize("D,K", [(64, 8192), (128, 8192), (256, 8192), (64, 2048), (128, 1024), (256, 512), (256, 1024), (64, 4096)])
 def test_cfg5_sweep_points_vs_chunked_reference(ref, D, K):
     """Codebook sweep at N = 524 288 (B = 128, 64x64): train step 0 on half clustered / half N(0,1) rows (near-ties and the
     exact fix-up), train step 1 on the collapsed codebook, against the row-chunked reference.  Covers the K/512-slice

@@ -10,7 +10,7 @@ sys.path.insert(0, ".")
 import vq_vae_2_pytorch_b200 as vq  # noqa: E402
 
 dev = "cuda:0"
-for D, K in ((256, 512),):
+for D, K in [tuple(int(v) for v in a.split('x')) for a in (sys.argv[1:] or ['256x512', '256x1024', '256x2048', '256x8192'])]:
     N = 524288
     torch.manual_seed(0)
     q = vq.Quantize(D, K).to(dev)
@@ -20,7 +20,7 @@ for D, K in ((256, 512),):
         xs.append((q.embed.t()[pick] + 0.1 * torch.randn(N, D, device=dev)).contiguous())
     q.cluster_size.data.fill_(N / K); q.embed_avg.data.copy_(q.embed * (N / K))
 
-    def timed(fn, iters=20):
+    def timed(fn, iters=10):
         for i in range(3):
             fn(i)
         torch.cuda.synchronize()

@@ -152,7 +152,7 @@ struct WParams {
 };
 
 enum WBar { WB_B = 0, WB_XF = 1, WB_XE = 5, WB_AF = 9, WB_AE = 13, WB_TF = 17, WB_TE = 21, WB_RF = 25, WB_RE = 27, WB_PF = 29,
-            WB_PE = 31, WB_PB = 33, WB_COUNT = 34 };
+            WB_PE = 31, WB_PB = 33, WB_AFP = 34, WB_COUNT = 38 };
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar, uint64_t policy) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
@@ -198,7 +198,6 @@ __device__ __forceinline__ void issue_misc(uint32_t d_tmem, uint32_t am_lo, uint
 // operand image -- KL = 512 codes stay resident at D = 256 (128 KB per CTA), i.e. ONE pass over x instead of two.
 template <int DB, int XS, bool DBG, bool PRE, bool CTA2 = false>
 __global__ void __launch_bounds__(THREADS, 1) k_vq_tcw(const __grid_constant__ WParams p) {
-    static_assert(!(CTA2 && PRE), "the CTA-pair variant converts in the kernel");
     constexpr int D = 64 * DB;
     constexpr int AS = PRE ? as_pre(DB) : AS_CONV;
     constexpr int NP = n_partials(PRE, DB), NSLOT = n_part_slots(PRE, DB);
@@ -240,6 +239,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tcw(const __grid_constant__ W
     if (threadIdx.x == 0) {
         mbar_init(bar(WB_B), 1);
         mbar_init(bar(WB_PB), 1);
+        for (int s = 0; s < AS; ++s) mbar_init(bar(WB_AFP + s), 2);      // streamed pair: one relay arrival per CTA (below)
         for (int s = 0; s < XS; ++s) { mbar_init(bar(WB_XF + s), 1); mbar_init(bar(WB_XE + s), 4); }
         for (int s = 0; s < AS; ++s) { mbar_init(bar(WB_AF + s), PRE ? 1 : PAIR_WARPS); mbar_init(bar(WB_AE + s), 1); }
         for (int s = 0; s < NBUF; ++s) { mbar_init(bar(WB_TF + s), 1); mbar_init(bar(WB_TE + s), PAIR_WARPS); }
@@ -327,24 +327,24 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tcw(const __grid_constant__ W
                 // is one unit scan + one unit of MMAs instead of the scans of a whole tile).
                 for (int b = 0; b < DB; ++b) {
                     const uint32_t g = it * DB + b;
-                    mbar_wait(bar(WB_AF + g % AS), (g / AS) & 1u);
+                    if (CTA2) mbar_wait_cluster(bar(WB_AFP + g % AS), (g / AS) & 1u); else mbar_wait(bar(WB_AF + g % AS), (g / AS) & 1u);
                 }
                 tc_fence_after();
                 for (int u = 0; u < U; ++u) {
                     const uint32_t uc = it * (uint32_t)U + (uint32_t)u, buf = uc % NBUF, pht = (uc / NBUF) & 1u;
-                    mbar_wait(bar(WB_TE + buf), pht ^ 1u);
+                    if (CTA2) mbar_wait_cluster(bar(WB_TE + buf), pht ^ 1u); else mbar_wait(bar(WB_TE + buf), pht ^ 1u);
                     tc_fence_after();
                     for (int b = 0; b < DB; ++b)
-                        issue_block4(tmem_base + buf * UNIT_N, desc_lo(sA + ((it * DB + b) % AS) * A_STAGE),
-                                     b_lo0 + ((((uint32_t)b * KL + (uint32_t)u * UNIT_N) * 128u) >> 4), b != 0 ? 1u : 0u);
-                    issue_misc(tmem_base + buf * UNIT_N, am_lo, bm_lo0 + (((uint32_t)u * UNIT_N * 32u) >> 4));
-                    commit_elected<false>(bar(WB_TF + buf));
+                        issue_block4<CTA2>(tmem_base + buf * UNIT_N, desc_lo(sA + ((it * DB + b) % AS) * A_STAGE),
+                                           b_lo0 + ((((uint32_t)b * KLB + (uint32_t)u * UROWS) * 128u) >> 4), b != 0 ? 1u : 0u);
+                    issue_misc<CTA2>(tmem_base + buf * UNIT_N, am_lo, bm_lo0 + (((uint32_t)u * UROWS * 32u) >> 4));
+                    commit_elected<CTA2>(bar(WB_TF + buf));
                 }
-                for (int b = 0; b < DB; ++b) commit_elected<false>(bar(WB_AE + (it * DB + b) % AS));
+                for (int b = 0; b < DB; ++b) commit_elected<CTA2>(bar(WB_AE + (it * DB + b) % AS));
             } else
             for (int b = 0; b < DB; ++b) {
                 const uint32_t g = it * DB + b, sa = g % AS, pha = (g / AS) & 1u;
-                if (CTA2) mbar_wait_cluster(bar(WB_AF + sa), pha); else mbar_wait(bar(WB_AF + sa), pha);
+                if (CTA2) mbar_wait_cluster(bar((PRE ? WB_AFP : WB_AF) + sa), pha); else mbar_wait(bar(WB_AF + sa), pha);
                 tc_fence_after();
                 const uint32_t a_lo = desc_lo(sA + sa * A_STAGE);
                 for (int u = 0; u < U; ++u) {
@@ -371,6 +371,19 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tcw(const __grid_constant__ W
         const int cw = warp - W_CONV;            // rows h*64 + cw*16 .. +15 of both halves h of a block
         const int half = lane >> 4, q4 = lane & 15;
         const uint32_t conv_iter = PRE ? 0u : n_iter;             // PRE: nothing to convert
+        if constexpr (PRE && CTA2) {
+            // streamed pair: the A stages are filled by each CTA's own bulk copies (local transaction barrier); the first idle
+            // converter warp relays "my stage s has landed" to the leader's barrier the MMA issuer waits on
+            if (cw == 0) {
+                for (uint32_t it = 0; it < n_iter; ++it)
+                    for (int b = 0; b < DB; ++b) {
+                        const uint32_t g = it * DB + b, sa = g % AS, pha = (g / AS) & 1u;
+                        mbar_wait(bar(WB_AF + sa), pha);
+                        if (lane == 0) arrive_mma_side(WB_AFP + sa);
+                        __syncwarp();
+                    }
+            }
+        }
         // row (within the tile) handled in trip gi (0..3: half gi >> 1), slot u, by this half-warp
         auto row_of = [&](int gi, int u) { return (gi >> 1) * 64 + cw * 16 + 2 * (4 * (gi & 1) + u) + half; };
         for (uint32_t it = 0; it != conv_iter; ++it) {
@@ -601,9 +614,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tcw(const __grid_constant__ W
 // codes per launch: the bf16 operand image of a launch is 128 KB of shared memory
 // CTA-pair variant (VQB200_TCW_CTA2, default on): D = 256, K = 512 -- the deep fork's quantizers (vqvae_deep.py:252,257) -- keeps
 // all 512 codes resident over a pair of SMs (128 KB of image per CTA) and runs ONE pass over x instead of two
+// (larger codebooks at D = 256: 512-code pair passes -- K = 1024 as two converting passes instead of four streamed 256-code
+//  passes, K >= 2048 as streamed pair passes: half as many passes and half the operand-image reads per MMA and SM)
 inline bool tcw_pair(int dim, int n_embed) {
     static const bool on = [] { const char* e = getenv("VQB200_TCW_CTA2"); return e ? atoi(e) != 0 : true; }();
-    return on && dim == 256 && n_embed == 512;
+    static const int kmax = [] { const char* e = getenv("VQB200_TCW_CTA2_KMAX"); return e ? atoi(e) : 16384; }();
+    // D = 128 streamed passes as pairs: built, parity-green and measured -- no gain (K = 2048: 377 vs 375 us, K = 8192: 1150 vs
+    // 1164 us; those passes are bound by the scan, not by operand reads), so it stays opt-in
+    static const bool d128 = [] { const char* e = getenv("VQB200_TCW_CTA2_D128"); return e ? atoi(e) != 0 : false; }();
+    if (on && d128 && dim == 128 && n_embed % 512 == 0 && n_embed / 512 > 2) return true;     // streamed passes (K >= 2048)
+    return on && dim == 256 && n_embed % 512 == 0 && n_embed <= kmax;
 }
 inline int tcw_slice(int dim, int n_embed) {                  // codes per launch: 2 or 4 units of 128 codes
     return ((dim == 128 && n_embed >= 512) || tcw_pair(dim, n_embed)) ? 512 : 256;
@@ -740,7 +760,9 @@ inline int tcw_forward(const float* x, const RowLayout& L, int dim, int n_embed,
             prm.norms = pre ? sc.wide_norm + (size_t)t0 * tc::TILE_M : nullptr;
             int rc;
             if (pre) {
-                if (DB == 2) rc = dbg_scores ? tcw_launch<2, 1, true, true>(prm, st) : tcw_launch<2, 1, false, true>(prm, st);
+                if (DB == 2 && tcw_pair(dim, n_embed)) rc = dbg_scores ? tcw_launch<2, 1, true, true, true>(prm, st) : tcw_launch<2, 1, false, true, true>(prm, st);
+                else if (DB == 2) rc = dbg_scores ? tcw_launch<2, 1, true, true>(prm, st) : tcw_launch<2, 1, false, true>(prm, st);
+                else if (KL == 512) rc = dbg_scores ? tcw_launch<4, 1, true, true, true>(prm, st) : tcw_launch<4, 1, false, true, true>(prm, st);
                 else rc = dbg_scores ? tcw_launch<4, 1, true, true>(prm, st) : tcw_launch<4, 1, false, true>(prm, st);
             } else if (DB == 2) {
                 if (KL == 512) rc = dbg_scores ? tcw_launch<2, 2, true, false>(prm, st) : tcw_launch<2, 2, false, false>(prm, st);
