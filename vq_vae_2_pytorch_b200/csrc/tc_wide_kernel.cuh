@@ -765,6 +765,8 @@ inline int tcw_forward(const float* x, const RowLayout& L, int dim, int n_embed,
                 else if (KL == 512) rc = dbg_scores ? tcw_launch<4, 1, true, true, true>(prm, st) : tcw_launch<4, 1, false, true, true>(prm, st);
                 else rc = dbg_scores ? tcw_launch<4, 1, true, true>(prm, st) : tcw_launch<4, 1, false, true>(prm, st);
             } else if (DB == 2) {
+                // (D = 128 converting passes as CTA pairs with four x stages instead of two were measured: assign 123 -> 120 us, eval
+                //  forward 142 -> 157 us, training step 223 -> 230 us at K = 512 -- the converters, not the x loads, bound them: not kept)
                 if (KL == 512) rc = dbg_scores ? tcw_launch<2, 2, true, false>(prm, st) : tcw_launch<2, 2, false, false>(prm, st);
                 else rc = dbg_scores ? tcw_launch<2, 4, true, false>(prm, st) : tcw_launch<2, 4, false, false>(prm, st);
             } else if (KL == 512) {              // D = 256, all 512 codes resident over a CTA pair
