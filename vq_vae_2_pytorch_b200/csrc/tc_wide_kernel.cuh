@@ -616,8 +616,28 @@ __global__ void __launch_bounds__(THREADS, 1) k_vq_tcw(const __grid_constant__ W
 // all 512 codes resident over a pair of SMs (128 KB of image per CTA) and runs ONE pass over x instead of two
 // (larger codebooks at D = 256: 512-code pair passes -- K = 1024 as two converting passes instead of four streamed 256-code
 //  passes, K >= 2048 as streamed pair passes: half as many passes and half the operand-image reads per MMA and SM)
+inline bool tcw_pair_available() {
+    // one probe per process: can a cluster of two CTAs of the pair kernel (its full shared-memory footprint) be co-scheduled here?
+    // (an SM partition without whole SM pairs, or a driver without cluster launch, keeps the single-CTA passes)
+    static const bool ok = [] {
+        auto kern = tcw::k_vq_tcw<4, 2, false, false, true>;
+        const tcw::Plan P{512, 4, 2, tcw::AS_CONV, tcw::n_partials(false, 4), tcw::n_part_slots(false, 4), tcw::enorm_in_smem(false, 4) ? 1 : 0, 2};
+        const int smem = (int)P.total();
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(2); cfg.blockDim = dim3(tc::THREADS); cfg.dynamicSmemBytes = (size_t)smem;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+        return n > 0;
+    }();
+    return ok;
+}
 inline bool tcw_pair(int dim, int n_embed) {
-    static const bool on = [] { const char* e = getenv("VQB200_TCW_CTA2"); return e ? atoi(e) != 0 : true; }();
+    static const bool on = [] { const char* e = getenv("VQB200_TCW_CTA2"); return e ? atoi(e) != 0 : true; }() && tcw_pair_available();
     static const int kmax = [] { const char* e = getenv("VQB200_TCW_CTA2_KMAX"); return e ? atoi(e) : 16384; }();
     // D = 128 streamed passes as pairs: built, parity-green and measured -- no gain (K = 2048: 377 vs 375 us, K = 8192: 1150 vs
     // 1164 us; those passes are bound by the scan, not by operand reads), so it stays opt-in
