@@ -99,6 +99,8 @@ def _row_layout(shape, stride):
 def _non_overlapping_and_dense(x: torch.Tensor) -> bool:
     """True when x's elements tile one gap-free block of memory in SOME dimension order (then torch's element-wise ops,
     and vqvae.py:73 with them, return a tensor with exactly x's strides)."""
+    if x.is_contiguous():                    # (the common case, one C++ call)
+        return True
     dims = sorted((st, n) for n, st in zip(x.shape, x.stride()) if n != 1)
     expect = 1
     for st, n in dims:
@@ -325,9 +327,10 @@ class Quantize(nn.Module):
             raise RuntimeError("Quantize: module buffers must be float32 on the input's device")
 
     # ------------------------------------------------------------------ forward
-    def _run_forward(self, x, keep_image=False, want_quantize=True):
+    def _run_forward(self, x, keep_image=False, want_quantize=True, lay=None):
         lib = _native.load()
-        lay = row_layout(x)
+        if lay is None:
+            lay = row_layout(x)
         if lay is None:
             raise RuntimeError("Quantize: unsupported input strides (internal: forward() copies such inputs)")
         n, rpi, img, row, col = lay
@@ -413,13 +416,14 @@ class Quantize(nn.Module):
             # strided slices, expanded views: vqvae.py:73 (`input + (...)`) returns a DENSE tensor in the input's dimension
             # order -- exactly what clone(preserve_format) allocates; the kernels then work on / return that layout
             input = input.clone(memory_format=torch.preserve_format)
-        if row_layout(input) is None:         # dense, but in a dimension order the kernels do not address: one explicit
+        lay = row_layout(input)
+        if lay is None:                       # dense, but in a dimension order the kernels do not address: one explicit
             out_like = input                  # copy, like reshape() in vqvae.py:43, and the result goes back to that order
             input = input.contiguous()
         if input.requires_grad and torch.is_grad_enabled():
             quantize, diff, embed_ind = _QuantizeFunction.apply(input, self)
         else:
-            quantize, diff, embed_ind, _, _ = self._run_forward(input)
+            quantize, diff, embed_ind, _, _ = self._run_forward(input, lay=lay)
         if out_like is not None:
             quantize = torch.empty_like(out_like).copy_(quantize)
         return quantize, diff, embed_ind
