@@ -640,7 +640,8 @@ inline bool tcw_pair(int dim, int n_embed) {
     static const bool on = [] { const char* e = getenv("VQB200_TCW_CTA2"); return e ? atoi(e) != 0 : true; }() && tcw_pair_available();
     static const int kmax = [] { const char* e = getenv("VQB200_TCW_CTA2_KMAX"); return e ? atoi(e) : 16384; }();
     // D = 128 streamed passes as pairs: built, parity-green and measured -- no gain (K = 2048: 377 vs 375 us, K = 8192: 1150 vs
-    // 1164 us; those passes are bound by the scan, not by operand reads), so it stays opt-in
+    // 1164 us; those passes are bound by the scan, not by operand reads; eight A stages in the freed shared memory instead of
+    // four did not help either: 1193 vs 1167 us), so it stays opt-in
     static const bool d128 = [] { const char* e = getenv("VQB200_TCW_CTA2_D128"); return e ? atoi(e) != 0 : false; }();
     if (on && d128 && dim == 128 && n_embed % 512 == 0 && n_embed / 512 > 2) return true;     // streamed passes (K >= 2048)
     return on && dim == 256 && n_embed % 512 == 0 && n_embed <= kmax;
