@@ -45,7 +45,8 @@ extern "C" {
 
 /* assignment engines for vqb200_quantize_forward / vqb200_assign */
 /* tcgen05 coverage: dim 64 with n_embed 256 / 512 / k*512 <= 16384 (dense or NCHW-physical rows), and the wide engine
- * for dim 128 (n_embed 256 or k*512) and dim 256 (n_embed k*256), n_embed <= 16384, dense rows (vqvae_deep.py:252,257). */
+ * for dim 128 (n_embed 256 or k*512) and dim 256 (n_embed k*256), n_embed <= 16384, dense rows (vqvae_deep.py:252,257).
+ * At dim 256 with n_embed k*512 the wide engine runs as CTA pairs (tcgen05.mma.cta_group::2): 512 codes per pass.           */
 #define VQB200_ENGINE_AUTO    0   /* tcgen05 path when the shape is covered, else exact SIMT        */
 #define VQB200_ENGINE_SIMT    1   /* exact fp32 SIMT distance kernel                                */
 #define VQB200_ENGINE_TCGEN05 2   /* TMA + tcgen05 split-bf16 filter with exact fp32 re-score       */
